@@ -1,0 +1,207 @@
+/* mtam.h -- C-ABI of libmtam_b200.so, the sm_100a implementation of MTAMRecommender's
+ * training / scoring hot path.
+ *
+ * The reference (TensorFlow 1.14, pure Python) has no FFI of its own: the only seam is
+ * `tf.Session.run(fetches, feed_dict)` under the Python classes in Embedding/ and Model/.  Each
+ * entry point below names the reference call site (file:line under /root/reference) whose device
+ * work it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / C++ types.
+ *  - every function returns 0 on success or a negative mtam_status; `mtam_last_error()` gives text.
+ *  - all data pointers are DEVICE pointers owned by the caller unless the name says `host`.
+ *    The library allocates nothing on the device: parameters, gradients, Adam slots and the
+ *    workspace are arenas the caller allocates (sizes from `mtam_plan`) and hands over.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync inside
+ *    unless stated.  A handle is not thread-safe.
+ *  - floats are fp32, indices int32, exactly as the reference's placeholders
+ *    (Embedding/Behavior_embedding_time_aware_attention.py:21-46).
+ */
+#ifndef MTAM_H_
+#define MTAM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTAM_ABI_VERSION 1
+
+typedef enum {
+  MTAM_OK = 0,
+  MTAM_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  MTAM_ERR_CUDA = -2,        /* CUDA runtime error (text in mtam_last_error) */
+  MTAM_ERR_WORKSPACE = -3,   /* workspace too small */
+  MTAM_ERR_UNSUPPORTED = -4  /* model kind / feature not built */
+} mtam_status;
+
+/* train_process.py:164-218 experiment_type dispatch */
+typedef enum {
+  MTAM_KIND_MTAM = 0,       /* 'MTAM'                              Model/MTAMRec_model.py:61-92 */
+  MTAM_KIND_PISTREC = 1,    /* Time_Aware_self_Attention_model     Model/PISTRec_model.py:38-74 */
+  MTAM_KIND_SASREC = 2,     /* 'SASrec'                            Model/attention_baseline_models.py:33-46 */
+  MTAM_KIND_TA_SASREC = 3,  /* 'Time_Aware_Self_Attention_Model'   Model/attention_baseline_models.py:47-65 */
+  MTAM_KIND_TISASREC = 4,   /* 'Ti_Self_Attention_Model'           Model/attention_baseline_models.py:66-84 */
+  MTAM_KIND_BPRMF = 5       /* 'bpr'                               Model/BPRMF.py:10-59 */
+} mtam_kind;
+
+/* How the dense contractions are computed. */
+typedef enum {
+  MTAM_GEMM_FP32 = 0,       /* fp32 FFMA everywhere (tightest parity) */
+  MTAM_GEMM_TF32X3 = 1      /* tcgen05 kind::tf32, 3-term error-compensated split (fp32-class accuracy) */
+} mtam_gemm_mode;
+
+typedef struct {
+  int32_t abi_version;      /* MTAM_ABI_VERSION */
+  int32_t kind;             /* mtam_kind */
+  int32_t max_batch;        /* largest B any call will pass */
+  int32_t L;                /* FLAGS.length_of_user_history  (config/model_parameter.py:49) */
+  int32_t D;                /* FLAGS.num_units   (:14)  64 or 128 */
+  int32_t H;                /* FLAGS.num_heads   (:13) */
+  int32_t N;                /* FLAGS.num_blocks  (:12) */
+  int32_t user_rows;        /* user_count + 3      (Behavior_...py:64) */
+  int32_t item_rows;        /* item_count + 3      (:71) */
+  int32_t category_rows;    /* category_count + 3  (:78) */
+  int32_t position_rows;    /* max_length_seq + 3  (:86) */
+  float reg;                /* FLAGS.regulation_rate  (base_model.py:309) */
+  float clip;               /* FLAGS.max_gradient_norm (base_model.py:294) */
+  float beta1, beta2, eps;  /* tf.train.AdamOptimizer defaults (base_model.py:76) */
+  int32_t gemm_mode;        /* mtam_gemm_mode */
+  int32_t reserved[7];
+} mtam_config;
+
+typedef struct {
+  uint64_t param_floats;    /* length (floats) of each of the four arenas: params, grads, adam m, adam v */
+  uint64_t workspace_bytes; /* scratch for max_batch */
+} mtam_sizes;
+
+/* The 11 feed arrays of init_placeholders (Behavior_...py:21-46), as device pointers. */
+typedef struct {
+  int32_t B;
+  const int32_t* user_id;            /* [B]   */
+  const int32_t* item_list;          /* [B,L] */
+  const int32_t* category_list;      /* [B,L] */
+  const int32_t* position_list;      /* [B,L] */
+  const float* time_list;            /* [B,L] */
+  const float* timelast_list;        /* [B,L] */
+  const float* timenow_list;         /* [B,L]  (sliced but unused by the live graph) */
+  const int32_t* target_item_id;     /* [B]   */
+  const int32_t* target_item_category; /* [B] (unused by the live graph) */
+  const float* target_item_time;     /* [B]   */
+  const int32_t* seq_length;         /* [B]   */
+} mtam_batch;
+
+#define MTAM_NAME_MAX 160
+#define MTAM_PARAM_DEAD 1    /* created by the reference but never reached by tf.gradients */
+#define MTAM_PARAM_TABLE 2   /* embedding table (sparse + dense gradient pieces) */
+
+typedef struct {
+  char name[MTAM_NAME_MAX];  /* reference-compatible variable name */
+  int32_t rows, cols;        /* logical shape (1-D variables: rows = 1) */
+  int32_t ndim;              /* 1 or 2 */
+  int32_t ld;                /* row stride in floats inside the arena (>= cols) */
+  uint64_t offset;           /* first element, in floats, from the arena base */
+  int32_t flags;
+} mtam_param_info;
+
+/* Scalars a train / forward call writes to `scalars_out` (device float[8]). */
+enum {
+  MTAM_S_LOSS = 0,         /* self.loss          base_model.py:322 */
+  MTAM_S_LOSS_ORIGIN = 1,  /* mean(loss_origin)  :323 */
+  MTAM_S_L2_NORM = 2,      /* l2_norm            :302-307 */
+  MTAM_S_GLOBAL_NORM = 3,  /* tf.clip_by_global_norm's norm  :294 */
+  MTAM_S_CLIP_SCALE = 4,
+  MTAM_S_COUNT = 8
+};
+
+typedef struct mtam_model* mtam_handle;
+
+/* ---- stand-alone bandwidth kernels (callable without a model) ----------------------------- */
+
+/* out[i,:] = table[idx[i],:]   -- tf.nn.embedding_lookup, Behavior_...py:68,75,82,90.
+ * D must be a multiple of 4; table/out 16-byte aligned.  Bit-exact copy. */
+int mtam_gather(const float* table, int32_t table_rows, int32_t D, const int32_t* idx, int64_t n,
+                float* out, void* stream);
+
+/* Bytes of scratch mtam_scatter_add needs for n indices into a table of `table_rows` rows. */
+size_t mtam_scatter_add_workspace(int64_t n, int32_t table_rows, int32_t D);
+
+/* dst[idx[i],:] += rows[i,:]  for i in [0,n)  -- the gradient of tf.nn.embedding_lookup
+ * (tf.gradients -> IndexedSlices -> unsorted_segment_sum, base_model.py:292,296).
+ * Deterministic: stable radix sort of (idx, i) then a segmented reduction that adds the rows of
+ * one index in ascending i, then one add into dst per distinct index.  If `unique_idx`/`n_unique`
+ * are non-null they receive the distinct indices (ascending) and their count (device). */
+int mtam_scatter_add(float* dst, int32_t table_rows, int32_t D, const int32_t* idx, const float* rows,
+                     int64_t n, void* workspace, size_t workspace_bytes, int32_t* unique_idx,
+                     int32_t* n_unique, void* stream);
+
+/* ---- model --------------------------------------------------------------------------------- */
+
+int mtam_plan(const mtam_config* cfg, mtam_sizes* out);
+
+/* Arenas are param_floats long each; the library keeps the pointers, the caller keeps ownership. */
+int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam_m, float* adam_v,
+                void* workspace, size_t workspace_bytes, mtam_handle* out);
+int mtam_destroy(mtam_handle h);
+const char* mtam_last_error(mtam_handle h);   /* h may be NULL: last error of a create/plan call */
+
+/* Variable inventory: tf.trainable_variables() of the model (base_model.py:328) */
+int mtam_param_count(mtam_handle h);
+int mtam_param_info_get(mtam_handle h, int32_t i, mtam_param_info* out);
+
+/* Adam time step t (beta1_power/beta2_power state of tf.train.AdamOptimizer); 0 after create. */
+int mtam_get_adam_step(mtam_handle h, int64_t* t);
+int mtam_set_adam_step(mtam_handle h, int64_t t);
+
+/* Forward only: the graph up to self.loss / self.predict_behavior_emb (base_model.py:300-323).
+ * pred_out [B,D] and loss_origin_out [B] may be NULL. */
+int mtam_forward(mtam_handle h, const mtam_batch* batch, float* scalars_out, float* loss_origin_out,
+                 float* pred_out, void* stream);
+
+/* One `sess.run([loss, merged, train_op])` (base_model.py:150-167): forward, tf.gradients,
+ * clip_by_global_norm, Adam.apply_gradients.  lr is the float64 placeholder of base_model.py:25. */
+int mtam_train_step(mtam_handle h, const mtam_batch* batch, double lr, float* scalars_out, void* stream);
+
+/* The same step in three phases so a data-parallel driver can put its collectives between them.
+ *  1. forward_backward: local loss pieces and gradients, with the mean taken over `global_batch`
+ *     sequences.  Dense pieces land in the grads arena, the sparse embedding pieces (IndexedSlices
+ *     values) stay in the workspace.  scalars_out gets the local partial sums.
+ *     `norm_sq_sparse` (device float[1]) += sum of squares of the local un-deduplicated sparse values.
+ *  2. finish_grads: adds the sum of squares of the (already all-reduced) dense pieces to the value
+ *     in norm_sq (device float[1], pre-loaded with the all-reduced sparse part), then scatter-adds the
+ *     local sparse pieces into the grads arena (deterministic sort + segmented reduce).
+ *  3. apply: clip by sqrt(*norm_sq) and run Adam over the arenas; zeroes the grads arena rows it
+ *     dirtied. */
+int mtam_forward_backward(mtam_handle h, const mtam_batch* batch, int32_t global_batch,
+                          float* scalars_out, float* norm_sq_sparse, void* stream);
+int mtam_finish_grads(mtam_handle h, float* norm_sq, void* stream);
+int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_out, void* stream);
+
+/* Full-catalogue scoring + top-k: tf.matmul(pred, item_table^T) + tf.nn.top_k (base_model.py:194-202).
+ * Sorted descending, ties -> lower index.  idx_out [B,k] int32, score_out [B,k] (may be NULL).
+ * `row_begin`/`row_end` restrict scoring to item rows [row_begin,row_end) (a table shard); indices
+ * written are global row numbers. */
+int mtam_eval_topk(mtam_handle h, const mtam_batch* batch, int32_t k, int32_t* idx_out, float* score_out,
+                   void* stream);
+int mtam_score_topk(const float* pred, int32_t B, int32_t D, const float* item_table, int32_t row_begin,
+                    int32_t row_end, int32_t k, int32_t* idx_out, float* score_out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+size_t mtam_score_topk_workspace(int32_t B, int32_t rows, int32_t k);
+
+/* Merge per-shard top-k lists: in_idx/in_score are [n_lists,B,k] (each list sorted, shard order =
+ * index order) -> out [B,k].  Used after the all-gather of the row-sharded eval. */
+int mtam_merge_topk(const int32_t* in_idx, const float* in_score, int32_t n_lists, int32_t B, int32_t k,
+                    int32_t* out_idx, float* out_score, void* stream);
+
+/* HR@k / NDCG@k of calculate_topK (base_model.py:215-242) for k in {1,5,10,30,50} from a top-50
+ * list: out10 (device float[10]) = hr1,ndcg1,hr5,ndcg5,...,hr50,ndcg50. */
+int mtam_hr_ndcg(const int32_t* topk_idx, int32_t B, int32_t k, const int32_t* target, float* out10,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTAM_H_ */

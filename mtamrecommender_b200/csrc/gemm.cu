@@ -1,0 +1,259 @@
+// fp32 FFMA GEMM with fused epilogues (bias / ReLU / ReLU-mask / add / accumulate) and a
+// deterministic split-K path for the weight-gradient shapes (tiny M,N; K = B*L tokens).
+// This is the exact-fp32 contraction path (MTAM_GEMM_FP32); the tcgen05 path lives in tc_gemm.cu.
+//
+// Reference call sites: tf.layers.dense / tf.matmul in
+//   Embedding/Behavior_embedding_time_aware_attention.py:95-103, Model/Modules/time_aware_attention.py:249-253,
+//   Model/Modules/time_aware_rnn.py:243-256 and their tf.gradients (Model/base_model.py:292).
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/mtam.h"
+
+namespace mtam {
+
+constexpr int GM = 64, GN = 64, GK = 16, GT = 256;
+
+struct EpiDev {
+  const float* bias;
+  const float* mask_pos;
+  const float* add;
+  int ld_mask, ld_add, relu, accumulate;
+  float alpha;
+};
+
+__device__ __forceinline__ float apply_epi(float v, int m, int n, const EpiDev& e, const float* C, int ldc) {
+  v *= e.alpha;
+  if (e.bias) v += e.bias[n];
+  if (e.relu) v = fmaxf(v, 0.f);
+  if (e.mask_pos) v = (e.mask_pos[(int64_t)m * e.ld_mask + n] > 0.f) ? v : 0.f;
+  if (e.add) v += e.add[(int64_t)m * e.ld_add + n];
+  if (e.accumulate) v += C[(int64_t)m * ldc + n];
+  return v;
+}
+
+template <int TA, int TB, int VA, int VB>
+__global__ void __launch_bounds__(GT) gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                      const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                                      int ldc, EpiDev epi, int kchunk, float* __restrict__ partial) {
+  __shared__ __align__(16) float As[GK][GM + 4];
+  __shared__ __align__(16) float Bs[GK][GN + 4];
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += GK) {
+    // ---- A tile -> As[k][m]
+    if (TA == 0) {  // A[m][k], k fastest
+      int m = t >> 2, k4 = (t & 3) * 4;
+      int gm = m0 + m, gk = k0 + k4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gm < M) {
+        const float* p = A + (int64_t)gm * lda + gk;
+        if (VA && gk + 3 < kend) {
+          float4 q = *reinterpret_cast<const float4*>(p);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (gk + i < kend) v[i] = p[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[k4 + i][m] = v[i];
+    } else {  // A stored [k][m], m fastest
+      int k = t >> 4, m4 = (t & 15) * 4;
+      int gk = k0 + k, gm = m0 + m4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gk < kend) {
+        const float* p = A + (int64_t)gk * lda + gm;
+        if (VA && gm + 3 < M) {
+          float4 q = *reinterpret_cast<const float4*>(p);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (gm + i < M) v[i] = p[i];
+        }
+      }
+      *reinterpret_cast<float4*>(&As[k][m4]) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    // ---- B tile -> Bs[k][n]
+    if (TB == 0) {  // B[k][n], n fastest
+      int k = t >> 4, n4 = (t & 15) * 4;
+      int gk = k0 + k, gn = n0 + n4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gk < kend) {
+        const float* p = B + (int64_t)gk * ldb + gn;
+        if (VB && gn + 3 < N) {
+          float4 q = *reinterpret_cast<const float4*>(p);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (gn + i < N) v[i] = p[i];
+        }
+      }
+      *reinterpret_cast<float4*>(&Bs[k][n4]) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {  // B stored [n][k], k fastest
+      int n = t >> 2, k4 = (t & 3) * 4;
+      int gn = n0 + n, gk = k0 + k4;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gn < N) {
+        const float* p = B + (int64_t)gn * ldb + gk;
+        if (VB && gk + 3 < kend) {
+          float4 q = *reinterpret_cast<const float4*>(p);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (gk + i < kend) v[i] = p[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[k4 + i][n] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      if (partial)
+        partial[((int64_t)blockIdx.z * M + m) * N + n] = acc[i][j];
+      else
+        C[(int64_t)m * ldc + n] = apply_epi(acc[i][j], m, n, epi, C, ldc);
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, int M, int N, float* __restrict__ C,
+                                     int ldc, EpiDev epi) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  int m = (int)(i / N), n = (int)(i % N);
+  float s = 0.f;
+  for (int z = 0; z < S; ++z) s += partial[(int64_t)z * M * N + i];  // fixed order: deterministic
+  C[(int64_t)m * ldc + n] = apply_epi(s, m, n, epi, C, ldc);
+}
+
+static int pick_splits(int M, int N, int K) {
+  int tiles = cdiv(M, GM) * cdiv(N, GN);
+  if (tiles >= kNumSMs || K < 1024) return 1;
+  int want = cdiv(2 * kNumSMs, tiles);
+  int maxs = std::max(1, K / 256);
+  return std::max(1, std::min(want, maxs));
+}
+
+size_t gemm_splitk_workspace_bytes(int M, int N, int K) {
+  int S = pick_splits(M, N, K);
+  return S > 1 ? (size_t)S * M * N * sizeof(float) + 256 : 0;
+}
+
+int gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+             float* C, int ldc, const GemmEpilogue& e, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  EpiDev epi{e.bias, e.mask_pos, e.add, e.ld_mask, e.ld_add, e.relu, e.accumulate, e.alpha};
+  int S = pick_splits(M, N, K);
+  int kchunk = K;
+  float* partial = nullptr;
+  if (S > 1) {
+    kchunk = cdiv(cdiv(K, S), GK) * GK;
+    S = cdiv(K, kchunk);
+  }
+  if (S > 1) {
+    size_t need = (size_t)S * M * N * sizeof(float);
+    if (!ws || ws_bytes < need) return set_error(MTAM_ERR_WORKSPACE, "gemm split-K workspace %zu < %zu", ws_bytes, need);
+    partial = (float*)ws;
+  }
+  if (K <= 0) kchunk = GK;
+  bool va = ((uintptr_t)A % 16 == 0) && (lda % 4 == 0);
+  bool vb = ((uintptr_t)B % 16 == 0) && (ldb % 4 == 0);
+  // with split-K the chunk starts are multiples of GK=16 so alignment of k offsets is preserved
+  dim3 grid(cdiv(N, GN), cdiv(M, GM), S);
+#define LAUNCH(TA, TB, VA, VB) \
+  gemm_f32_kernel<TA, TB, VA, VB><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, epi, kchunk, partial)
+#define DISPATCH_V(TA, TB)                     \
+  do {                                         \
+    if (va && vb) LAUNCH(TA, TB, 1, 1);        \
+    else if (va) LAUNCH(TA, TB, 1, 0);         \
+    else if (vb) LAUNCH(TA, TB, 0, 1);         \
+    else LAUNCH(TA, TB, 0, 0);                 \
+  } while (0)
+  if (!transA && !transB) DISPATCH_V(0, 0);
+  else if (!transA && transB) DISPATCH_V(0, 1);
+  else if (transA && !transB) DISPATCH_V(1, 0);
+  else DISPATCH_V(1, 1);
+#undef DISPATCH_V
+#undef LAUNCH
+  MTAM_LAUNCH_CHECK();
+  if (S > 1) {
+    int64_t tot = (int64_t)M * N;
+    splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, st>>>(partial, S, M, N, C, ldc, epi);
+    MTAM_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---- deterministic column sums: out[n] = sum_m A[m,n] * (Bmul ? Bmul[m,n] : 1) -----------------
+constexpr int CS_ROWS = 256;  // rows per partial block
+
+__global__ void colsum_partial_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+                                      int M, int N, float* __restrict__ partial) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int m0 = blockIdx.y * CS_ROWS, m1 = min(M, m0 + CS_ROWS);
+  float s = 0.f;
+  if (Bm) {
+    for (int m = m0; m < m1; ++m) s += A[(int64_t)m * lda + n] * Bm[(int64_t)m * ldb + n];
+  } else {
+    for (int m = m0; m < m1; ++m) s += A[(int64_t)m * lda + n];
+  }
+  partial[(int64_t)blockIdx.y * N + n] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int P, int N, float* __restrict__ out,
+                                    int accumulate) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += partial[(int64_t)p * N + n];
+  out[n] = accumulate ? out[n] + s : s;
+}
+size_t colsum_workspace_bytes(int M, int N) { return (size_t)cdiv(M, CS_ROWS) * N * sizeof(float) + 256; }
+
+int colsum_f32(const float* A, int lda, const float* Bmul, int ldb, int M, int N, float* out, int accumulate,
+               void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (N <= 0) return 0;
+  int P = std::max(1, cdiv(M, CS_ROWS));
+  if (ws_bytes < (size_t)P * N * sizeof(float)) return set_error(MTAM_ERR_WORKSPACE, "colsum workspace too small");
+  dim3 grid(cdiv(N, 128), P);
+  colsum_partial_kernel<<<grid, 128, 0, st>>>(A, lda, Bmul, ldb, M, N, (float*)ws);
+  colsum_final_kernel<<<cdiv(N, 128), 128, 0, st>>>((const float*)ws, P, N, out, accumulate);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mtam

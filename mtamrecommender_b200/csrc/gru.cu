@@ -1,0 +1,302 @@
+// Time-aware GRU ("new" cell) recurrence, forward and backward, as persistent CTA-per-row-tile
+// kernels: the recurrent [D,3D] weights stay in shared memory for all L steps, the state stays
+// on chip, and the x-side products [B*L,D]x[D,3D] are hoisted out of the loop into one GEMM.
+//
+// Reference: TimeAwareGRUCell_decay_new.call  Model/Modules/time_aware_rnn.py:186-269
+//            dynamic_rnn(sequence_length = seq_len-1)  Model/Modules/gru.py:69-77, MTAMRec_model.py:68-79
+//   a  = relu(x*kw1 + kb1 + h*hw1)                 (:228)
+//   s  = relu(tw1*dt + tb1)                        (:236)
+//   T  = sigmoid(kw2*a + tw12*s + tb12)            (:237)
+//   r,u = split(sigmoid([x,h] Wg + bg))            (:243-248)
+//   c  = tanh([x, r*h] Wc + bc)                    (:250-256)
+//   h' = u*h + (1-u)*c*T                           (:268)
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "model_kernels.h"
+
+namespace mtam {
+
+constexpr int RB = 8;  // batch rows per CTA
+
+// vecs layout [8][D]: kw1, kb1, hw1, tw1, tb1, kw2, tw12, tb12   (GRU_LIVE_VECS order)
+template <int D>
+__global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict__ X, const float* __restrict__ GX,
+                                                        const float* __restrict__ timelast,
+                                                        const int32_t* __restrict__ seq_len,
+                                                        const float* __restrict__ Wgru, const float* __restrict__ vecs,
+                                                        int B, int L, float* __restrict__ Hs, float* __restrict__ RUCT,
+                                                        float* __restrict__ RH, float* __restrict__ q0) {
+  extern __shared__ __align__(16) float sm[];
+  float* Wh = sm;                   // [D][3D]  rows D..2D of W_gru (the h-side)
+  float* hT = Wh + 3 * D * D;       // [D][RB]
+  float* rhT = hT + D * RB;         // [D][RB]
+  float* uS = rhT + D * RB;         // [D][RB]
+  __shared__ int steps[RB];
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * RB;
+  for (int i = tid; i < 3 * D * D; i += 4 * D) Wh[i] = Wgru[D * 3 * D + i];
+  for (int i = tid; i < D * RB; i += 4 * D) hT[i] = 0.f;
+  if (tid < RB) steps[tid] = (b0 + tid < B) ? min(max(seq_len[b0 + tid] - 1, 0), L) : 0;
+  __syncthreads();
+  int tmax = 0;
+#pragma unroll
+  for (int r = 0; r < RB; ++r) tmax = max(tmax, steps[r]);
+
+  const int n1 = tid % (2 * D), rg1 = tid / (2 * D);  // phase 1: column of [r|u], rows rg1*4..+3
+  const int n2 = tid % D, rg2 = tid / D;              // phase 2: column of c,      rows rg2*2..+1
+  const float kw1 = vecs[0 * D + n2], kb1 = vecs[1 * D + n2], hw1 = vecs[2 * D + n2], tw1 = vecs[3 * D + n2],
+              tb1 = vecs[4 * D + n2], kw2 = vecs[5 * D + n2], tw12 = vecs[6 * D + n2], tb12 = vecs[7 * D + n2];
+
+  for (int t = 0; t < tmax; ++t) {
+    // ---- phase 1: r,u ----
+    float g1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int row = rg1 * 4 + i;
+      g1[i] = (t < steps[row]) ? __ldg(GX + ((int64_t)(b0 + row) * L + t) * (3 * D) + n1) : 0.f;
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int k = 0; k < D; ++k) {
+      float w = Wh[k * 3 * D + n1];
+      float4 h4 = *reinterpret_cast<const float4*>(&hT[k * RB + rg1 * 4]);
+      acc[0] = fmaf(h4.x, w, acc[0]); acc[1] = fmaf(h4.y, w, acc[1]);
+      acc[2] = fmaf(h4.z, w, acc[2]); acc[3] = fmaf(h4.w, w, acc[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int row = rg1 * 4 + i;
+      if (t < steps[row]) {
+        int64_t tok = (int64_t)(b0 + row) * L + t;
+        float v = sigmoidf_(acc[i] + g1[i]);
+        RUCT[tok * (4 * D) + n1] = v;  // r at [0,D), u at [D,2D)
+        if (n1 < D) {
+          float rh = v * hT[n1 * RB + row];
+          rhT[n1 * RB + row] = rh;
+          RH[tok * D + n1] = rh;
+        } else {
+          uS[(n1 - D) * RB + row] = v;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: candidate, time gate, state update ----
+    float g2[2], xv[2], dl[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int row = rg2 * 2 + i;
+      bool live = t < steps[row];
+      int64_t tok = (int64_t)(b0 + row) * L + t;
+      g2[i] = live ? __ldg(GX + tok * (3 * D) + 2 * D + n2) : 0.f;
+      xv[i] = live ? __ldg(X + tok * D + n2) : 0.f;
+      dl[i] = live ? __ldg(timelast + tok) : 0.f;
+    }
+    float acc2[2] = {0.f, 0.f};
+#pragma unroll 8
+    for (int k = 0; k < D; ++k) {
+      float w = Wh[k * 3 * D + 2 * D + n2];
+      float2 r2 = *reinterpret_cast<const float2*>(&rhT[k * RB + rg2 * 2]);
+      acc2[0] = fmaf(r2.x, w, acc2[0]);
+      acc2[1] = fmaf(r2.y, w, acc2[1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int row = rg2 * 2 + i;
+      if (t < steps[row]) {
+        int64_t tok = (int64_t)(b0 + row) * L + t;
+        float c = tanhf(acc2[i] + g2[i]);
+        float hold = hT[n2 * RB + row];
+        float a = fmaxf(fmaf(xv[i], kw1, kb1) + hold * hw1, 0.f);
+        float s = fmaxf(fmaf(tw1, dl[i], tb1), 0.f);
+        float Tg = sigmoidf_(kw2 * a + tw12 * s + tb12);
+        float u = uS[n2 * RB + row];
+        float hn = u * hold + (1.f - u) * c * Tg;
+        RUCT[tok * (4 * D) + 2 * D + n2] = c;
+        RUCT[tok * (4 * D) + 3 * D + n2] = Tg;
+        Hs[(tok + 1) * D + n2] = hn;  // Hs has one leading zero row
+        hT[n2 * RB + row] = hn;       // only this thread touches this element in phase 2
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int row = rg2 * 2 + i;
+    if (b0 + row < B) q0[(int64_t)(b0 + row) * D + n2] = hT[n2 * RB + row];
+  }
+}
+
+// Reverse-time pass.  dGX[t] = [d r_pre | d u_pre | d c_pre] (zero past length; caller memsets),
+// dX[t] += element-wise path, vec_partial[block][8][D] = per-CTA sums of the 8 vector-parameter
+// gradients.  dq0[b] is d loss / d short_term_intent (state after the last real item).
+template <int D>
+__global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
+    const float* __restrict__ X, const float* __restrict__ timelast, const int32_t* __restrict__ seq_len,
+    const float* __restrict__ Wgru, const float* __restrict__ vecs, const float* __restrict__ Hs,
+    const float* __restrict__ RUCT, const float* __restrict__ dq0, int B, int L, float* __restrict__ dGX,
+    float* __restrict__ dX, float* __restrict__ vec_partial) {
+  extern __shared__ __align__(16) float sm[];
+  float* WhT = sm;                 // [3D][D]   WhT[n][k] = W_gru[D+k][n]
+  float* dpcS = WhT + 3 * D * D;   // [D][RB]
+  float* dpgS = dpcS + D * RB;     // [2D][RB]
+  __shared__ int steps[RB];
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * RB;
+  for (int i = tid; i < 3 * D * D; i += 4 * D) {
+    int k = i / (3 * D), n = i % (3 * D);
+    WhT[n * D + k] = Wgru[D * 3 * D + i];
+  }
+  if (tid < RB) steps[tid] = (b0 + tid < B) ? min(max(seq_len[b0 + tid] - 1, 0), L) : 0;
+  __syncthreads();
+  int tmax = 0;
+#pragma unroll
+  for (int r = 0; r < RB; ++r) tmax = max(tmax, steps[r]);
+
+  const int n = tid % D, rg = tid / D;  // rows rg*2, rg*2+1
+  const float kw1 = vecs[0 * D + n], kb1 = vecs[1 * D + n], hw1 = vecs[2 * D + n], tw1 = vecs[3 * D + n],
+              tb1 = vecs[4 * D + n], kw2 = vecs[5 * D + n], tw12 = vecs[6 * D + n], tb12 = vecs[7 * D + n];
+  float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // kw1,kb1,hw1,tw1,tb1,kw2,tw12,tb12
+  float dh[2] = {0.f, 0.f};
+
+  for (int t = tmax - 1; t >= 0; --t) {
+    float dhacc[2], rr[2], hh[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int row = rg * 2 + i;
+      dhacc[i] = 0.f; rr[i] = 0.f; hh[i] = 0.f;
+      if (t < steps[row]) {
+        int64_t b = b0 + row;
+        int64_t tok = b * L + t;
+        if (t == steps[row] - 1) dh[i] += __ldg(dq0 + b * D + n);
+        const float* s4 = RUCT + tok * (4 * D);
+        float r = __ldg(s4 + n), u = __ldg(s4 + D + n), c = __ldg(s4 + 2 * D + n), Tg = __ldg(s4 + 3 * D + n);
+        float hold = __ldg(Hs + tok * D + n);  // h_{t-1}: Hs is shifted by one (leading zero row)
+        float x = __ldg(X + tok * D + n), dl = __ldg(timelast + tok);
+        float d = dh[i];
+        float du = d * (hold - c * Tg), dc = d * (1.f - u) * Tg, dT = d * (1.f - u) * c;
+        dhacc[i] = d * u;
+        float dpc = dc * (1.f - c * c);
+        dpcS[n * RB + row] = dpc;
+        dGX[tok * (3 * D) + 2 * D + n] = dpc;
+        float dpT = dT * Tg * (1.f - Tg);
+        float apre = fmaf(x, kw1, kb1) + hold * hw1, spre = fmaf(tw1, dl, tb1);
+        float a = fmaxf(apre, 0.f), s = fmaxf(spre, 0.f);
+        float dpa = (apre > 0.f) ? dpT * kw2 : 0.f;
+        float dps = (spre > 0.f) ? dpT * tw12 : 0.f;
+        dX[tok * D + n] += dpa * kw1;
+        dhacc[i] = fmaf(dpa, hw1, dhacc[i]);
+        g[0] = fmaf(dpa, x, g[0]); g[1] += dpa; g[2] = fmaf(dpa, hold, g[2]);
+        g[3] = fmaf(dps, dl, g[3]); g[4] += dps;
+        g[5] = fmaf(dpT, a, g[5]); g[6] = fmaf(dpT, s, g[6]); g[7] += dpT;
+        float dupre = du * u * (1.f - u);
+        dpgS[(D + n) * RB + row] = dupre;
+        dGX[tok * (3 * D) + D + n] = dupre;
+        rr[i] = r; hh[i] = hold;
+      } else {
+        dpcS[n * RB + row] = 0.f;
+        dpgS[(D + n) * RB + row] = 0.f;
+      }
+    }
+    __syncthreads();
+    // d(r*h)[n] = sum_m dpc[m] * Wc_h[n][m]
+    float acc[2] = {0.f, 0.f};
+#pragma unroll 8
+    for (int m = 0; m < D; ++m) {
+      float w = WhT[(2 * D + m) * D + n];
+      float2 d2 = *reinterpret_cast<const float2*>(&dpcS[m * RB + rg * 2]);
+      acc[0] = fmaf(d2.x, w, acc[0]);
+      acc[1] = fmaf(d2.y, w, acc[1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int row = rg * 2 + i;
+      float drpre = 0.f;
+      if (t < steps[row]) {
+        float drh = acc[i];
+        dhacc[i] = fmaf(drh, rr[i], dhacc[i]);
+        drpre = drh * hh[i] * rr[i] * (1.f - rr[i]);
+        dGX[((int64_t)(b0 + row) * L + t) * (3 * D) + n] = drpre;
+      }
+      dpgS[n * RB + row] = drpre;
+    }
+    __syncthreads();
+    // dh_prev[n] += sum_m dpg[m] * Wg_h[n][m],  m over 2D
+    float acc2[2] = {0.f, 0.f};
+#pragma unroll 8
+    for (int m = 0; m < 2 * D; ++m) {
+      float w = WhT[m * D + n];
+      float2 d2 = *reinterpret_cast<const float2*>(&dpgS[m * RB + rg * 2]);
+      acc2[0] = fmaf(d2.x, w, acc2[0]);
+      acc2[1] = fmaf(d2.y, w, acc2[1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (t < steps[rg * 2 + i]) dh[i] = dhacc[i] + acc2[i];
+    __syncthreads();
+  }
+  // per-CTA reduction of the vector-parameter gradients over the 4 row groups (fixed order)
+  float* red = dpgS;  // reuse: [4][8][D] floats = 32*D <= 2D*RB*... (2D*8 = 16D) -> use WhT instead
+  red = WhT;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[(rg * 8 + j) * D + n] = g[j];
+  __syncthreads();
+  if (rg == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = red[(0 * 8 + j) * D + n] + red[(1 * 8 + j) * D + n] + red[(2 * 8 + j) * D + n] +
+                red[(3 * 8 + j) * D + n];
+      vec_partial[((int64_t)blockIdx.x * 8 + j) * D + n] = s;
+    }
+  }
+}
+
+static size_t gru_smem_bytes(int D) { return (size_t)(3 * D * D + 3 * D * RB) * sizeof(float); }
+int gru_num_blocks(int B) { return cdiv(B, RB); }
+
+template <int D>
+static int gru_fwd_launch(const float* X, const float* GX, const float* timelast, const int32_t* seq_len,
+                          const float* Wgru, const float* vecs, int B, int L, float* Hs, float* RUCT, float* RH,
+                          float* q0, cudaStream_t st) {
+  size_t smem = gru_smem_bytes(D);
+  MTAM_CUDA_CHECK(cudaFuncSetAttribute(gru_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gru_fwd_kernel<D><<<gru_num_blocks(B), 4 * D, smem, st>>>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+template <int D>
+static int gru_bwd_launch(const float* X, const float* timelast, const int32_t* seq_len, const float* Wgru,
+                          const float* vecs, const float* Hs, const float* RUCT, const float* dq0, int B, int L,
+                          float* dGX, float* dX, float* vec_partial, cudaStream_t st) {
+  size_t smem = gru_smem_bytes(D);
+  MTAM_CUDA_CHECK(cudaFuncSetAttribute(gru_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gru_bwd_kernel<D><<<gru_num_blocks(B), 4 * D, smem, st>>>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, B, L, dGX,
+                                                          dX, vec_partial);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
+int gru_forward(int D, const float* X, const float* GX, const float* timelast, const int32_t* seq_len,
+                const float* Wgru, const float* vecs, int B, int L, float* Hs, float* RUCT, float* RH, float* q0,
+                cudaStream_t st) {
+  switch (D) {
+    case 32: return gru_fwd_launch<32>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, st);
+    case 64: return gru_fwd_launch<64>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, st);
+    case 128: return gru_fwd_launch<128>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, st);
+  }
+  return set_error(-1, "T-GRU: num_units=%d not supported (32, 64, 128)", D);
+}
+int gru_backward(int D, const float* X, const float* timelast, const int32_t* seq_len, const float* Wgru,
+                 const float* vecs, const float* Hs, const float* RUCT, const float* dq0, int B, int L, float* dGX,
+                 float* dX, float* vec_partial, cudaStream_t st) {
+  switch (D) {
+    case 32: return gru_bwd_launch<32>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, B, L, dGX, dX, vec_partial, st);
+    case 64: return gru_bwd_launch<64>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, B, L, dGX, dX, vec_partial, st);
+    case 128: return gru_bwd_launch<128>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, B, L, dGX, dX, vec_partial, st);
+  }
+  return set_error(-1, "T-GRU: num_units=%d not supported (32, 64, 128)", D);
+}
+
+}  // namespace mtam

@@ -1,0 +1,428 @@
+// MTAM multi-hop time-aware attentive memory read (Tq = 1), forward and backward.
+// One warp owns one sequence for all N hops: the query never leaves registers, keys/values are
+// streamed once per hop with full-line coalesced reads (lanes across D), the time gate is computed
+// in-register.  HBM/L2-bound by the K,V reads; no tensor-core reshaping.
+//
+// Reference: Time_Aware_Attention.vanilla_attention  Model/Modules/time_aware_attention.py:524-556
+//            time_aware_multihead_attention          :215-456   (math restated in SURVEY 9.4)
+//            final tf.contrib layer_norm             Model/MTAMRec_model.py:91, net_utils.py:229-232
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "model_kernels.h"
+
+namespace mtam {
+
+constexpr int HOP_WARPS = 4;
+
+template <int VPL>
+__device__ __forceinline__ void ldv(float (&r)[VPL], const float* p) {
+  if (VPL == 4) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+  } else if (VPL == 2) {
+    float2 t = *reinterpret_cast<const float2*>(p);
+    r[0] = t.x; r[1] = t.y;
+  } else {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) r[v] = p[v];
+  }
+}
+template <int VPL>
+__device__ __forceinline__ void stv(float* p, const float (&r)[VPL]) {
+  if (VPL == 4) *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
+  else if (VPL == 2) *reinterpret_cast<float2*>(p) = make_float2(r[0], r[1]);
+  else {
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) p[v] = r[v];
+  }
+}
+__device__ __forceinline__ float group_sum_rt(float v, int lanes) {
+  for (int o = lanes >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(HOP_WARPS * 32) hop_fwd_kernel(HopArgs a) {
+  constexpr int D = VPL * 32;
+  extern __shared__ __align__(16) float sm[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * HOP_WARPS + w;
+  if (b >= a.B) return;
+  const int L = a.L, H = a.H, N = a.N;
+  float* qs = sm + (size_t)w * (D + 2 * H * L);
+  float* sc = qs + D;
+  const int d0 = lane * VPL;
+  const int lph = 32 / H, head = lane / lph;
+  const float sqrt_dh = sqrtf((float)(D / H));
+  const int len = min(max(a.seq_len[b], 0), L);
+  const float tq = a.target_time[b];
+  const int ldkv = 2 * N * D;
+
+  float q[VPL];
+  ldv<VPL>(q, a.Qin + (int64_t)b * D + d0);
+  for (int i = 0; i < N; ++i) {
+    stv<VPL>(qs + d0, q);
+    __syncwarp();
+    // Q = relu(q Wq + bq), qt = q Wt   (:249, :320)
+    float Q[VPL], qt[VPL];
+    ldv<VPL>(Q, a.bq + (int64_t)i * D + d0);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) qt[v] = 0.f;
+    const float* Wq = a.Wq + (int64_t)i * D * D;
+    const float* Wt = a.Wt + (int64_t)i * D * D;
+#pragma unroll 4
+    for (int k = 0; k < D; ++k) {
+      float qk = qs[k];
+      float wq[VPL], wt[VPL];
+      ldv<VPL>(wq, Wq + k * D + d0);
+      ldv<VPL>(wt, Wt + k * D + d0);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        Q[v] = fmaf(qk, wq[v], Q[v]);
+        qt[v] = fmaf(qk, wt[v], qt[v]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) Q[v] = fmaxf(Q[v], 0.f);
+    const int64_t ib = (int64_t)i * a.B + b;
+    stv<VPL>(a.Qr + ib * D + d0, Q);
+    stv<VPL>(a.Qt + ib * D + d0, qt);
+
+    const float* w1 = a.gate + ((int64_t)i * 5 + 0) * L;
+    const float* b1 = a.gate + ((int64_t)i * 5 + 1) * L;
+    const float* o1 = a.gate + ((int64_t)i * 5 + 2) * L;
+    const float* o2 = a.gate + ((int64_t)i * 5 + 3) * L;
+    const float* ob = a.gate + ((int64_t)i * 5 + 4) * L;
+    // ---- pass 1: gated scores ----
+#pragma unroll 2
+    for (int j = 0; j < len; ++j) {
+      const int64_t tok = (int64_t)b * L + j;
+      float x[VPL], kk[VPL];
+      ldv<VPL>(x, a.X + tok * D + d0);
+      ldv<VPL>(kk, a.KV + tok * ldkv + (int64_t)i * 2 * D + d0);
+      float pz = 0.f, pa = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        pz = fmaf(qt[v], x[v], pz);
+        pa = fmaf(Q[v], kk[v], pa);
+      }
+      float z = warp_sum(pz);
+      float av = group_sum_rt(pa, lph);
+      float Z = tanhf(z);                                              // :323
+      float dlt = logf(fabsf(tq - __ldg(a.time_list + tok)) + 1.f);    // :339
+      float Dk = tanhf(fmaf(dlt, __ldg(w1 + j), __ldg(b1 + j)));       // :343
+      float G = __ldg(o1 + j) * Dk + __ldg(o2 + j) * Z + __ldg(ob + j);  // :350
+      float gate = sigmoidf_(G);
+      float s = (av * gate) / sqrt_dh;                                 // :381-384
+      if ((lane % lph) == 0) {
+        sc[head * L + j] = s;
+        a.AA[(ib * H + head) * L + j] = av;
+      }
+      if (lane == 0) {
+        a.ZZ[ib * L + j] = Z;
+        a.DK[ib * L + j] = Dk;
+        a.GT[ib * L + j] = gate;
+      }
+    }
+    __syncwarp();
+    // ---- softmax over the len valid keys (masked keys get exactly 0: exp(-2^32 - m) == 0) ----
+    for (int h = 0; h < H; ++h) {
+      float m = -INFINITY;
+      for (int j = lane; j < len; j += 32) m = fmaxf(m, sc[h * L + j]);
+      m = warp_max(m);
+      float s = 0.f;
+      for (int j = lane; j < len; j += 32) {
+        float e = expf(sc[h * L + j] - m);
+        sc[h * L + j] = e;
+        s += e;
+      }
+      s = warp_sum(s);
+      for (int j = lane; j < L; j += 32) {
+        float p = (j < len) ? sc[h * L + j] / s : 0.f;
+        sc[h * L + j] = p;
+        a.PA[(ib * H + h) * L + j] = p;
+      }
+    }
+    __syncwarp();
+    // ---- pass 2: O = P V ----
+    float O[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) O[v] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < len; ++j) {
+      const int64_t tok = (int64_t)b * L + j;
+      float vv[VPL];
+      ldv<VPL>(vv, a.KV + tok * ldkv + (int64_t)i * 2 * D + D + d0);
+      float p = sc[head * L + j];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) O[v] = fmaf(p, vv[v], O[v]);
+    }
+    // ---- residual + normalize (eps 1e-8)  :447-454, :7-34 ----
+    float y[VPL], s1 = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) { y[v] = O[v] + q[v]; s1 += y[v]; }
+    float mean = warp_sum(s1) / D;
+    float s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) { y[v] -= mean; s2 = fmaf(y[v], y[v], s2); }
+    float var = warp_sum(s2) / D;
+    float rstd = 1.f / sqrtf(var + 1e-8f);
+    float gm[VPL], bt[VPL], xh[VPL];
+    ldv<VPL>(gm, a.ln_gamma + (int64_t)i * D + d0);
+    ldv<VPL>(bt, a.ln_beta + (int64_t)i * D + d0);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) { xh[v] = y[v] * rstd; q[v] = fmaf(gm[v], xh[v], bt[v]); }
+    stv<VPL>(a.XH + ((int64_t)b * N + i) * D + d0, xh);
+    if (lane == 0) a.RSTD[(int64_t)b * N + i] = rstd;
+    stv<VPL>(a.Qin + ((int64_t)(i + 1) * a.B + b) * D + d0, q);
+    __syncwarp();
+  }
+  // ---- final tf.contrib layer_norm (eps 1e-12) ----
+  {
+    float s1 = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) s1 += q[v];
+    float mean = warp_sum(s1) / D;
+    float s2 = 0.f, y[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) { y[v] = q[v] - mean; s2 = fmaf(y[v], y[v], s2); }
+    float var = warp_sum(s2) / D;
+    float rstd = rsqrtf(var + 1e-12f);
+    float gm[VPL], bt[VPL], xh[VPL], o[VPL];
+    ldv<VPL>(gm, a.lnf_gamma + d0);
+    ldv<VPL>(bt, a.lnf_beta + d0);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) { xh[v] = y[v] * rstd; o[v] = fmaf(gm[v], xh[v], bt[v]); }
+    stv<VPL>(a.XHF + (int64_t)b * D + d0, xh);
+    if (lane == 0) a.RSTDF[b] = rstd;
+    stv<VPL>(a.pred + (int64_t)b * D + d0, o);
+  }
+}
+
+// layer-norm backward for one row held across a warp
+template <int VPL>
+__device__ __forceinline__ void ln_bwd_row(const float (&dout)[VPL], const float (&gamma)[VPL],
+                                           const float (&xh)[VPL], float rstd, int D, float (&dy)[VPL]) {
+  float dxh[VPL], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    dxh[v] = dout[v] * gamma[v];
+    s1 += dxh[v];
+    s2 = fmaf(dxh[v], xh[v], s2);
+  }
+  float m1 = warp_sum(s1) / D, m2 = warp_sum(s2) / D;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) dy[v] = (dxh[v] - m1 - xh[v] * m2) * rstd;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(HOP_WARPS * 32) hop_bwd_kernel(HopArgs a, HopGradArgs g) {
+  constexpr int D = VPL * 32;
+  extern __shared__ __align__(16) float sm[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * HOP_WARPS + w;
+  if (b >= a.B) return;
+  const int L = a.L, H = a.H, N = a.N;
+  float* qs = sm + (size_t)w * (2 * D + 2 * H * L + 32);
+  float* qs2 = qs + D;
+  float* ps = qs2 + D;      // [H][L] probabilities
+  float* dps = ps + H * L;  // [H][L] dP
+  float* dsum = dps + H * L;  // [H]
+  const int d0 = lane * VPL;
+  const int lph = 32 / H, head = lane / lph;
+  const float sqrt_dh = sqrtf((float)(D / H));
+  const int len = min(max(a.seq_len[b], 0), L);
+  const float tq = a.target_time[b];
+  const int ldkv = 2 * N * D;
+
+  float dq[VPL];
+  {
+    float dp[VPL], gm[VPL], xh[VPL];
+    ldv<VPL>(dp, g.dpred + (int64_t)b * D + d0);
+    ldv<VPL>(gm, a.lnf_gamma + d0);
+    ldv<VPL>(xh, a.XHF + (int64_t)b * D + d0);
+    ln_bwd_row<VPL>(dp, gm, xh, a.RSTDF[b], D, dq);
+  }
+  for (int i = N - 1; i >= 0; --i) {
+    const int64_t ib = (int64_t)i * a.B + b;
+    stv<VPL>(g.DOUT + ((int64_t)b * N + i) * D + d0, dq);  // for d gamma_i / d beta_i column sums
+    float dy[VPL];
+    {
+      float gm[VPL], xh[VPL];
+      ldv<VPL>(gm, a.ln_gamma + (int64_t)i * D + d0);
+      ldv<VPL>(xh, a.XH + ((int64_t)b * N + i) * D + d0);
+      ln_bwd_row<VPL>(dq, gm, xh, a.RSTD[(int64_t)b * N + i], D, dy);
+    }
+    float Q[VPL], qt[VPL];
+    ldv<VPL>(Q, a.Qr + ib * D + d0);
+    ldv<VPL>(qt, a.Qt + ib * D + d0);
+    for (int j = lane; j < H * L; j += 32) ps[j] = a.PA[ib * H * L + j];
+    // ---- pass A: dP[h][j] = dO_h . V_hj ----
+#pragma unroll 2
+    for (int j = 0; j < len; ++j) {
+      const int64_t tok = (int64_t)b * L + j;
+      float vv[VPL];
+      ldv<VPL>(vv, a.KV + tok * ldkv + (int64_t)i * 2 * D + D + d0);
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) s = fmaf(dy[v], vv[v], s);
+      s = group_sum_rt(s, lph);
+      if ((lane % lph) == 0) dps[head * L + j] = s;
+    }
+    __syncwarp();
+    for (int h = 0; h < H; ++h) {
+      float s = 0.f;
+      for (int j = lane; j < len; j += 32) s = fmaf(ps[h * L + j], dps[h * L + j], s);
+      s = warp_sum(s);
+      if (lane == 0) dsum[h] = s;
+    }
+    __syncwarp();
+    const float* w1 = a.gate + ((int64_t)i * 5 + 0) * L;
+    const float* o1 = a.gate + ((int64_t)i * 5 + 2) * L;
+    const float* o2 = a.gate + ((int64_t)i * 5 + 3) * L;
+    float* gb = g.GB + (int64_t)b * (5 * N * L) + (int64_t)i * 5 * L;
+    (void)w1;
+    float dQ[VPL], dqt[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) { dQ[v] = 0.f; dqt[v] = 0.f; }
+    const float my_dsum = dsum[head];
+    // ---- pass B ----
+#pragma unroll 2
+    for (int j = 0; j < len; ++j) {
+      const int64_t tok = (int64_t)b * L + j;
+      float x[VPL], kk[VPL], vv[VPL];
+      ldv<VPL>(x, a.X + tok * D + d0);
+      ldv<VPL>(kk, a.KV + tok * ldkv + (int64_t)i * 2 * D + d0);
+      ldv<VPL>(vv, a.KV + tok * ldkv + (int64_t)i * 2 * D + D + d0);
+      const float gate = __ldg(a.GT + ib * L + j), Z = __ldg(a.ZZ + ib * L + j), Dk = __ldg(a.DK + ib * L + j);
+      float dgate = 0.f;
+      for (int h = 0; h < H; ++h) {
+        float dS = ps[h * L + j] * (dps[h * L + j] - dsum[h]);
+        dgate = fmaf(dS, __ldg(a.AA + (ib * H + h) * L + j), dgate);
+      }
+      dgate /= sqrt_dh;
+      const float dG = dgate * gate * (1.f - gate);
+      const float dDk = dG * __ldg(o1 + j);
+      const float dpre = dDk * (1.f - Dk * Dk);
+      if (lane == 0) {
+        float dlt = logf(fabsf(tq - __ldg(a.time_list + tok)) + 1.f);
+        gb[0 * L + j] = dpre * dlt;  // _time_input_w1
+        gb[1 * L + j] = dpre;        // _time_input_b1
+        gb[2 * L + j] = dG * Dk;     // time_output_w1
+        gb[3 * L + j] = dG * Z;      // time_output_w2
+        gb[4 * L + j] = dG;          // time_output_b
+      }
+      const float dM = dG * __ldg(o2 + j) * (1.f - Z * Z);
+      const float p = ps[head * L + j];
+      const float dS = p * (dps[head * L + j] - my_dsum);
+      const float dA = dS * gate / sqrt_dh;
+      float dK[VPL], dV[VPL], dx[VPL];
+      ldv<VPL>(dx, g.dX + tok * D + d0);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        dQ[v] = fmaf(dA, kk[v], dQ[v]);
+        dK[v] = (kk[v] > 0.f) ? dA * Q[v] : 0.f;
+        dV[v] = (vv[v] > 0.f) ? p * dy[v] : 0.f;
+        dqt[v] = fmaf(dM, x[v], dqt[v]);
+        dx[v] = fmaf(dM, qt[v], dx[v]);
+      }
+      stv<VPL>(g.dKV + tok * ldkv + (int64_t)i * 2 * D + d0, dK);
+      stv<VPL>(g.dKV + tok * ldkv + (int64_t)i * 2 * D + D + d0, dV);
+      stv<VPL>(g.dX + tok * D + d0, dx);
+    }
+    float dQp[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) dQp[v] = (Q[v] > 0.f) ? dQ[v] : 0.f;
+    stv<VPL>(g.DQP + ((int64_t)b * N + i) * D + d0, dQp);
+    stv<VPL>(g.DQT + ((int64_t)b * N + i) * D + d0, dqt);
+    // dq = dy (residual) + dQpre Wq^T + dqt Wt^T   (transposed copies prepared by the host side)
+    stv<VPL>(qs + d0, dQp);
+    stv<VPL>(qs2 + d0, dqt);
+    __syncwarp();
+    const float* WqT = g.WqT + (int64_t)i * D * D;
+    const float* WtT = g.WtT + (int64_t)i * D * D;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) dq[v] = dy[v];
+#pragma unroll 4
+    for (int k = 0; k < D; ++k) {
+      float s1 = qs[k], s2 = qs2[k];
+      float wq[VPL], wt[VPL];
+      ldv<VPL>(wq, WqT + k * D + d0);
+      ldv<VPL>(wt, WtT + k * D + d0);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) dq[v] = fmaf(s1, wq[v], fmaf(s2, wt[v], dq[v]));
+    }
+    __syncwarp();
+  }
+  stv<VPL>(g.dq0 + (int64_t)b * D + d0, dq);
+}
+
+size_t hop_smem_bytes(int D, int H, int L, bool bwd) {
+  size_t per_warp = bwd ? (size_t)(2 * D + 2 * H * L + 32) : (size_t)(D + 2 * H * L);
+  return per_warp * HOP_WARPS * sizeof(float);
+}
+
+int hop_forward(const HopArgs& a, cudaStream_t st) {
+  if (a.H < 1 || a.H > 32 || (32 % a.H) != 0 || (a.D % a.H) != 0)
+    return set_error(-1, "attention: num_heads=%d must divide 32 and num_units", a.H);
+  size_t smem = hop_smem_bytes(a.D, a.H, a.L, false);
+  int blocks = cdiv(a.B, HOP_WARPS);
+#define HOP_FWD(V)                                                                                            \
+  do {                                                                                                        \
+    MTAM_CUDA_CHECK(cudaFuncSetAttribute(hop_fwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    hop_fwd_kernel<V><<<blocks, HOP_WARPS * 32, smem, st>>>(a);                                               \
+  } while (0)
+  switch (a.D) {
+    case 32: HOP_FWD(1); break;
+    case 64: HOP_FWD(2); break;
+    case 128: HOP_FWD(4); break;
+    default: return set_error(-1, "attention: num_units=%d not supported (32, 64, 128)", a.D);
+  }
+#undef HOP_FWD
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
+int hop_backward(const HopArgs& a, const HopGradArgs& g, cudaStream_t st) {
+  size_t smem = hop_smem_bytes(a.D, a.H, a.L, true);
+  int blocks = cdiv(a.B, HOP_WARPS);
+#define HOP_BWD(V)                                                                                            \
+  do {                                                                                                        \
+    MTAM_CUDA_CHECK(cudaFuncSetAttribute(hop_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    hop_bwd_kernel<V><<<blocks, HOP_WARPS * 32, smem, st>>>(a, g);                                            \
+  } while (0)
+  switch (a.D) {
+    case 32: HOP_BWD(1); break;
+    case 64: HOP_BWD(2); break;
+    case 128: HOP_BWD(4); break;
+    default: return set_error(-1, "attention: num_units=%d not supported (32, 64, 128)", a.D);
+  }
+#undef HOP_BWD
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
+// dst[n][k] = src[k][n] for `count` DxD matrices
+__global__ void transpose_dd_kernel(const float* __restrict__ src, float* __restrict__ dst, int D) {
+  __shared__ float tile[32][33];
+  const float* s = src + (int64_t)blockIdx.z * D * D;
+  float* d = dst + (int64_t)blockIdx.z * D * D;
+  int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
+  for (int r = 0; r < 32; r += 8)
+    if (x < D && y + r < D) tile[threadIdx.y + r][threadIdx.x] = s[(y + r) * D + x];
+  __syncthreads();
+  x = blockIdx.y * 32 + threadIdx.x;
+  y = blockIdx.x * 32 + threadIdx.y;
+  for (int r = 0; r < 32; r += 8)
+    if (x < D && y + r < D) d[(y + r) * D + x] = tile[threadIdx.x][threadIdx.y + r];
+}
+int transpose_dd(const float* src, float* dst, int D, int count, cudaStream_t st) {
+  dim3 grid(cdiv(D, 32), cdiv(D, 32), count);
+  transpose_dd_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, D);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mtam

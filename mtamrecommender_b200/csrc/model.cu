@@ -1,0 +1,623 @@
+// Model handle, arena layout and step orchestration behind the C-ABI (include/mtam.h).
+// Replaces the device work of `sess.run([loss, merged, train_op], feed)` in
+// base_model.train (Model/base_model.py:150-167) for the MTAM graph (Model/MTAMRec_model.py:61-92).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "model_kernels.h"
+#include "selfattn.h"
+#include "../../include/mtam.h"
+
+namespace mtam {
+
+struct ParamDesc {
+  std::string name;
+  int rows, cols, ndim, ld;
+  size_t off;
+  int flags;
+};
+
+static const char* kGruLive[8] = {"_time_kernel_w1", "_time_kernel_b1", "_time_history_w1", "_time_w1",
+                                  "_time_b1", "_time_kernel_w2", "_time_w12", "_time_b12"};
+static const char* kGruDead[6] = {"_time_history_b1", "_time_kernel_b2", "_time_history_w2",
+                                  "_time_history_b2", "_time_w2", "_time_b2"};
+static const char* kGateLive[5] = {"_time_input_w1", "_time_input_b1", "time_output_w1", "time_output_w2",
+                                   "time_output_b"};
+
+// Arena layout (floats).  Tables whose gradient is sparse-only come first so that the dense-piece
+// norm can skip them; every block starts on a 4-float boundary.
+struct Layout {
+  size_t user = 0, cat = 0, pos = 0, dense_begin = 0, item = 0, Wemb = 0, Wgru = 0, bgru = 0, gruvec = 0, Wq = 0,
+         bq = 0, Wkv = 0, bkv = 0, Wt = 0, gate = 0, gate_dead = 0, lnb = 0, lng = 0, lnfb = 0, lnfg = 0, item_b = 0,
+         total = 0;
+  std::vector<ParamDesc> params;
+};
+
+struct Workspace {
+  // activations
+  float *E2, *R, *X, *GX, *Hs, *RUCT, *RH, *KV;
+  float *Qin, *Qr, *Qt, *AA, *PA, *ZZ, *DK, *GT, *XH, *RSTD, *XHF, *RSTDF, *pred;
+  float *tlogit, *lse, *loss_origin;
+  // gradients of activations
+  float *dpred, *dX, *dKV, *DOUT, *DQP, *DQT, *GB, *dq0, *WqT, *WtT, *dGX, *vec_partial, *dR, *dE2, *dEp, *dEu;
+  // partial-sum buffers and device scalars
+  float *l2_partial, *sq_partial, *ce_partial, *norm_partial, *dev_scalars;  // dev_scalars: [16]
+  void *ce_ws, *gemm_ws, *colsum_ws, *scatter_ws, *sa_ws, *topk_ws;
+  size_t ce_ws_bytes, gemm_ws_bytes, colsum_ws_bytes, scatter_ws_bytes, sa_ws_bytes, topk_ws_bytes;
+  size_t total_bytes;
+};
+
+}  // namespace mtam
+
+using namespace mtam;
+
+struct mtam_model {
+  mtam_config cfg;
+  Layout lay;
+  Workspace ws;
+  float *params, *grads, *m, *v;
+  int64_t adam_t = 0;
+  float b1_pow = 1.f, b2_pow = 1.f;  // fp32 running products, like TF's beta1_power / beta2_power variables
+  mtam_batch last_batch;
+  int last_B = 0;
+  bool grads_pending = false;
+  std::string err;
+};
+
+namespace mtam {
+
+static size_t a4(size_t x) { return (x + 3) / 4 * 4; }
+
+static void add_param(Layout& l, const std::string& name, int rows, int cols, int ndim, int ld, size_t off,
+                      int flags = 0) {
+  l.params.push_back(ParamDesc{name, rows, cols, ndim, ld, off, flags});
+}
+
+static int build_layout(const mtam_config& c, Layout& l) {
+  const int D = c.D, L = c.L, N = c.N;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o = a4(o + n); return r; };
+  l.user = take((size_t)c.user_rows * D);
+  l.cat = take((size_t)c.category_rows * D);
+  l.pos = take((size_t)c.position_rows * D);
+  l.dense_begin = o;
+  l.item = take((size_t)c.item_rows * D);
+  add_param(l, "embedding_layer/user", c.user_rows, D, 2, D, l.user, MTAM_PARAM_TABLE);
+  add_param(l, "embedding_layer/item", c.item_rows, D, 2, D, l.item, MTAM_PARAM_TABLE);
+  add_param(l, "embedding_layer/category", c.category_rows, D, 2, D, l.cat, MTAM_PARAM_TABLE);
+  add_param(l, "embedding_layer/position", c.position_rows, D, 2, D, l.pos, MTAM_PARAM_TABLE);
+  l.Wemb = take((size_t)2 * D * D);
+  add_param(l, "position_embedding/dense4emb/kernel", 2 * D, D, 2, D, l.Wemb);
+  if (c.kind == MTAM_KIND_BPRMF) {
+    l.item_b = take((size_t)c.item_rows);
+    add_param(l, "embedding_layer/item_b", c.item_rows, 1, 2, 1, l.item_b, MTAM_PARAM_TABLE);
+    l.total = o;
+    return 0;
+  }
+  if (c.kind == MTAM_KIND_MTAM) {
+    const std::string g = "ShortTermIntentEncoder/";
+    l.Wgru = take((size_t)2 * D * 3 * D);
+    add_param(l, g + "gates/kernel", 2 * D, 2 * D, 2, 3 * D, l.Wgru);
+    add_param(l, g + "candidate/kernel", 2 * D, D, 2, 3 * D, l.Wgru + 2 * D);
+    l.bgru = take((size_t)3 * D);
+    add_param(l, g + "gates/bias", 1, 2 * D, 1, 2 * D, l.bgru);
+    add_param(l, g + "candidate/bias", 1, D, 1, D, l.bgru + 2 * D);
+    l.gruvec = take((size_t)14 * D);
+    for (int i = 0; i < 8; ++i) add_param(l, g + kGruLive[i], 1, D, 1, D, l.gruvec + (size_t)i * D);
+    for (int i = 0; i < 6; ++i)
+      add_param(l, g + kGruDead[i], 1, D, 1, D, l.gruvec + (size_t)(8 + i) * D, MTAM_PARAM_DEAD);
+    l.Wq = take((size_t)N * D * D);
+    l.bq = take((size_t)N * D);
+    l.Wkv = take((size_t)D * 2 * N * D);
+    l.bkv = take((size_t)2 * N * D);
+    l.Wt = take((size_t)N * D * D);
+    l.gate = take((size_t)N * 5 * L);
+    l.gate_dead = take((size_t)N * L);
+    l.lnb = take((size_t)N * D);
+    l.lng = take((size_t)N * D);
+    for (int i = 0; i < N; ++i) {
+      const std::string b = "NextItemDecoder/decoder/num_blocks_" + std::to_string(i) + "/";
+      add_param(l, b + "dense/kernel", D, D, 2, D, l.Wq + (size_t)i * D * D);
+      add_param(l, b + "dense/bias", 1, D, 1, D, l.bq + (size_t)i * D);
+      add_param(l, b + "dense_1/kernel", D, D, 2, 2 * N * D, l.Wkv + (size_t)i * 2 * D);
+      add_param(l, b + "dense_1/bias", 1, D, 1, D, l.bkv + (size_t)i * 2 * D);
+      add_param(l, b + "dense_2/kernel", D, D, 2, 2 * N * D, l.Wkv + (size_t)i * 2 * D + D);
+      add_param(l, b + "dense_2/bias", 1, D, 1, D, l.bkv + (size_t)i * 2 * D + D);
+      add_param(l, b + "vanilla_attention/_time_input_w", D, D, 2, D, l.Wt + (size_t)i * D * D);
+      for (int k = 0; k < 5; ++k)
+        add_param(l, b + "vanilla_attention/" + kGateLive[k], 1, L, 2, L, l.gate + ((size_t)i * 5 + k) * L);
+      add_param(l, b + "vanilla_attention/time_output_w3", 1, L, 2, L, l.gate_dead + (size_t)i * L, MTAM_PARAM_DEAD);
+      add_param(l, b + "vanilla_attention/ln/beta", 1, D, 1, D, l.lnb + (size_t)i * D);
+      add_param(l, b + "vanilla_attention/ln/gamma", 1, D, 1, D, l.lng + (size_t)i * D);
+    }
+    l.lnfb = take(D);
+    l.lnfg = take(D);
+    add_param(l, "NextItemDecoder/LayerNorm/beta", 1, D, 1, D, l.lnfb);
+    add_param(l, "NextItemDecoder/LayerNorm/gamma", 1, D, 1, D, l.lnfg);
+    l.total = o;
+    return 0;
+  }
+  // self-attention family (PISTRec / SASRec / TA-SASRec / TiSASRec)
+  MTAM_TRY(sa_build_layout(c, o, l.params, l.lnfb, l.lnfg));
+  l.total = a4(o);
+  return 0;
+}
+
+static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspace& w) {
+  const int64_t B = c.max_batch, L = c.L, D = c.D, N = c.N, H = c.H;
+  const int64_t T = B * L;
+  Bump b(base, cap);
+  memset(&w, 0, sizeof(w));
+  w.E2 = b.take<float>(T * 2 * D);
+  w.R = b.take<float>(T * D);
+  w.X = b.take<float>(T * D);
+  w.pred = b.take<float>(B * D);
+  w.XHF = b.take<float>(B * D);
+  w.RSTDF = b.take<float>(B);
+  w.tlogit = b.take<float>(B);
+  w.lse = b.take<float>(B);
+  w.loss_origin = b.take<float>(B);
+  w.dpred = b.take<float>(B * D);
+  w.dX = b.take<float>(T * D);
+  w.dR = b.take<float>(T * D);
+  w.dE2 = b.take<float>(T * 2 * D);
+  w.dEp = b.take<float>(T * D);
+  w.dEu = b.take<float>(B * D);
+  w.l2_partial = b.take<float>(kEmbedMaxBlocks);
+  w.sq_partial = b.take<float>(kEmbedMaxBlocks);
+  w.ce_partial = b.take<float>(cdiv(B, 256) + 1);
+  w.norm_partial = b.take<float>(kNumSMs * 4 + 4);
+  w.dev_scalars = b.take<float>(16);
+  size_t gemm_ws = 0, colsum_ws = 0;
+  auto G = [&](int M, int Nn, int K) { gemm_ws = std::max(gemm_ws, gemm_splitk_workspace_bytes(M, Nn, K)); };
+  auto CS = [&](int M, int Nn) { colsum_ws = std::max(colsum_ws, colsum_workspace_bytes(M, Nn)); };
+  G(2 * D, D, T);  // dWemb
+  if (c.kind == MTAM_KIND_MTAM) {
+    w.GX = b.take<float>(T * 3 * D);
+    w.Hs = b.take<float>((T + 1) * D);
+    w.RUCT = b.take<float>(T * 4 * D);
+    w.RH = b.take<float>(T * D);
+    w.KV = b.take<float>(T * 2 * N * D);
+    w.Qin = b.take<float>((N + 1) * B * D);
+    w.Qr = b.take<float>(N * B * D);
+    w.Qt = b.take<float>(N * B * D);
+    w.AA = b.take<float>(N * B * H * L);
+    w.PA = b.take<float>(N * B * H * L);
+    w.ZZ = b.take<float>(N * B * L);
+    w.DK = b.take<float>(N * B * L);
+    w.GT = b.take<float>(N * B * L);
+    w.XH = b.take<float>(N * B * D);
+    w.RSTD = b.take<float>(N * B);
+    w.dKV = b.take<float>(T * 2 * N * D);
+    w.DOUT = b.take<float>(B * N * D);
+    w.DQP = b.take<float>(B * N * D);
+    w.DQT = b.take<float>(B * N * D);
+    w.GB = b.take<float>(B * 5 * N * L);
+    w.dq0 = b.take<float>(B * D);
+    w.WqT = b.take<float>(N * D * D);
+    w.WtT = b.take<float>(N * D * D);
+    w.dGX = b.take<float>(T * 3 * D);
+    w.vec_partial = b.take<float>((int64_t)gru_num_blocks(B) * 8 * D);
+    G(D, 2 * N * D, T); G(D, 3 * D, T); G(D, 2 * D, T); G(D, D, T); G(D, D, B);
+    CS(T, 2 * N * D); CS(T, 3 * D); CS(B, 5 * N * L); CS(B, N * D); CS(gru_num_blocks(B), 8 * D); CS(B, D);
+  } else if (c.kind != MTAM_KIND_BPRMF) {
+    w.sa_ws_bytes = sa_workspace_bytes(c);
+    w.sa_ws = b.take<char>(w.sa_ws_bytes);
+    G(D, 3 * D, T); G(D, D, T);
+    CS(T, 3 * D); CS(T, D); CS(B, D); CS(B, L * L); CS(T, L);
+  }
+  w.ce_ws_bytes = ce_workspace_bytes(B, D, c.item_rows);
+  w.ce_ws = b.take<char>(w.ce_ws_bytes);
+  w.gemm_ws_bytes = gemm_ws + 256;
+  w.gemm_ws = b.take<char>(w.gemm_ws_bytes);
+  w.colsum_ws_bytes = colsum_ws + 256;
+  w.colsum_ws = b.take<char>(w.colsum_ws_bytes);
+  size_t sc = 0;
+  sc = std::max(sc, scatter_add_workspace_bytes(T, c.item_rows, D));
+  sc = std::max(sc, scatter_add_workspace_bytes(T, c.category_rows, D));
+  sc = std::max(sc, scatter_add_workspace_bytes(T, c.position_rows, D));
+  sc = std::max(sc, scatter_add_workspace_bytes(B, c.user_rows, D));
+  w.scatter_ws_bytes = sc;
+  w.scatter_ws = b.take<char>(sc);
+  w.topk_ws_bytes = score_topk_workspace_bytes((int)B, c.item_rows, std::min(50, c.item_rows));
+  w.topk_ws = b.take<char>(w.topk_ws_bytes);
+  w.total_bytes = b.off + 1024;
+  if (base && !b.ok()) return set_error(MTAM_ERR_WORKSPACE, "workspace %zu bytes < required %zu", cap, w.total_bytes);
+  return 0;
+}
+
+static int validate(const mtam_config* c) {
+  if (!c) return set_error(MTAM_ERR_INVALID, "config is null");
+  if (c->abi_version != MTAM_ABI_VERSION)
+    return set_error(MTAM_ERR_INVALID, "abi_version %d != %d", c->abi_version, MTAM_ABI_VERSION);
+  if (c->kind < 0 || c->kind > MTAM_KIND_BPRMF) return set_error(MTAM_ERR_INVALID, "unknown model kind %d", c->kind);
+  if (c->D != 32 && c->D != 64 && c->D != 128)
+    return set_error(MTAM_ERR_INVALID, "num_units=%d not supported (32, 64 or 128)", c->D);
+  if (c->max_batch < 1 || c->L < 1 || c->N < 0) return set_error(MTAM_ERR_INVALID, "bad max_batch/L/N");
+  if (c->H < 1 || c->H > 32 || (32 % c->H) != 0 || (c->D % c->H) != 0)
+    return set_error(MTAM_ERR_INVALID, "num_heads=%d must divide 32 and num_units", c->H);
+  if (c->user_rows < 1 || c->item_rows < 1 || c->category_rows < 1 || c->position_rows < 1)
+    return set_error(MTAM_ERR_INVALID, "table row counts must be positive");
+  if (c->gemm_mode != MTAM_GEMM_FP32)
+    return set_error(MTAM_ERR_UNSUPPORTED, "gemm_mode %d not built in this version", c->gemm_mode);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MTAM forward / backward
+// ---------------------------------------------------------------------------------------------
+static int gemm(mtam_model* h, int tA, int tB, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb,
+                float* C, int ldc, const GemmEpilogue& e, cudaStream_t st) {
+  return gemm_f32(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, e, h->ws.gemm_ws, h->ws.gemm_ws_bytes, st);
+}
+static int colsum(mtam_model* h, const float* A, int lda, const float* Bm, int ldb, int M, int N, float* out,
+                  cudaStream_t st) {
+  return colsum_f32(A, lda, Bm, ldb, M, N, out, 0, h->ws.colsum_ws, h->ws.colsum_ws_bytes, st);
+}
+
+static HopArgs hop_args(mtam_model* h, const mtam_batch* bt) {
+  const mtam_config& c = h->cfg;
+  const Layout& l = h->lay;
+  Workspace& w = h->ws;
+  HopArgs a;
+  a.B = bt->B; a.L = c.L; a.D = c.D; a.H = c.H; a.N = c.N;
+  a.seq_len = bt->seq_length; a.target_time = bt->target_item_time; a.time_list = bt->time_list;
+  a.X = w.X; a.KV = w.KV;
+  a.Wq = h->params + l.Wq; a.bq = h->params + l.bq; a.Wt = h->params + l.Wt; a.gate = h->params + l.gate;
+  a.ln_gamma = h->params + l.lng; a.ln_beta = h->params + l.lnb;
+  a.lnf_gamma = h->params + l.lnfg; a.lnf_beta = h->params + l.lnfb;
+  a.Qin = w.Qin; a.Qr = w.Qr; a.Qt = w.Qt; a.AA = w.AA; a.PA = w.PA; a.ZZ = w.ZZ; a.DK = w.DK; a.GT = w.GT;
+  a.XH = w.XH; a.RSTD = w.RSTD; a.XHF = w.XHF; a.RSTDF = w.RSTDF; a.pred = w.pred;
+  return a;
+}
+
+// shared by all sequence models: embedding layer forward  (Behavior_...py:62-114)
+static int embed_forward(mtam_model* h, const mtam_batch* bt, int include_user, int* n_l2, cudaStream_t st) {
+  const mtam_config& c = h->cfg;
+  const Layout& l = h->lay;
+  Workspace& w = h->ws;
+  const int B = bt->B, D = c.D;
+  const int64_t T = (int64_t)B * c.L;
+  float* P = h->params;
+  MTAM_TRY(embed_gather(P + l.item, P + l.cat, P + l.pos, P + l.user, bt->item_list, bt->category_list,
+                        bt->position_list, bt->user_id, B, c.L, D, include_user, w.E2, w.l2_partial, n_l2, st));
+  GemmEpilogue e;
+  e.relu = 1;
+  MTAM_TRY(gemm(h, 0, 0, (int)T, D, 2 * D, w.E2, 2 * D, P + l.Wemb, D, w.R, D, e, st));
+  MTAM_TRY(add_pos(w.R, P + l.pos, bt->position_list, T, D, w.X, st));
+  return 0;
+}
+
+// shared: loss scalars  (base_model.py:302-323)
+static int loss_scalars(mtam_model* h, int n_l2, int n_ce, int global_batch, float* scalars_out, cudaStream_t st) {
+  Workspace& w = h->ws;
+  float* ds = w.dev_scalars;
+  MTAM_TRY(finalize_sum(w.l2_partial, n_l2, 0.5f, ds + MTAM_S_L2_NORM, 0, st));
+  MTAM_TRY(finalize_sum(w.ce_partial, n_ce, 1.0f / (float)global_batch, ds + MTAM_S_LOSS_ORIGIN, 0, st));
+  MTAM_TRY(finalize_sum(ds + MTAM_S_L2_NORM, 1, h->cfg.reg, ds + MTAM_S_LOSS, 0, st));
+  MTAM_TRY(finalize_sum(ds + MTAM_S_LOSS_ORIGIN, 1, 1.0f, ds + MTAM_S_LOSS, 1, st));
+  if (scalars_out)
+    MTAM_CUDA_CHECK(cudaMemcpyAsync(scalars_out, ds, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+static int mtam_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float* scalars_out, bool with_loss,
+                    cudaStream_t st) {
+  const mtam_config& c = h->cfg;
+  const Layout& l = h->lay;
+  Workspace& w = h->ws;
+  const int B = bt->B, D = c.D, N = c.N, L = c.L;
+  const int64_t T = (int64_t)B * L;
+  float* P = h->params;
+  int n_l2 = 0, n_ce = 0;
+  MTAM_TRY(embed_forward(h, bt, 1, &n_l2, st));
+  {  // x-side GRU pre-activations: [T,D] x [D,3D] + [bg|bc]
+    GemmEpilogue e;
+    e.bias = P + l.bgru;
+    MTAM_TRY(gemm(h, 0, 0, (int)T, 3 * D, D, w.X, D, P + l.Wgru, 3 * D, w.GX, 3 * D, e, st));
+  }
+  MTAM_CUDA_CHECK(cudaMemsetAsync(w.Hs, 0, (size_t)(T + 1) * D * sizeof(float), st));
+  MTAM_CUDA_CHECK(cudaMemsetAsync(w.RH, 0, (size_t)T * D * sizeof(float), st));
+  MTAM_TRY(gru_forward(D, w.X, w.GX, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, B, L, w.Hs, w.RUCT,
+                       w.RH, w.Qin, st));
+  {  // K,V of all hops: relu([T,D] x [D,2ND] + b)
+    GemmEpilogue e;
+    e.bias = P + l.bkv;
+    e.relu = 1;
+    MTAM_TRY(gemm(h, 0, 0, (int)T, 2 * N * D, D, w.X, D, P + l.Wkv, 2 * N * D, w.KV, 2 * N * D, e, st));
+  }
+  HopArgs a = hop_args(h, bt);
+  MTAM_TRY(hop_forward(a, st));
+  if (!with_loss) return 0;
+  MTAM_CUDA_CHECK(cudaMemsetAsync(w.tlogit, 0, (size_t)B * sizeof(float), st));
+  MTAM_TRY(ce_forward(D, w.pred, P + l.item, bt->target_item_id, B, c.item_rows, w.ce_ws, w.tlogit, w.lse,
+                      w.loss_origin, w.ce_partial, &n_ce, st));
+  MTAM_TRY(loss_scalars(h, n_l2, n_ce, global_batch, scalars_out, st));
+  return 0;
+}
+
+// shared: embedding-layer backward from dX; leaves the IndexedSlices values in dE2/dEp/dEu and
+// adds their squared norm to *norm_sq_sparse.
+static int embed_backward(mtam_model* h, const mtam_batch* bt, int include_user, float* norm_sq_sparse,
+                          cudaStream_t st) {
+  const mtam_config& c = h->cfg;
+  const Layout& l = h->lay;
+  Workspace& w = h->ws;
+  const int B = bt->B, D = c.D;
+  const int64_t T = (int64_t)B * c.L;
+  float* P = h->params;
+  float* G = h->grads;
+  MTAM_TRY(relu_mask(w.dX, w.R, T * D, w.dR, st));
+  GemmEpilogue e;
+  MTAM_TRY(gemm(h, 1, 0, 2 * D, D, (int)T, w.E2, 2 * D, w.dR, D, G + l.Wemb, D, e, st));     // dW = E2^T dR
+  MTAM_TRY(gemm(h, 0, 1, (int)T, 2 * D, D, w.dR, D, P + l.Wemb, D, w.dE2, 2 * D, e, st));    // dE2 = dR W^T
+  int n_sq = 0;
+  MTAM_TRY(embed_bwd_tail(w.E2, w.dX, P + l.pos, P + l.user, bt->position_list, bt->user_id, B, c.L, D, c.reg,
+                          include_user, w.dE2, w.dEp, w.dEu, w.sq_partial, &n_sq, st));
+  MTAM_TRY(finalize_sum(w.sq_partial, n_sq, 1.0f, norm_sq_sparse, 1, st));
+  return 0;
+}
+
+static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float* norm_sq_sparse, cudaStream_t st) {
+  const mtam_config& c = h->cfg;
+  const Layout& l = h->lay;
+  Workspace& w = h->ws;
+  const int B = bt->B, D = c.D, N = c.N, L = c.L;
+  const int64_t T = (int64_t)B * L;
+  float* P = h->params;
+  float* G = h->grads;
+  GemmEpilogue e0, eacc;
+  eacc.accumulate = 1;
+  // softmax CE: dense item-table gradient straight into the arena, dpred
+  MTAM_TRY(ce_backward(D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
+                       w.ce_ws, G + l.item, w.dpred, st));
+  // hops
+  MTAM_CUDA_CHECK(cudaMemsetAsync(w.dX, 0, (size_t)T * D * sizeof(float), st));
+  MTAM_CUDA_CHECK(cudaMemsetAsync(w.dKV, 0, (size_t)T * 2 * N * D * sizeof(float), st));
+  MTAM_CUDA_CHECK(cudaMemsetAsync(w.GB, 0, (size_t)B * 5 * N * L * sizeof(float), st));
+  MTAM_TRY(transpose_dd(P + l.Wq, w.WqT, D, N, st));
+  MTAM_TRY(transpose_dd(P + l.Wt, w.WtT, D, N, st));
+  HopArgs a = hop_args(h, bt);
+  HopGradArgs g;
+  g.dpred = w.dpred; g.WqT = w.WqT; g.WtT = w.WtT; g.dX = w.dX; g.dKV = w.dKV; g.DOUT = w.DOUT; g.DQP = w.DQP;
+  g.DQT = w.DQT; g.GB = w.GB; g.dq0 = w.dq0;
+  MTAM_TRY(hop_backward(a, g, st));
+  // hop parameter gradients
+  MTAM_TRY(colsum(h, w.dpred, D, nullptr, 0, B, D, G + l.lnfb, st));
+  MTAM_TRY(colsum(h, w.dpred, D, w.XHF, D, B, D, G + l.lnfg, st));
+  MTAM_TRY(colsum(h, w.DOUT, N * D, nullptr, 0, B, N * D, G + l.lnb, st));
+  MTAM_TRY(colsum(h, w.DOUT, N * D, w.XH, N * D, B, N * D, G + l.lng, st));
+  MTAM_TRY(colsum(h, w.DQP, N * D, nullptr, 0, B, N * D, G + l.bq, st));
+  MTAM_TRY(colsum(h, w.GB, 5 * N * L, nullptr, 0, B, 5 * N * L, G + l.gate, st));
+  for (int i = 0; i < N; ++i) {
+    const float* qin = w.Qin + (size_t)i * B * D;
+    MTAM_TRY(gemm(h, 1, 0, D, D, B, qin, D, w.DQP + (size_t)i * D, N * D, G + l.Wq + (size_t)i * D * D, D, e0, st));
+    MTAM_TRY(gemm(h, 1, 0, D, D, B, qin, D, w.DQT + (size_t)i * D, N * D, G + l.Wt + (size_t)i * D * D, D, e0, st));
+  }
+  MTAM_TRY(colsum(h, w.dKV, 2 * N * D, nullptr, 0, (int)T, 2 * N * D, G + l.bkv, st));
+  MTAM_TRY(gemm(h, 1, 0, D, 2 * N * D, (int)T, w.X, D, w.dKV, 2 * N * D, G + l.Wkv, 2 * N * D, e0, st));
+  MTAM_TRY(gemm(h, 0, 1, (int)T, D, 2 * N * D, w.dKV, 2 * N * D, P + l.Wkv, 2 * N * D, w.dX, D, eacc, st));
+  // T-GRU
+  MTAM_CUDA_CHECK(cudaMemsetAsync(w.dGX, 0, (size_t)T * 3 * D * sizeof(float), st));
+  MTAM_TRY(gru_backward(D, w.X, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, w.Hs, w.RUCT, w.dq0, B, L,
+                        w.dGX, w.dX, w.vec_partial, st));
+  MTAM_TRY(colsum(h, w.vec_partial, 8 * D, nullptr, 0, gru_num_blocks(B), 8 * D, G + l.gruvec, st));
+  MTAM_TRY(colsum(h, w.dGX, 3 * D, nullptr, 0, (int)T, 3 * D, G + l.bgru, st));
+  MTAM_TRY(gemm(h, 1, 0, D, 3 * D, (int)T, w.X, D, w.dGX, 3 * D, G + l.Wgru, 3 * D, e0, st));
+  // h-side: h_{t-1} = Hs shifted by one row (leading zero row), r*h_{t-1} = RH
+  MTAM_TRY(gemm(h, 1, 0, D, 2 * D, (int)T, w.Hs, D, w.dGX, 3 * D, G + l.Wgru + (size_t)D * 3 * D, 3 * D, e0, st));
+  MTAM_TRY(gemm(h, 1, 0, D, D, (int)T, w.RH, D, w.dGX + 2 * D, 3 * D, G + l.Wgru + (size_t)D * 3 * D + 2 * D, 3 * D, e0, st));
+  MTAM_TRY(gemm(h, 0, 1, (int)T, D, 3 * D, w.dGX, 3 * D, P + l.Wgru, 3 * D, w.dX, D, eacc, st));
+  MTAM_TRY(embed_backward(h, bt, 1, norm_sq_sparse, st));
+  return 0;
+}
+
+static int check_batch(mtam_model* h, const mtam_batch* bt) {
+  if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
+  if (!bt) return set_error(MTAM_ERR_INVALID, "null batch");
+  if (bt->B < 1 || bt->B > h->cfg.max_batch)
+    return set_error(MTAM_ERR_INVALID, "batch size %d outside [1, max_batch=%d]", bt->B, h->cfg.max_batch);
+  if (!bt->user_id || !bt->item_list || !bt->category_list || !bt->position_list || !bt->time_list ||
+      !bt->timelast_list || !bt->target_item_id || !bt->target_item_time || !bt->seq_length)
+    return set_error(MTAM_ERR_INVALID, "batch has a null feed array");
+  return 0;
+}
+
+static int fwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* scalars_out, bool with_loss,
+                        cudaStream_t st) {
+  switch (h->cfg.kind) {
+    case MTAM_KIND_MTAM: return mtam_fwd(h, bt, gb, scalars_out, with_loss, st);
+    case MTAM_KIND_BPRMF: return set_error(MTAM_ERR_UNSUPPORTED, "BPRMF is not built yet");
+    default: return set_error(MTAM_ERR_UNSUPPORTED, "self-attention models are not built yet");
+  }
+}
+static int bwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* nsq, cudaStream_t st) {
+  switch (h->cfg.kind) {
+    case MTAM_KIND_MTAM: return mtam_bwd(h, bt, gb, nsq, st);
+    default: return set_error(MTAM_ERR_UNSUPPORTED, "model kind %d backward is not built yet", h->cfg.kind);
+  }
+}
+
+}  // namespace mtam
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" {
+
+const char* mtam_last_error(mtam_handle h) {
+  (void)h;
+  return mtam::last_error_slot().c_str();
+}
+
+int mtam_plan(const mtam_config* cfg, mtam_sizes* out) {
+  MTAM_TRY(validate(cfg));
+  if (!out) return set_error(MTAM_ERR_INVALID, "out is null");
+  Layout l;
+  MTAM_TRY(build_layout(*cfg, l));
+  Workspace w;
+  MTAM_TRY(plan_workspace(*cfg, nullptr, 0, w));
+  out->param_floats = l.total;
+  out->workspace_bytes = w.total_bytes;
+  return 0;
+}
+
+int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam_m, float* adam_v, void* workspace,
+                size_t workspace_bytes, mtam_handle* out) {
+  MTAM_TRY(validate(cfg));
+  if (!params || !grads || !adam_m || !adam_v || !workspace || !out)
+    return set_error(MTAM_ERR_INVALID, "mtam_create: null arena / out pointer");
+  if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)adam_m | (uintptr_t)adam_v | (uintptr_t)workspace) & 15)
+    return set_error(MTAM_ERR_INVALID, "mtam_create: arenas must be 16-byte aligned");
+  mtam_model* h = new mtam_model();
+  h->cfg = *cfg;
+  int s = build_layout(*cfg, h->lay);
+  if (s == 0) s = plan_workspace(*cfg, workspace, workspace_bytes, h->ws);
+  if (s != 0) {
+    delete h;
+    return s;
+  }
+  h->params = params; h->grads = grads; h->m = adam_m; h->v = adam_v;
+  memset(&h->last_batch, 0, sizeof(h->last_batch));
+  *out = h;
+  return 0;
+}
+
+int mtam_destroy(mtam_handle h) {
+  delete h;
+  return 0;
+}
+
+int mtam_param_count(mtam_handle h) { return h ? (int)h->lay.params.size() : set_error(MTAM_ERR_INVALID, "null handle"); }
+
+int mtam_param_info_get(mtam_handle h, int32_t i, mtam_param_info* out) {
+  if (!h || !out || i < 0 || i >= (int)h->lay.params.size()) return set_error(MTAM_ERR_INVALID, "bad param index");
+  const ParamDesc& p = h->lay.params[i];
+  memset(out, 0, sizeof(*out));
+  strncpy(out->name, p.name.c_str(), MTAM_NAME_MAX - 1);
+  out->rows = p.rows; out->cols = p.cols; out->ndim = p.ndim; out->ld = p.ld; out->offset = p.off; out->flags = p.flags;
+  return 0;
+}
+
+int mtam_get_adam_step(mtam_handle h, int64_t* t) {
+  if (!h || !t) return set_error(MTAM_ERR_INVALID, "null argument");
+  *t = h->adam_t;
+  return 0;
+}
+int mtam_set_adam_step(mtam_handle h, int64_t t) {
+  if (!h || t < 0) return set_error(MTAM_ERR_INVALID, "bad argument");
+  h->adam_t = t;
+  h->b1_pow = 1.f; h->b2_pow = 1.f;
+  for (int64_t i = 0; i < t; ++i) { h->b1_pow *= h->cfg.beta1; h->b2_pow *= h->cfg.beta2; }
+  return 0;
+}
+
+int mtam_forward(mtam_handle h, const mtam_batch* batch, float* scalars_out, float* loss_origin_out, float* pred_out,
+                 void* stream) {
+  MTAM_TRY(check_batch(h, batch));
+  cudaStream_t st = (cudaStream_t)stream;
+  MTAM_TRY(fwd_dispatch(h, batch, batch->B, scalars_out, true, st));
+  if (loss_origin_out)
+    MTAM_CUDA_CHECK(cudaMemcpyAsync(loss_origin_out, h->ws.loss_origin, (size_t)batch->B * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+  if (pred_out)
+    MTAM_CUDA_CHECK(cudaMemcpyAsync(pred_out, h->ws.pred, (size_t)batch->B * h->cfg.D * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int mtam_forward_backward(mtam_handle h, const mtam_batch* batch, int32_t global_batch, float* scalars_out,
+                          float* norm_sq_sparse, void* stream) {
+  MTAM_TRY(check_batch(h, batch));
+  if (!norm_sq_sparse) return set_error(MTAM_ERR_INVALID, "norm_sq_sparse is null");
+  if (global_batch < batch->B) return set_error(MTAM_ERR_INVALID, "global_batch < local batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  MTAM_TRY(fwd_dispatch(h, batch, global_batch, scalars_out, true, st));
+  MTAM_TRY(bwd_dispatch(h, batch, global_batch, norm_sq_sparse, st));
+  h->last_batch = *batch;
+  h->last_B = batch->B;
+  h->grads_pending = true;
+  return 0;
+}
+
+int mtam_finish_grads(mtam_handle h, float* norm_sq, void* stream) {
+  if (!h || !norm_sq) return set_error(MTAM_ERR_INVALID, "null argument");
+  if (!h->grads_pending) return set_error(MTAM_ERR_INVALID, "mtam_finish_grads without a pending forward_backward");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mtam_config& c = h->cfg;
+  const Layout& l = h->lay;
+  Workspace& w = h->ws;
+  const mtam_batch& bt = h->last_batch;
+  const int B = h->last_B, D = c.D;
+  const int64_t T = (int64_t)B * c.L;
+  // dense pieces: everything from the item table to the end of the arena (the sparse-only table
+  // regions in front are excluded; their pieces were counted un-deduplicated by forward_backward)
+  int np = 0;
+  MTAM_TRY(sumsq_partials(h->grads + l.dense_begin, (int64_t)(l.total - l.dense_begin), w.norm_partial, &np, st));
+  MTAM_TRY(finalize_sum(w.norm_partial, np, 1.0f, norm_sq, 1, st));
+  float* G = h->grads;
+  MTAM_TRY(scatter_add_rows(G + l.item, c.item_rows, D, D, bt.item_list, w.dE2, 2 * D, T, w.scatter_ws,
+                            w.scatter_ws_bytes, nullptr, nullptr, st));
+  MTAM_TRY(scatter_add_rows(G + l.cat, c.category_rows, D, D, bt.category_list, w.dE2 + D, 2 * D, T, w.scatter_ws,
+                            w.scatter_ws_bytes, nullptr, nullptr, st));
+  MTAM_TRY(scatter_add_rows(G + l.pos, c.position_rows, D, D, bt.position_list, w.dEp, D, T, w.scatter_ws,
+                            w.scatter_ws_bytes, nullptr, nullptr, st));
+  if (c.kind != MTAM_KIND_PISTREC)
+    MTAM_TRY(scatter_add_rows(G + l.user, c.user_rows, D, D, bt.user_id, w.dEu, D, B, w.scatter_ws,
+                              w.scatter_ws_bytes, nullptr, nullptr, st));
+  return 0;
+}
+
+int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_out, void* stream) {
+  if (!h || !norm_sq) return set_error(MTAM_ERR_INVALID, "null argument");
+  if (!h->grads_pending) return set_error(MTAM_ERR_INVALID, "mtam_apply without pending gradients");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mtam_config& c = h->cfg;
+  const Layout& l = h->lay;
+  Workspace& w = h->ws;
+  float* ds = w.dev_scalars;
+  MTAM_TRY(clip_scale(norm_sq, c.clip, ds + MTAM_S_GLOBAL_NORM, ds + MTAM_S_CLIP_SCALE, st));
+  h->adam_t += 1;
+  h->b1_pow *= c.beta1;
+  h->b2_pow *= c.beta2;
+  const float lr32 = (float)lr;  // float64 placeholder cast to fp32 (base_model.py:25)
+  const float lr_t = lr32 * sqrtf(1.f - h->b2_pow) / (1.f - h->b1_pow);
+  MTAM_TRY(adam_apply(h->params, h->m, h->v, h->grads, (int64_t)l.total, ds + MTAM_S_CLIP_SCALE, lr_t, c.beta1, c.beta2,
+                      c.eps, st));
+  // restore the invariant "sparse-only table regions of the grads arena are zero"
+  MTAM_CUDA_CHECK(cudaMemsetAsync(h->grads + l.cat, 0, (l.dense_begin - l.cat) * sizeof(float), st));
+  if (c.kind != MTAM_KIND_PISTREC) MTAM_TRY(zero_rows(h->grads + l.user, h->last_batch.user_id, h->last_B, c.D, st));
+  if (scalars_out)
+    MTAM_CUDA_CHECK(cudaMemcpyAsync(scalars_out + MTAM_S_GLOBAL_NORM, ds + MTAM_S_GLOBAL_NORM, 2 * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+  h->grads_pending = false;
+  return 0;
+}
+
+int mtam_eval_topk(mtam_handle h, const mtam_batch* batch, int32_t k, int32_t* idx_out, float* score_out, void* stream) {
+  MTAM_TRY(check_batch(h, batch));
+  if (!idx_out) return set_error(MTAM_ERR_INVALID, "idx_out is null");
+  cudaStream_t st = (cudaStream_t)stream;
+  MTAM_TRY(fwd_dispatch(h, batch, batch->B, nullptr, false, st));
+  return score_topk(h->ws.pred, batch->B, h->cfg.D, h->params + h->lay.item, 0, h->cfg.item_rows, k, idx_out, score_out,
+                    h->ws.topk_ws, h->ws.topk_ws_bytes, st);
+}
+
+int mtam_train_step(mtam_handle h, const mtam_batch* batch, double lr, float* scalars_out, void* stream) {
+  MTAM_TRY(check_batch(h, batch));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* nsq = h->ws.dev_scalars + 8;
+  MTAM_CUDA_CHECK(cudaMemsetAsync(nsq, 0, sizeof(float), st));
+  MTAM_TRY(mtam_forward_backward(h, batch, batch->B, scalars_out, nsq, stream));
+  MTAM_TRY(mtam_finish_grads(h, nsq, stream));
+  MTAM_TRY(mtam_apply(h, lr, nsq, scalars_out, stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// Gradient global norm (tf.clip_by_global_norm) and TF-style Adam over the flat arenas.
+//
+// Reference: cal_gradient  Model/base_model.py:290-297; tf.train.AdamOptimizer  :76
+//   global_norm = sqrt(sum over gradient tensors of sum(values^2)), IndexedSlices contribute their
+//   un-deduplicated values (SURVEY trap T1): the caller passes that part in norm_sq already.
+//   Adam (trap T2): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+//   w -= lr_t * m / (sqrt(v) + eps).  TF's sparse apply is non-lazy, i.e. this dense update with
+//   g = 0 on untouched rows.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "model_kernels.h"
+
+namespace mtam {
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ x, int64_t n4, const float* __restrict__ tail,
+                                                    int ntail, float* __restrict__ partial) {
+  __shared__ float red[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = __ldg(x + i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < ntail) s += tail[threadIdx.x] * tail[threadIdx.x];
+  float tot = block_sum(s, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+int sumsq_num_partials(int64_t n) { return std::max(1, (int)std::min<int64_t>(cdiv(n / 4 + 1, 256 * 4), kNumSMs * 4)); }
+
+// partial[0..*n_partial) = block sums of x[i]^2, i in [0,n).  x must be 16-byte aligned.
+int sumsq_partials(const float* x, int64_t n, float* partial, int* n_partial, cudaStream_t st) {
+  int blocks = sumsq_num_partials(n);
+  int64_t n4 = n / 4;
+  sumsq_kernel<<<blocks, 256, 0, st>>>((const float4*)x, n4, x + n4 * 4, (int)(n - n4 * 4), partial);
+  MTAM_LAUNCH_CHECK();
+  *n_partial = blocks;
+  return 0;
+}
+
+// scalars[GLOBAL_NORM] = sqrt(*norm_sq); scalars[CLIP_SCALE] = clip / max(norm, clip)
+__global__ void clip_scale_kernel(const float* norm_sq, float clip, float* gn_out, float* scale_out) {
+  float gn = sqrtf(norm_sq[0]);
+  gn_out[0] = gn;
+  scale_out[0] = clip / fmaxf(gn, clip);
+}
+int clip_scale(const float* norm_sq, float clip, float* gn_out, float* scale_out, cudaStream_t st) {
+  clip_scale_kernel<<<1, 1, 0, st>>>(norm_sq, clip, gn_out, scale_out);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v,
+                                                   const float4* __restrict__ g, int64_t n4, const float* __restrict__ scale_p,
+                                                   float lr_t, float b1, float b2, float eps) {
+  const float sc = scale_p[0];
+  const float ob1 = 1.f - b1, ob2 = 1.f - b2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 gg = __ldg(g + i), mm = m[i], vv = v[i], ww = w[i];
+#define ADAM1(c)                                   \
+  {                                                \
+    float gs = gg.c * sc;                          \
+    mm.c = b1 * mm.c + ob1 * gs;                   \
+    vv.c = b2 * vv.c + ob2 * gs * gs;              \
+    ww.c = ww.c - lr_t * mm.c / (sqrtf(vv.c) + eps); \
+  }
+    ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+    m[i] = mm; v[i] = vv; w[i] = ww;
+  }
+}
+
+// arenas are padded to a multiple of 4 floats by the planner
+int adam_apply(float* w, float* m, float* v, const float* g, int64_t n, const float* scale_p, float lr_t, float b1,
+               float b2, float eps, cudaStream_t st) {
+  int64_t n4 = n / 4;
+  int blocks = std::max(1, (int)std::min<int64_t>(cdiv(n4, 256), kNumSMs * 8));
+  adam_kernel<<<blocks, 256, 0, st>>>((float4*)w, (float4*)m, (float4*)v, (const float4*)g, n4, scale_p, lr_t, b1, b2, eps);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mtam

@@ -1,0 +1,317 @@
+"""Host-side engine: owns the device arenas (torch tensors as plain device memory), the model
+handle and the streams, and turns the reference's feed dictionaries into C-ABI calls.
+
+It plays the role `tf.Session` plays in the reference (train_process.py:146, base_model.py:150-167):
+`Engine.train_step(feed, lr)` == `sess.run([loss, merged, train_op], feed_dict)`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Batch, Config, ParamInfo, Sizes, check
+
+FEED_INT = ("user_id", "item_list", "category_list", "position_list", "target_item_id",
+            "target_item_category", "seq_length")
+FEED_FLOAT = ("time_list", "timelast_list", "timenow_list", "target_item_time")
+FEED_KEYS = FEED_INT + FEED_FLOAT
+
+
+@dataclass
+class ModelConfig:
+    kind: str = "MTAM"
+    max_batch: int = 256
+    L: int = 50
+    D: int = 128
+    H: int = 1
+    N: int = 6
+    user_count: int = 0
+    item_count: int = 0
+    category_count: int = 0
+    reg: float = 5e-5
+    clip: float = 1.0
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    gemm_mode: int = _lib.GEMM_FP32
+
+    def to_c(self) -> Config:
+        c = Config()
+        c.abi_version = _lib.ABI_VERSION
+        c.kind = _lib.KINDS[self.kind]
+        c.max_batch, c.L, c.D, c.H, c.N = self.max_batch, self.L, self.D, self.H, self.N
+        c.user_rows, c.item_rows = self.user_count + 3, self.item_count + 3
+        c.category_rows, c.position_rows = self.category_count + 3, self.L + 3
+        c.reg, c.clip, c.beta1, c.beta2, c.eps = self.reg, self.clip, self.beta1, self.beta2, self.eps
+        c.gemm_mode = self.gemm_mode
+        return c
+
+
+class DeviceBatch:
+    """The 11 feed arrays resident on the device, plus the C struct that points at them."""
+
+    def __init__(self, tensors: Dict[str, torch.Tensor], B: int):
+        self.t = tensors
+        self.B = B
+        self.c = Batch()
+        self.c.B = B
+        for k in FEED_KEYS:
+            setattr(self.c, k, tensors[k].data_ptr())
+
+    def nbytes(self) -> int:
+        return sum(v.numel() * v.element_size() for v in self.t.values())
+
+
+class Engine:
+    def __init__(self, cfg: ModelConfig, device: str = "cuda:0", seed: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise _lib.MtamError("mtamrecommender_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.c_cfg = cfg.to_c()
+        sizes = Sizes()
+        check(self.lib.mtam_plan(C.byref(self.c_cfg), C.byref(sizes)), "mtam_plan")
+        self.n_floats = int(sizes.param_floats)
+        self.workspace_bytes = int(sizes.workspace_bytes)
+        dev = self.device
+        self.params = torch.zeros(self.n_floats, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(self.n_floats, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(self.n_floats, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(self.n_floats, dtype=torch.float32, device=dev)
+        self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=dev)
+        self.scalars = torch.zeros(_lib.S_COUNT, dtype=torch.float32, device=dev)
+        self.norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        h = C.c_void_p()
+        check(self.lib.mtam_create(C.byref(self.c_cfg), self.params.data_ptr(), self.grads.data_ptr(),
+                                   self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.workspace.data_ptr(),
+                                   self.workspace_bytes, C.byref(h)), "mtam_create")
+        self.h = h
+        self.info: Dict[str, ParamInfo] = {}
+        for i in range(self.lib.mtam_param_count(self.h)):
+            pi = ParamInfo()
+            check(self.lib.mtam_param_info_get(self.h, i, C.byref(pi)), "mtam_param_info_get")
+            self.info[pi.name.decode()] = pi
+        # pinned staging for the per-step host->device feed copy
+        self._pinned: Dict[str, torch.Tensor] = {}
+        self._dev: Dict[str, torch.Tensor] = {}
+        B, L = cfg.max_batch, cfg.L
+        for k in FEED_KEYS:
+            shape = (B, L) if k.endswith("_list") else (B,)
+            dt = torch.int32 if k in FEED_INT else torch.float32
+            self._pinned[k] = torch.empty(shape, dtype=dt).pin_memory()
+            self._dev[k] = torch.empty(shape, dtype=dt, device=dev)
+        self._scalars_host = torch.empty(_lib.S_COUNT, dtype=torch.float32).pin_memory()
+        if seed is not None:
+            self.init_random(seed)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.mtam_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- parameters ----------------------------------------------------------------------
+    def param_names(self):
+        return list(self.info.keys())
+
+    def _view(self, arena: torch.Tensor, name: str) -> torch.Tensor:
+        pi = self.info[name]
+        v = arena.as_strided((pi.rows, pi.cols), (pi.ld, 1), int(pi.offset))
+        return v[0] if pi.ndim == 1 else v
+
+    def param_view(self, name): return self._view(self.params, name)
+    def grad_view(self, name): return self._view(self.grads, name)
+    def adam_m_view(self, name): return self._view(self.adam_m, name)
+    def adam_v_view(self, name): return self._view(self.adam_v, name)
+
+    def is_dead(self, name: str) -> bool:
+        return bool(self.info[name].flags & _lib.PARAM_DEAD)
+
+    def set_param(self, name: str, value) -> None:
+        v = self.param_view(name)
+        t = torch.as_tensor(np.asarray(value), dtype=torch.float32).reshape(v.shape)
+        v.copy_(t.to(self.device))
+
+    def get_param(self, name: str) -> np.ndarray:
+        return self.param_view(name).detach().cpu().numpy().copy()
+
+    def set_params(self, params: Dict[str, np.ndarray]) -> None:
+        missing = set(self.info) - set(params)
+        extra = set(params) - set(self.info)
+        if missing or extra:
+            raise KeyError(f"parameter name mismatch: missing={sorted(missing)} extra={sorted(extra)}")
+        for k, v in params.items():
+            self.set_param(k, v)
+
+    def get_params(self) -> Dict[str, np.ndarray]:
+        return {k: self.get_param(k) for k in self.info}
+
+    def init_random(self, seed: int = 1234) -> None:
+        """Initialisers the reference ends up with: tables U(+-sqrt(6/D)), glorot-uniform
+        for get_variable defaults, dense bias 0, GRU gate bias 1, LayerNorm gamma 1 / beta 0."""
+        g = torch.Generator(device="cpu")
+        g.manual_seed(seed)
+        for name, pi in self.info.items():
+            leaf = name.rsplit("/", 1)[-1]
+            shape = (pi.rows, pi.cols) if pi.ndim == 2 else (pi.cols,)
+            if name.startswith("embedding_layer/"):
+                r = (6.0 / pi.cols) ** 0.5
+                t = (torch.rand(shape, generator=g) * 2 - 1) * r
+            elif leaf == "gamma":
+                t = torch.ones(shape)
+            elif leaf == "beta":
+                t = torch.zeros(shape)
+            elif leaf == "bias":
+                t = torch.ones(shape) if name.endswith("gates/bias") else torch.zeros(shape)
+            else:
+                fi, fo = (shape[0], shape[0]) if len(shape) == 1 else (shape[0], shape[1])
+                lim = (6.0 / (fi + fo)) ** 0.5
+                t = (torch.rand(shape, generator=g) * 2 - 1) * lim
+            self.param_view(name).copy_(t.to(self.device))
+
+    def adam_step(self) -> int:
+        t = C.c_int64()
+        check(self.lib.mtam_get_adam_step(self.h, C.byref(t)), "mtam_get_adam_step")
+        return int(t.value)
+
+    def set_adam_step(self, t: int) -> None:
+        check(self.lib.mtam_set_adam_step(self.h, int(t)), "mtam_set_adam_step")
+
+    # ---- feed ----------------------------------------------------------------------------
+    def upload(self, feed: Dict[str, np.ndarray]) -> DeviceBatch:
+        """Host feed (numpy, as make_feed_dic_new builds it) -> pinned staging -> device."""
+        B = int(len(feed["user_id"]))
+        if B < 1 or B > self.cfg.max_batch:
+            raise ValueError(f"batch size {B} outside [1, {self.cfg.max_batch}]")
+        out = {}
+        for k in FEED_KEYS:
+            src = torch.from_numpy(np.ascontiguousarray(feed[k]))
+            pin = self._pinned[k][:B]
+            pin.copy_(src)
+            dv = self._dev[k][:B]
+            dv.copy_(pin, non_blocking=True)
+            out[k] = dv
+        return DeviceBatch(out, B)
+
+    def device_batch(self, tensors: Dict[str, torch.Tensor]) -> DeviceBatch:
+        B = int(tensors["user_id"].shape[0])
+        for k in FEED_KEYS:
+            t = tensors[k]
+            want = torch.int32 if k in FEED_INT else torch.float32
+            if t.dtype != want or not t.is_cuda or not t.is_contiguous():
+                raise TypeError(f"feed array {k}: need contiguous cuda {want}")
+        return DeviceBatch(tensors, B)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- steps ---------------------------------------------------------------------------
+    def train_step_device(self, batch: DeviceBatch, lr: float) -> None:
+        check(self.lib.mtam_train_step(self.h, C.byref(batch.c), float(lr), self.scalars.data_ptr(), self._stream()),
+              "mtam_train_step")
+
+    def read_scalars(self) -> np.ndarray:
+        self._scalars_host.copy_(self.scalars, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._scalars_host.numpy().copy()
+
+    def train_step(self, feed: Dict[str, np.ndarray], lr: float) -> float:
+        self.train_step_device(self.upload(feed), lr)
+        return float(self.read_scalars()[_lib.S_LOSS])
+
+    def forward_device(self, batch: DeviceBatch, want_pred=True):
+        B, D = batch.B, self.cfg.D
+        lo = torch.empty(B, dtype=torch.float32, device=self.device)
+        pred = torch.empty((B, D), dtype=torch.float32, device=self.device) if want_pred else None
+        check(self.lib.mtam_forward(self.h, C.byref(batch.c), self.scalars.data_ptr(), lo.data_ptr(),
+                                    pred.data_ptr() if want_pred else None, self._stream()), "mtam_forward")
+        return lo, pred
+
+    def forward(self, feed):
+        lo, pred = self.forward_device(self.upload(feed))
+        s = self.read_scalars()
+        return dict(loss=float(s[_lib.S_LOSS]), loss_origin_mean=float(s[_lib.S_LOSS_ORIGIN]),
+                    l2_norm=float(s[_lib.S_L2_NORM]), loss_origin=lo.cpu().numpy(), pred=pred.cpu().numpy())
+
+    def forward_backward_device(self, batch: DeviceBatch, global_batch: Optional[int] = None) -> None:
+        self.norm_sq.zero_()
+        check(self.lib.mtam_forward_backward(self.h, C.byref(batch.c), int(global_batch or batch.B),
+                                             self.scalars.data_ptr(), self.norm_sq.data_ptr(), self._stream()),
+              "mtam_forward_backward")
+
+    def finish_grads(self) -> None:
+        check(self.lib.mtam_finish_grads(self.h, self.norm_sq.data_ptr(), self._stream()), "mtam_finish_grads")
+
+    def apply(self, lr: float) -> None:
+        check(self.lib.mtam_apply(self.h, float(lr), self.norm_sq.data_ptr(), self.scalars.data_ptr(), self._stream()),
+              "mtam_apply")
+
+    def gradients(self, feed) -> Dict[str, np.ndarray]:
+        """Dense (de-duplicated) gradients of the last batch, for parity tests: runs forward_backward and
+        finish_grads but not apply; the arena is cleaned afterwards."""
+        b = self.upload(feed)
+        self.forward_backward_device(b)
+        self.finish_grads()
+        out = {k: self.grad_view(k).detach().cpu().numpy().copy() for k in self.info}
+        out["__norm_sq__"] = float(self.norm_sq.item())
+        out["__scalars__"] = self.read_scalars()
+        self.grads.zero_()
+        # drop the pending flag by applying a zero-lr step on zero grads would change Adam state;
+        # instead recreate nothing: the next forward_backward simply overwrites.
+        return out
+
+    def eval_topk_device(self, batch: DeviceBatch, k: int = 50):
+        idx = torch.empty((batch.B, k), dtype=torch.int32, device=self.device)
+        sc = torch.empty((batch.B, k), dtype=torch.float32, device=self.device)
+        check(self.lib.mtam_eval_topk(self.h, C.byref(batch.c), k, idx.data_ptr(), sc.data_ptr(), self._stream()),
+              "mtam_eval_topk")
+        return idx, sc
+
+    def hr_ndcg_device(self, idx: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(10, dtype=torch.float32, device=self.device)
+        check(self.lib.mtam_hr_ndcg(idx.data_ptr(), idx.shape[0], idx.shape[1], target.data_ptr(), out.data_ptr(),
+                                    self._stream()), "mtam_hr_ndcg")
+        return out
+
+
+# ---- stand-alone kernels --------------------------------------------------------------------
+def gather(table: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    n = idx.numel()
+    D = table.shape[1]
+    if out is None:
+        out = torch.empty((n, D), dtype=torch.float32, device=table.device)
+    check(lib.mtam_gather(table.data_ptr(), table.shape[0], D, idx.data_ptr(), n, out.data_ptr(),
+                          torch.cuda.current_stream(table.device).cuda_stream), "mtam_gather")
+    return out
+
+
+def scatter_add_workspace(n: int, table_rows: int, D: int) -> int:
+    return int(_lib.load().mtam_scatter_add_workspace(n, table_rows, D))
+
+
+def scatter_add(dst: torch.Tensor, idx: torch.Tensor, rows: torch.Tensor, workspace: Optional[torch.Tensor] = None,
+                want_unique: bool = False):
+    lib = _lib.load()
+    n = idx.numel()
+    R, D = dst.shape
+    if workspace is None:
+        workspace = torch.empty(max(scatter_add_workspace(n, R, D), 16), dtype=torch.uint8, device=dst.device)
+    uniq = torch.empty(max(n, 1), dtype=torch.int32, device=dst.device) if want_unique else None
+    nuniq = torch.zeros(1, dtype=torch.int32, device=dst.device) if want_unique else None
+    check(lib.mtam_scatter_add(dst.data_ptr(), R, D, idx.data_ptr(), rows.data_ptr(), n, workspace.data_ptr(),
+                               workspace.numel(), uniq.data_ptr() if want_unique else None,
+                               nuniq.data_ptr() if want_unique else None,
+                               torch.cuda.current_stream(dst.device).cuda_stream), "mtam_scatter_add")
+    if want_unique:
+        return dst, uniq, nuniq
+    return dst
