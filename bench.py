@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the MTAM train step (forward + backward + clip + Adam) on B200.
+
+Contract (one JSON line on stdout from rank 0):
+  python bench.py --gpus N --steps K --warmup W            -> the CUDA path (libmtam_b200.so)
+  python bench.py --impl reference ...                     -> CPU port of the reference graph on the host cores
+Workload at N=1 is BASELINE.json configs[2]: synthetic MTAMRec, 100K items, seq len 50, batch 1024,
+embed dim 64 (N=6 hops, 1 head).  With N>1 every rank runs the same per-GPU batch
+(weak scaling) and the gradients are combined as described in DESIGN.md (multi-GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: kind, B per GPU, L, D, N hops, H, items, cats, users
+    "cfg3": dict(kind="MTAM", B=1024, L=50, D=64, N=6, H=1, items=100_000, cats=1_000, users=1_000_000),
+    "cfg4": dict(kind="MTAM", B=1024, L=200, D=64, N=6, H=1, items=10_000_000, cats=1_000, users=1_000_000),
+    "cfg1": dict(kind="MTAM", B=256, L=50, D=128, N=6, H=1, items=3_706, cats=301, users=4_832),
+    "tiny": dict(kind="MTAM", B=64, L=16, D=64, N=2, H=1, items=2_000, cats=50, users=500),
+}
+METRIC = "train seqs/s fwd+bwd (full train step incl. clip+Adam)"
+UNIT = "seq/s"
+LR = 1e-3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.p = None
+        self.path = f"/tmp/mtam_clocks_{os.getpid()}.csv"
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm)); out["sm_max_mhz"] = float(max(mx)); out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def make_feeds(w, n, seed0):
+    from mtamrecommender_b200.synth import ZipfSampler, synth_feed
+    samp = ZipfSampler(w["items"], 1.05)
+    return [synth_feed(w["B"], w["L"], w["items"], w["cats"], w["users"], seed0 + i, samp) for i in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, w):
+    """CPU arm: the oracle's torch-fp32 port of the reference graph on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import mtam_oracle as O
+    from oracle.cpu_port import TorchPort
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = min(w["B"], args.cpu_batch)
+    cfg = O.OracleConfig(kind=O.MTAM, L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
+                         item_count=w["items"], category_count=w["cats"])
+    port = TorchPort(cfg, O.init_params(cfg, 1234))
+    feeds = make_feeds(dict(w, B=Bs), 2, 1234)
+    for i in range(args.warmup):
+        port.train_step(feeds[i % 2], LR)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        port.train_step(feeds[i % 2], LR)
+    dt = time.perf_counter() - t0
+    val = Bs * args.steps / dt
+    sample = f"{args.steps} steps of {Bs} sequences (full V={w['items']}, L={w['L']}, D={w['D']}, N={w['N']})"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload, **{k: w[k] for k in ("B", "L", "D", "N", "H", "items")},
+                      "note": "TF 1.14 cannot run in this image; torch-CPU fp32 port of the same graph (oracle/cpu_port.py)"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline(w, seconds_budget=25.0):
+    import torch
+    from oracle import mtam_oracle as O
+    from oracle.cpu_port import TorchPort
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = min(w["B"], 256)
+    cfg = O.OracleConfig(kind=O.MTAM, L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
+                         item_count=w["items"], category_count=w["cats"])
+    port = TorchPort(cfg, O.init_params(cfg, 1234))
+    feed = make_feeds(dict(w, B=Bs), 1, 99)[0]
+    port.train_step(feed, LR)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < seconds_budget / 3 and n < 8):
+        port.train_step(feed, LR)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": Bs * n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} steps of {Bs} sequences after 1 warm-up (full V={w['items']}, L={w['L']}, D={w['D']}, "
+                      f"N={w['N']}); torch-CPU fp32 port of the reference graph, not TF 1.14"}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_cuda(args, w):
+    import torch
+    import torch.distributed as dist
+    from mtamrecommender_b200 import engine as E
+    from mtamrecommender_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    dev = f"cuda:{local}"
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    mc = E.ModelConfig(kind=w["kind"], max_batch=w["B"], L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
+                       item_count=w["items"], category_count=w["cats"])
+    eng = E.Engine(mc, device=dev, seed=1234)           # same seed on every rank: replicas start identical
+    dp = None
+    if world > 1:
+        from mtamrecommender_b200.parallel import DataParallel
+        dp = DataParallel(eng)
+    nb = 4
+    feeds = make_feeds(w, nb, 1234 + 1000 * rank)
+    batches = []
+    for f in feeds:   # device-resident copies for the HBM-resident measurement
+        t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in f.items()}
+        batches.append(eng.device_batch(t))
+
+    def step_dev(i):
+        if dp is not None:
+            dp.train_step_device(batches[i % nb], LR)
+        else:
+            eng.train_step_device(batches[i % nb], LR)
+
+    def step_e2e(i):
+        if dp is not None:
+            return dp.train_step(feeds[i % nb], LR)
+        return eng.train_step(feeds[i % nb], LR)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(steps):
+            fn(i)
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        step_dev(i)
+    use_graph = (dp is None) and (not args.no_graph)
+    if use_graph:
+        eng.capture_train_graph(w["B"])
+        stage = {k: v for k, v in eng._dev.items()}
+
+        def step_graph(i):
+            b = batches[i % nb]
+            for k in E.FEED_KEYS:                     # device->device refresh of the captured input buffers
+                stage[k][:b.B].copy_(b.t[k], non_blocking=True)
+            eng.train_step_graph(LR)
+        for i in range(2):
+            step_graph(i)
+        fn_dev = step_graph
+    else:
+        fn_dev = step_dev
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launch_count()
+    ms_dev = timed(fn_dev, args.steps)
+    launches = eng.launch_count() - l0
+    if use_graph:   # launches inside a replayed graph are not re-counted by the host counter: count one eager step
+        l0 = eng.launch_count(); step_dev(0); launches = (eng.launch_count() - l0) * args.steps
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else {}
+    seqs = w["B"] * world * args.steps
+    value = seqs / (ms_dev / 1e3)
+    e2e_val = seqs / (ms_e2e / 1e3)
+    h2d = sum(v.nbytes for v in feeds[0].values())
+
+    out = None
+    if rank == 0:
+        pk = peaks()
+        # ---- per-phase device times of the same step (CUDA events on the step's stream) ----
+        phases = {}
+        reps = max(3, min(args.steps, 10))
+        if dp is None:
+            for i in range(reps):
+                p = eng.profile_step(batches[i % nb], LR)
+                for k, v in p.items():
+                    phases[k] = phases.get(k, 0.0) + v / reps
+        T = w["B"] * w["L"]
+        D, V, B, N = w["D"], w["items"] + 3, w["B"], w["N"]
+        flops = {"ce_bwd": 6.0 * B * D * V, "ce_fwd": 2.0 * B * D * V, "kv_gemm": 2.0 * T * D * 2 * N * D}
+        roof = None
+        if phases:
+            dom = max(phases, key=phases.get)
+            if dom in flops:
+                ach = flops[dom] / (phases[dom] * 1e-3) / 1e12
+                roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                        "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                        "ms": phases[dom], "share_of_step": phases[dom] / sum(phases.values())}
+            else:
+                byts = {"adam": 7.0 * 4 * eng.n_floats, "scatter": (3 * T + B) * (4 + 4 * D) * 2.0}.get(dom)
+                if byts:
+                    ach = byts / (phases[dom] * 1e-3) / 1e9
+                    roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                            "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"], "ms": phases[dom],
+                            "share_of_step": phases[dom] / sum(phases.values())}
+        # ---- the two graded bandwidth kernels at cfg-4 shapes (n = 8192*200 rows, D = 64) ----
+        bw = bandwidth_kernels(eng, dev, pk)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+               "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": args.workload, "model": "MTAM", "batch_per_gpu": w["B"], "global_batch": w["B"] * world,
+                          "seq_len": w["L"], "num_units": w["D"], "num_blocks": w["N"], "num_heads": w["H"],
+                          "item_count": w["items"], "user_count": w["users"], "category_count": w["cats"],
+                          "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
+                          "l2": "4 rotating batches; every step streams the 4 parameter/Adam arenas "
+                                f"({4 * 4 * eng.n_floats / 1e6:.0f} MB) through HBM, > 126 MB L2"},
+               "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
+                       "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": int(launches), "clocks": clk, "phases_ms": phases, "roofline": roof,
+               "bandwidth_kernels": bw}
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(w)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+def bandwidth_kernels(eng, dev, pk, n=8192 * 200, D=64, rows=10_000_003):
+    """Gather and scatter-add timed alone at cfg-4 shapes, inputs larger than L2."""
+    import torch
+    from mtamrecommender_b200 import engine as E
+    from mtamrecommender_b200.synth import ZipfSampler
+    res = {}
+    try:
+        table = torch.empty((rows, D), dtype=torch.float32, device=dev).uniform_(-0.3, 0.3)
+        rng = np.random.default_rng(5)
+        idx_np = ZipfSampler(rows - 3, 1.05).sample(rng, n)
+        idx_np[rng.random(n) < 0.45] = 0                      # pad id share of a ragged batch
+        idx = torch.from_numpy(idx_np).to(dev)
+        out = torch.empty((n, D), dtype=torch.float32, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def t(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(reps):
+                fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1) / reps
+        ms = t(lambda: E.gather(table, idx, out))
+        b = n * (4 + 2 * D * 4)
+        res["gather"] = {"rows": n, "D": D, "ms": ms, "achieved_GBs": b / ms / 1e6, "frac": b / ms / 1e6 / pk["hbm"],
+                         "algorithmic_bytes": b}
+        ws = torch.empty(E.scatter_add_workspace(n, rows, D), dtype=torch.uint8, device=dev)
+        dst = torch.zeros((rows, D), dtype=torch.float32, device=dev)
+        nu = int(np.unique(idx_np).size)
+        ms = t(lambda: E.scatter_add(dst, idx, out, ws), reps=5)
+        b = n * (4 + D * 4) + nu * D * 4
+        res["scatter_add"] = {"rows": n, "D": D, "unique": nu, "ms": ms, "achieved_GBs": b / ms / 1e6,
+                              "frac": b / ms / 1e6 / pk["hbm"], "algorithmic_bytes": b}
+        del table, out, dst, ws
+    except Exception as e:   # report, never hide
+        res["error"] = repr(e)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU arm (bounded sample)")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if args.steps == 20 and args.warmup == 5:
+            args.steps, args.warmup = 5, 1
+        run_reference(args, w)
+    else:
+        run_cuda(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -132,10 +132,11 @@ size_t mtam_scatter_add_workspace(int64_t n, int32_t table_rows, int32_t D);
 /* dst[idx[i],:] += rows[i,:]  for i in [0,n)  -- the gradient of tf.nn.embedding_lookup
  * (tf.gradients -> IndexedSlices -> unsorted_segment_sum, base_model.py:292,296).
  * Deterministic: stable radix sort of (idx, i) then a segmented reduction that adds the rows of
- * one index in ascending i, then one add into dst per distinct index.  If `unique_idx`/`n_unique`
+ * one index in ascending i, then one add into dst per distinct index.  `ld_rows` (>= D) is the row
+ * stride of `rows` in floats.  If `unique_idx`/`n_unique`
  * are non-null they receive the distinct indices (ascending) and their count (device). */
 int mtam_scatter_add(float* dst, int32_t table_rows, int32_t D, const int32_t* idx, const float* rows,
-                     int64_t n, void* workspace, size_t workspace_bytes, int32_t* unique_idx,
+                     int32_t ld_rows, int64_t n, void* workspace, size_t workspace_bytes, int32_t* unique_idx,
                      int32_t* n_unique, void* stream);
 
 /* ---- model --------------------------------------------------------------------------------- */
@@ -171,14 +172,45 @@ int mtam_train_step(mtam_handle h, const mtam_batch* batch, double lr, float* sc
  *     values) stay in the workspace.  scalars_out gets the local partial sums.
  *     `norm_sq_sparse` (device float[1]) += sum of squares of the local un-deduplicated sparse values.
  *  2. finish_grads: adds the sum of squares of the (already all-reduced) dense pieces to the value
- *     in norm_sq (device float[1], pre-loaded with the all-reduced sparse part), then scatter-adds the
- *     local sparse pieces into the grads arena (deterministic sort + segmented reduce).
+ *     in norm_sq (device float[1], pre-loaded with the all-reduced sparse part); if scatter_local != 0
+ *     it then scatter-adds the local sparse pieces into the grads arena (deterministic sort +
+ *     segmented reduce).  A data-parallel driver passes 0, all-gathers the pieces described by
+ *     mtam_sparse_pieces and calls mtam_scatter_add on the grads arena itself.
  *  3. apply: clip by sqrt(*norm_sq) and run Adam over the arenas; zeroes the grads arena rows it
  *     dirtied. */
 int mtam_forward_backward(mtam_handle h, const mtam_batch* batch, int32_t global_batch,
                           float* scalars_out, float* norm_sq_sparse, void* stream);
-int mtam_finish_grads(mtam_handle h, float* norm_sq, void* stream);
+int mtam_finish_grads(mtam_handle h, float* norm_sq, int32_t scatter_local, void* stream);
 int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_out, void* stream);
+
+/* Host-only half of mtam_apply: advances the Adam step and publishes lr_t in pinned memory.  Call it
+ * before replaying a CUDA graph that captured mtam_train_step / mtam_apply (the captured copy reads
+ * the pinned slot at replay time).  mtam_apply calls it itself when it has not been called. */
+int mtam_prepare_step(mtam_handle h, double lr);
+
+/* Where the sparse gradient pieces (IndexedSlices values) of the last forward_backward live. */
+typedef struct {
+  int32_t B, L, D;
+  const float* item_cat_rows;   /* [B*L, 2D]: item values in cols [0,D), category values in [D,2D) */
+  const float* position_rows;   /* [B*L, D] */
+  const float* user_rows;       /* [B, D]  (NULL-equivalent when has_user == 0) */
+  int32_t has_user;
+  uint64_t dense_begin;         /* grads arena: floats [dense_begin, param_floats) hold dense pieces */
+  uint64_t user_offset, item_offset, category_offset, position_offset;  /* table regions in the arenas */
+} mtam_sparse_view;
+int mtam_sparse_pieces(mtam_handle h, mtam_sparse_view* out);
+
+/* Per-phase device timing of a step (CUDA events on the step's stream). */
+enum {
+  MTAM_PH_EMBED_FWD = 0, MTAM_PH_GRU_X_GEMM, MTAM_PH_GRU_FWD, MTAM_PH_KV_GEMM, MTAM_PH_HOP_FWD, MTAM_PH_CE_FWD,
+  MTAM_PH_CE_BWD, MTAM_PH_HOP_BWD, MTAM_PH_HOP_PARAM_GRADS, MTAM_PH_GRU_BWD, MTAM_PH_GRU_PARAM_GRADS,
+  MTAM_PH_EMBED_BWD, MTAM_PH_DENSE_NORM, MTAM_PH_SCATTER, MTAM_PH_ADAM, MTAM_PHASE_COUNT
+};
+int mtam_profile_enable(mtam_handle h, int32_t on);
+int mtam_profile_read(mtam_handle h, float* ms_out, int32_t n);   /* ms_out[MTAM_PHASE_COUNT]; host sync */
+
+/* Kernels launched by the library since it was loaded (diagnostic). */
+long long mtam_launch_count(void);
 
 /* Full-catalogue scoring + top-k: tf.matmul(pred, item_table^T) + tf.nn.top_k (base_model.py:194-202).
  * Sorted descending, ties -> lower index.  idx_out [B,k] int32, score_out [B,k] (may be NULL).

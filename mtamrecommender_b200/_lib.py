@@ -44,12 +44,22 @@ class ParamInfo(C.Structure):
                 ("ld", C.c_int32), ("offset", C.c_uint64), ("flags", C.c_int32)]
 
 
+class SparseView(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("D", C.c_int32), ("item_cat_rows", C.c_void_p),
+                ("position_rows", C.c_void_p), ("user_rows", C.c_void_p), ("has_user", C.c_int32),
+                ("dense_begin", C.c_uint64), ("user_offset", C.c_uint64), ("item_offset", C.c_uint64),
+                ("category_offset", C.c_uint64), ("position_offset", C.c_uint64)]
+
+
+PHASES = ("embed_fwd", "gru_x_gemm", "gru_fwd", "kv_gemm", "hop_fwd", "ce_fwd", "ce_bwd", "hop_bwd",
+          "hop_param_grads", "gru_bwd", "gru_param_grads", "embed_bwd", "dense_norm", "scatter", "adam")
+
 # every symbol include/mtam.h declares: (restype, argtypes)
 _VP, _I32, _I64, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 SIGNATURES = {
     "mtam_gather": (C.c_int, [_VP, _I32, _I32, _VP, _I64, _VP, _VP]),
     "mtam_scatter_add_workspace": (_SZ, [_I64, _I32, _I32]),
-    "mtam_scatter_add": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _I64, _VP, _SZ, _VP, _VP, _VP]),
+    "mtam_scatter_add": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _I32, _I64, _VP, _SZ, _VP, _VP, _VP]),
     "mtam_plan": (C.c_int, [C.POINTER(Config), C.POINTER(Sizes)]),
     "mtam_create": (C.c_int, [C.POINTER(Config), _VP, _VP, _VP, _VP, _VP, _SZ, C.POINTER(_VP)]),
     "mtam_destroy": (C.c_int, [_VP]),
@@ -61,8 +71,13 @@ SIGNATURES = {
     "mtam_forward": (C.c_int, [_VP, C.POINTER(Batch), _VP, _VP, _VP, _VP]),
     "mtam_train_step": (C.c_int, [_VP, C.POINTER(Batch), C.c_double, _VP, _VP]),
     "mtam_forward_backward": (C.c_int, [_VP, C.POINTER(Batch), _I32, _VP, _VP, _VP]),
-    "mtam_finish_grads": (C.c_int, [_VP, _VP, _VP]),
+    "mtam_finish_grads": (C.c_int, [_VP, _VP, _I32, _VP]),
     "mtam_apply": (C.c_int, [_VP, C.c_double, _VP, _VP, _VP]),
+    "mtam_prepare_step": (C.c_int, [_VP, C.c_double]),
+    "mtam_sparse_pieces": (C.c_int, [_VP, C.POINTER(SparseView)]),
+    "mtam_profile_enable": (C.c_int, [_VP, _I32]),
+    "mtam_profile_read": (C.c_int, [_VP, _VP, _I32]),
+    "mtam_launch_count": (C.c_longlong, []),
     "mtam_eval_topk": (C.c_int, [_VP, C.POINTER(Batch), _I32, _VP, _VP, _VP]),
     "mtam_score_topk": (C.c_int, [_VP, _I32, _I32, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _SZ, _VP]),
     "mtam_score_topk_workspace": (_SZ, [_I32, _I32, _I32]),

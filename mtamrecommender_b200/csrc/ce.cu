@@ -288,6 +288,7 @@ static int ce_fwd_launch(const float* pred, const float* table, const int32_t* t
   ce_fwd_kernel<D><<<G, 256, smem, st>>>(pred, table, target, B, V, ms, tlogit);
   int nb = cdiv(B, 256);
   ce_finalize_kernel<<<nb, 256, 0, st>>>(ms, G, B, tlogit, lse, loss_origin, block_partial);
+  MTAM_LAUNCHES(1);
   MTAM_LAUNCH_CHECK();
   *n_partial = nb;
   return 0;
@@ -314,6 +315,7 @@ static int ce_bwd_launch(const float* pred, const float* table, const int32_t* t
   ce_bwd_kernel<D><<<G, 256, smem, st>>>(pred, table, target, lse, B, V, inv_batch, dTable, dpp);
   int64_t n = (int64_t)B * D;
   reduce_partials_kernel<<<cdiv(n, 256), 256, 0, st>>>(dpp, G, n, dpred);
+  MTAM_LAUNCHES(1);
   MTAM_LAUNCH_CHECK();
   return 0;
 }

@@ -21,7 +21,14 @@ int set_error(int code, const char* fmt, ...);
                                cudaGetErrorString(_e));                                      \
   } while (0)
 
-#define MTAM_LAUNCH_CHECK() MTAM_CUDA_CHECK(cudaGetLastError())
+// kernels launched by this library since load (diagnostic: bench.py reports launches per step)
+long long& launch_counter();
+#define MTAM_LAUNCHES(n) (::mtam::launch_counter() += (n))
+#define MTAM_LAUNCH_CHECK()                \
+  do {                                     \
+    MTAM_LAUNCHES(1);                      \
+    MTAM_CUDA_CHECK(cudaGetLastError());   \
+  } while (0)
 
 #define MTAM_TRY(expr)              \
   do {                              \

@@ -150,6 +150,7 @@ int exclusive_scan_i32(const int* in, int* out, int64_t n, int* tmp, int* total_
   scan_reduce_kernel<<<nb, SC_THREADS, 0, st>>>(in, n, tmp);
   scan_small_kernel<<<1, SC_THREADS, 0, st>>>(tmp, nb, total_out);
   scan_apply_kernel<<<nb, SC_THREADS, 0, st>>>(in, out, n, tmp);
+  MTAM_LAUNCHES(2);
   MTAM_LAUNCH_CHECK();
   return 0;
 }
@@ -277,6 +278,7 @@ int sort_by_row(const int32_t* idx, int64_t n, int table_rows, void* ws, size_t 
     rs_hist_kernel<<<p.nblk, RS_THREADS, 0, st>>>(kin, n, shift, hist, p.nblk);
     MTAM_TRY(exclusive_scan_i32(hist, hist, (int64_t)p.hist_ints, stmp, nullptr, st));
     rs_scatter_kernel<<<p.nblk, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist, p.nblk);
+    MTAM_LAUNCHES(1);
     MTAM_LAUNCH_CHECK();
     kin = kout;
     vin = vout;
@@ -454,6 +456,7 @@ int unique_sorted(const int32_t* keys_sorted, int64_t n, void* ws, size_t ws_byt
   head_flags_kernel<<<blocks, 256, 0, st>>>(keys_sorted, n, flags);
   MTAM_TRY(exclusive_scan_i32(flags, flags, n, tmp, n_unique, st));
   compact_heads_kernel<<<blocks, 256, 0, st>>>(keys_sorted, n, flags, unique_idx);
+  MTAM_LAUNCHES(1);
   MTAM_LAUNCH_CHECK();
   return 0;
 }
@@ -498,10 +501,11 @@ extern "C" size_t mtam_scatter_add_workspace(int64_t n, int32_t table_rows, int3
 }
 
 extern "C" int mtam_scatter_add(float* dst, int32_t table_rows, int32_t D, const int32_t* idx, const float* rows,
-                                int64_t n, void* workspace, size_t workspace_bytes, int32_t* unique_idx,
+                                int32_t ld_rows, int64_t n, void* workspace, size_t workspace_bytes, int32_t* unique_idx,
                                 int32_t* n_unique, void* stream) {
   if (!dst || n < 0 || (n > 0 && (!idx || !rows || !workspace)))
     return mtam::set_error(MTAM_ERR_INVALID, "mtam_scatter_add: null/negative argument");
-  return mtam::scatter_add_rows(dst, table_rows, D, D, idx, rows, D, n, workspace, workspace_bytes, unique_idx,
+  if (ld_rows < D) return mtam::set_error(MTAM_ERR_INVALID, "mtam_scatter_add: ld_rows < D");
+  return mtam::scatter_add_rows(dst, table_rows, D, D, idx, rows, ld_rows, n, workspace, workspace_bytes, unique_idx,
                                 n_unique, (cudaStream_t)stream);
 }

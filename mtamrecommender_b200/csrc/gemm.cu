@@ -252,6 +252,7 @@ int colsum_f32(const float* A, int lda, const float* Bmul, int ldb, int M, int N
   dim3 grid(cdiv(N, 128), P);
   colsum_partial_kernel<<<grid, 128, 0, st>>>(A, lda, Bmul, ldb, M, N, (float*)ws);
   colsum_final_kernel<<<cdiv(N, 128), 128, 0, st>>>((const float*)ws, P, N, out, accumulate);
+  MTAM_LAUNCHES(1);
   MTAM_LAUNCH_CHECK();
   return 0;
 }

@@ -67,10 +67,23 @@ struct mtam_model {
   mtam_batch last_batch;
   int last_B = 0;
   bool grads_pending = false;
+  float* lr_host = nullptr;          // pinned: lr_t of the current step (read by a captured H2D copy)
+  bool step_prepared = false;        // mtam_prepare_step already advanced the Adam state for this step
+  bool prof = false;
+  cudaEvent_t ev[MTAM_PHASE_COUNT + 1] = {};
+  bool ev_valid[MTAM_PHASE_COUNT + 1] = {};
   std::string err;
 };
 
 namespace mtam {
+
+// phase boundary marker (cudaEventRecord on the step's stream when profiling is on)
+static inline void phase(mtam_model* h, int id, cudaStream_t st) {
+  if (!h->prof) return;
+  if (!h->ev[id]) cudaEventCreate(&h->ev[id]);
+  cudaEventRecord(h->ev[id], st);
+  h->ev_valid[id] = true;
+}
 
 static size_t a4(size_t x) { return (x + 3) / 4 * 4; }
 
@@ -316,24 +329,30 @@ static int mtam_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   const int64_t T = (int64_t)B * L;
   float* P = h->params;
   int n_l2 = 0, n_ce = 0;
+  phase(h, MTAM_PH_EMBED_FWD, st);
   MTAM_TRY(embed_forward(h, bt, 1, &n_l2, st));
+  phase(h, MTAM_PH_GRU_X_GEMM, st);
   {  // x-side GRU pre-activations: [T,D] x [D,3D] + [bg|bc]
     GemmEpilogue e;
     e.bias = P + l.bgru;
     MTAM_TRY(gemm(h, 0, 0, (int)T, 3 * D, D, w.X, D, P + l.Wgru, 3 * D, w.GX, 3 * D, e, st));
   }
+  phase(h, MTAM_PH_GRU_FWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.Hs, 0, (size_t)(T + 1) * D * sizeof(float), st));
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.RH, 0, (size_t)T * D * sizeof(float), st));
   MTAM_TRY(gru_forward(D, w.X, w.GX, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, B, L, w.Hs, w.RUCT,
                        w.RH, w.Qin, st));
+  phase(h, MTAM_PH_KV_GEMM, st);
   {  // K,V of all hops: relu([T,D] x [D,2ND] + b)
     GemmEpilogue e;
     e.bias = P + l.bkv;
     e.relu = 1;
     MTAM_TRY(gemm(h, 0, 0, (int)T, 2 * N * D, D, w.X, D, P + l.Wkv, 2 * N * D, w.KV, 2 * N * D, e, st));
   }
+  phase(h, MTAM_PH_HOP_FWD, st);
   HopArgs a = hop_args(h, bt);
   MTAM_TRY(hop_forward(a, st));
+  phase(h, MTAM_PH_CE_FWD, st);
   if (!with_loss) return 0;
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.tlogit, 0, (size_t)B * sizeof(float), st));
   MTAM_TRY(ce_forward(D, w.pred, P + l.item, bt->target_item_id, B, c.item_rows, w.ce_ws, w.tlogit, w.lse,
@@ -375,9 +394,11 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   GemmEpilogue e0, eacc;
   eacc.accumulate = 1;
   // softmax CE: dense item-table gradient straight into the arena, dpred
+  phase(h, MTAM_PH_CE_BWD, st);
   MTAM_TRY(ce_backward(D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
                        w.ce_ws, G + l.item, w.dpred, st));
   // hops
+  phase(h, MTAM_PH_HOP_BWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.dX, 0, (size_t)T * D * sizeof(float), st));
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.dKV, 0, (size_t)T * 2 * N * D * sizeof(float), st));
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.GB, 0, (size_t)B * 5 * N * L * sizeof(float), st));
@@ -389,6 +410,7 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   g.DQT = w.DQT; g.GB = w.GB; g.dq0 = w.dq0;
   MTAM_TRY(hop_backward(a, g, st));
   // hop parameter gradients
+  phase(h, MTAM_PH_HOP_PARAM_GRADS, st);
   MTAM_TRY(colsum(h, w.dpred, D, nullptr, 0, B, D, G + l.lnfb, st));
   MTAM_TRY(colsum(h, w.dpred, D, w.XHF, D, B, D, G + l.lnfg, st));
   MTAM_TRY(colsum(h, w.DOUT, N * D, nullptr, 0, B, N * D, G + l.lnb, st));
@@ -404,9 +426,11 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   MTAM_TRY(gemm(h, 1, 0, D, 2 * N * D, (int)T, w.X, D, w.dKV, 2 * N * D, G + l.Wkv, 2 * N * D, e0, st));
   MTAM_TRY(gemm(h, 0, 1, (int)T, D, 2 * N * D, w.dKV, 2 * N * D, P + l.Wkv, 2 * N * D, w.dX, D, eacc, st));
   // T-GRU
+  phase(h, MTAM_PH_GRU_BWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.dGX, 0, (size_t)T * 3 * D * sizeof(float), st));
   MTAM_TRY(gru_backward(D, w.X, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, w.Hs, w.RUCT, w.dq0, B, L,
                         w.dGX, w.dX, w.vec_partial, st));
+  phase(h, MTAM_PH_GRU_PARAM_GRADS, st);
   MTAM_TRY(colsum(h, w.vec_partial, 8 * D, nullptr, 0, gru_num_blocks(B), 8 * D, G + l.gruvec, st));
   MTAM_TRY(colsum(h, w.dGX, 3 * D, nullptr, 0, (int)T, 3 * D, G + l.bgru, st));
   MTAM_TRY(gemm(h, 1, 0, D, 3 * D, (int)T, w.X, D, w.dGX, 3 * D, G + l.Wgru, 3 * D, e0, st));
@@ -414,7 +438,9 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   MTAM_TRY(gemm(h, 1, 0, D, 2 * D, (int)T, w.Hs, D, w.dGX, 3 * D, G + l.Wgru + (size_t)D * 3 * D, 3 * D, e0, st));
   MTAM_TRY(gemm(h, 1, 0, D, D, (int)T, w.RH, D, w.dGX + 2 * D, 3 * D, G + l.Wgru + (size_t)D * 3 * D + 2 * D, 3 * D, e0, st));
   MTAM_TRY(gemm(h, 0, 1, (int)T, D, 3 * D, w.dGX, 3 * D, P + l.Wgru, 3 * D, w.dX, D, eacc, st));
+  phase(h, MTAM_PH_EMBED_BWD, st);
   MTAM_TRY(embed_backward(h, bt, 1, norm_sq_sparse, st));
+  phase(h, MTAM_PH_DENSE_NORM, st);
   return 0;
 }
 
@@ -484,12 +510,21 @@ int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam
     return s;
   }
   h->params = params; h->grads = grads; h->m = adam_m; h->v = adam_v;
+  if (cudaMallocHost((void**)&h->lr_host, 64) != cudaSuccess) {
+    delete h;
+    return set_error(MTAM_ERR_CUDA, "cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   memset(&h->last_batch, 0, sizeof(h->last_batch));
   *out = h;
   return 0;
 }
 
 int mtam_destroy(mtam_handle h) {
+  if (h) {
+    if (h->lr_host) cudaFreeHost(h->lr_host);
+    for (int i = 0; i <= MTAM_PHASE_COUNT; ++i)
+      if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  }
   delete h;
   return 0;
 }
@@ -515,6 +550,50 @@ int mtam_set_adam_step(mtam_handle h, int64_t t) {
   h->adam_t = t;
   h->b1_pow = 1.f; h->b2_pow = 1.f;
   for (int64_t i = 0; i < t; ++i) { h->b1_pow *= h->cfg.beta1; h->b2_pow *= h->cfg.beta2; }
+  return 0;
+}
+
+int mtam_prepare_step(mtam_handle h, double lr) {
+  if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
+  h->adam_t += 1;
+  h->b1_pow *= h->cfg.beta1;
+  h->b2_pow *= h->cfg.beta2;
+  const float lr32 = (float)lr;  // float64 placeholder cast to fp32 (base_model.py:25)
+  *h->lr_host = lr32 * sqrtf(1.f - h->b2_pow) / (1.f - h->b1_pow);
+  h->step_prepared = true;
+  return 0;
+}
+
+int mtam_profile_enable(mtam_handle h, int32_t on) {
+  if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
+  h->prof = on != 0;
+  for (int i = 0; i <= MTAM_PHASE_COUNT; ++i) h->ev_valid[i] = false;
+  return 0;
+}
+
+int mtam_profile_read(mtam_handle h, float* ms_out, int32_t n) {
+  if (!h || !ms_out || n < MTAM_PHASE_COUNT) return set_error(MTAM_ERR_INVALID, "mtam_profile_read: bad argument");
+  if (!h->ev_valid[MTAM_PHASE_COUNT]) return set_error(MTAM_ERR_INVALID, "no profiled step recorded");
+  MTAM_CUDA_CHECK(cudaEventSynchronize(h->ev[MTAM_PHASE_COUNT]));
+  for (int i = 0; i < MTAM_PHASE_COUNT; ++i) {
+    ms_out[i] = 0.f;
+    if (!h->ev_valid[i]) continue;
+    int j = i + 1;
+    while (j < MTAM_PHASE_COUNT && !h->ev_valid[j]) ++j;
+    MTAM_CUDA_CHECK(cudaEventElapsedTime(&ms_out[i], h->ev[i], h->ev[j]));
+  }
+  return 0;
+}
+
+int mtam_sparse_pieces(mtam_handle h, mtam_sparse_view* out) {
+  if (!h || !out) return set_error(MTAM_ERR_INVALID, "null argument");
+  memset(out, 0, sizeof(*out));
+  out->B = h->last_B; out->L = h->cfg.L; out->D = h->cfg.D;
+  out->item_cat_rows = h->ws.dE2; out->position_rows = h->ws.dEp; out->user_rows = h->ws.dEu;
+  out->dense_begin = h->lay.dense_begin;
+  out->user_offset = h->lay.user; out->item_offset = h->lay.item; out->category_offset = h->lay.cat;
+  out->position_offset = h->lay.pos;
+  out->has_user = h->cfg.kind != MTAM_KIND_PISTREC;
   return 0;
 }
 
@@ -546,7 +625,7 @@ int mtam_forward_backward(mtam_handle h, const mtam_batch* batch, int32_t global
   return 0;
 }
 
-int mtam_finish_grads(mtam_handle h, float* norm_sq, void* stream) {
+int mtam_finish_grads(mtam_handle h, float* norm_sq, int32_t scatter_local, void* stream) {
   if (!h || !norm_sq) return set_error(MTAM_ERR_INVALID, "null argument");
   if (!h->grads_pending) return set_error(MTAM_ERR_INVALID, "mtam_finish_grads without a pending forward_backward");
   cudaStream_t st = (cudaStream_t)stream;
@@ -561,6 +640,8 @@ int mtam_finish_grads(mtam_handle h, float* norm_sq, void* stream) {
   int np = 0;
   MTAM_TRY(sumsq_partials(h->grads + l.dense_begin, (int64_t)(l.total - l.dense_begin), w.norm_partial, &np, st));
   MTAM_TRY(finalize_sum(w.norm_partial, np, 1.0f, norm_sq, 1, st));
+  phase(h, MTAM_PH_SCATTER, st);
+  if (!scatter_local) return 0;
   float* G = h->grads;
   MTAM_TRY(scatter_add_rows(G + l.item, c.item_rows, D, D, bt.item_list, w.dE2, 2 * D, T, w.scatter_ws,
                             w.scatter_ws_bytes, nullptr, nullptr, st));
@@ -583,12 +664,11 @@ int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_ou
   Workspace& w = h->ws;
   float* ds = w.dev_scalars;
   MTAM_TRY(clip_scale(norm_sq, c.clip, ds + MTAM_S_GLOBAL_NORM, ds + MTAM_S_CLIP_SCALE, st));
-  h->adam_t += 1;
-  h->b1_pow *= c.beta1;
-  h->b2_pow *= c.beta2;
-  const float lr32 = (float)lr;  // float64 placeholder cast to fp32 (base_model.py:25)
-  const float lr_t = lr32 * sqrtf(1.f - h->b2_pow) / (1.f - h->b1_pow);
-  MTAM_TRY(adam_apply(h->params, h->m, h->v, h->grads, (int64_t)l.total, ds + MTAM_S_CLIP_SCALE, lr_t, c.beta1, c.beta2,
+  phase(h, MTAM_PH_ADAM, st);
+  if (!h->step_prepared) MTAM_TRY(mtam_prepare_step(h, lr));
+  h->step_prepared = false;
+  MTAM_CUDA_CHECK(cudaMemcpyAsync(ds + 9, h->lr_host, sizeof(float), cudaMemcpyHostToDevice, st));
+  MTAM_TRY(adam_apply(h->params, h->m, h->v, h->grads, (int64_t)l.total, ds + MTAM_S_CLIP_SCALE, ds + 9, c.beta1, c.beta2,
                       c.eps, st));
   // restore the invariant "sparse-only table regions of the grads arena are zero"
   MTAM_CUDA_CHECK(cudaMemsetAsync(h->grads + l.cat, 0, (l.dense_begin - l.cat) * sizeof(float), st));
@@ -597,6 +677,7 @@ int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_ou
     MTAM_CUDA_CHECK(cudaMemcpyAsync(scalars_out + MTAM_S_GLOBAL_NORM, ds + MTAM_S_GLOBAL_NORM, 2 * sizeof(float),
                                     cudaMemcpyDeviceToDevice, st));
   h->grads_pending = false;
+  phase(h, MTAM_PHASE_COUNT, st);
   return 0;
 }
 
@@ -615,7 +696,7 @@ int mtam_train_step(mtam_handle h, const mtam_batch* batch, double lr, float* sc
   float* nsq = h->ws.dev_scalars + 8;
   MTAM_CUDA_CHECK(cudaMemsetAsync(nsq, 0, sizeof(float), st));
   MTAM_TRY(mtam_forward_backward(h, batch, batch->B, scalars_out, nsq, stream));
-  MTAM_TRY(mtam_finish_grads(h, nsq, stream));
+  MTAM_TRY(mtam_finish_grads(h, nsq, 1, stream));
   MTAM_TRY(mtam_apply(h, lr, nsq, scalars_out, stream));
   return 0;
 }

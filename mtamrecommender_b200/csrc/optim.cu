@@ -54,8 +54,9 @@ int clip_scale(const float* norm_sq, float clip, float* gn_out, float* scale_out
 
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v,
                                                    const float4* __restrict__ g, int64_t n4, const float* __restrict__ scale_p,
-                                                   float lr_t, float b1, float b2, float eps) {
+                                                   const float* __restrict__ lr_t_p, float b1, float b2, float eps) {
   const float sc = scale_p[0];
+  const float lr_t = lr_t_p[0];
   const float ob1 = 1.f - b1, ob2 = 1.f - b2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float
 }
 
 // arenas are padded to a multiple of 4 floats by the planner
-int adam_apply(float* w, float* m, float* v, const float* g, int64_t n, const float* scale_p, float lr_t, float b1,
+int adam_apply(float* w, float* m, float* v, const float* g, int64_t n, const float* scale_p, const float* lr_t, float b1,
                float b2, float eps, cudaStream_t st) {
   int64_t n4 = n / 4;
   int blocks = std::max(1, (int)std::min<int64_t>(cdiv(n4, 256), kNumSMs * 8));

@@ -8,6 +8,10 @@ std::string& last_error_slot() {
   static thread_local std::string s;
   return s;
 }
+long long& launch_counter() {
+  static long long n = 0;
+  return n;
+}
 int set_error(int code, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -18,3 +22,5 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 }  // namespace mtam
+
+extern "C" long long mtam_launch_count(void) { return mtam::launch_counter(); }

@@ -248,8 +248,9 @@ class Engine:
                                              self.scalars.data_ptr(), self.norm_sq.data_ptr(), self._stream()),
               "mtam_forward_backward")
 
-    def finish_grads(self) -> None:
-        check(self.lib.mtam_finish_grads(self.h, self.norm_sq.data_ptr(), self._stream()), "mtam_finish_grads")
+    def finish_grads(self, scatter_local: bool = True) -> None:
+        check(self.lib.mtam_finish_grads(self.h, self.norm_sq.data_ptr(), 1 if scatter_local else 0, self._stream()),
+              "mtam_finish_grads")
 
     def apply(self, lr: float) -> None:
         check(self.lib.mtam_apply(self.h, float(lr), self.norm_sq.data_ptr(), self.scalars.data_ptr(), self._stream()),
@@ -268,6 +269,45 @@ class Engine:
         # drop the pending flag by applying a zero-lr step on zero grads would change Adam state;
         # instead recreate nothing: the next forward_backward simply overwrites.
         return out
+
+    # ---- profiling / diagnostics --------------------------------------------------------------
+    def profile_step(self, batch: DeviceBatch, lr: float) -> Dict[str, float]:
+        """One train step with CUDA-event phase markers; returns milliseconds per phase."""
+        check(self.lib.mtam_profile_enable(self.h, 1), "mtam_profile_enable")
+        try:
+            self.train_step_device(batch, lr)
+            ms = (C.c_float * len(_lib.PHASES))()
+            check(self.lib.mtam_profile_read(self.h, ms, len(_lib.PHASES)), "mtam_profile_read")
+        finally:
+            check(self.lib.mtam_profile_enable(self.h, 0), "mtam_profile_enable")
+        return {k: float(ms[i]) for i, k in enumerate(_lib.PHASES)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.mtam_launch_count())
+
+    # ---- CUDA graph of the whole step ----------------------------------------------------------
+    def capture_train_graph(self, B: int) -> None:
+        """Captures mtam_train_step on the staging batch buffers (fixed addresses) into a CUDA graph.
+        `train_step_graph` then only advances the host-side Adam state and replays it."""
+        batch = DeviceBatch({k: v[:B] for k, v in self._dev.items()}, B)
+        t0 = self.adam_step()
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.train_step_device(batch, 0.0)       # warm-up outside capture: sets func attributes
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        raise_if = None
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            self.train_step_device(batch, 0.0)
+        self.set_adam_step(t0)
+        self._graph, self._graph_B = g, B
+        return raise_if
+
+    def train_step_graph(self, lr: float) -> None:
+        check(self.lib.mtam_prepare_step(self.h, float(lr)), "mtam_prepare_step")
+        self._graph.replay()
 
     def eval_topk_device(self, batch: DeviceBatch, k: int = 50):
         idx = torch.empty((batch.B, k), dtype=torch.int32, device=self.device)
@@ -308,7 +348,8 @@ def scatter_add(dst: torch.Tensor, idx: torch.Tensor, rows: torch.Tensor, worksp
         workspace = torch.empty(max(scatter_add_workspace(n, R, D), 16), dtype=torch.uint8, device=dst.device)
     uniq = torch.empty(max(n, 1), dtype=torch.int32, device=dst.device) if want_unique else None
     nuniq = torch.zeros(1, dtype=torch.int32, device=dst.device) if want_unique else None
-    check(lib.mtam_scatter_add(dst.data_ptr(), R, D, idx.data_ptr(), rows.data_ptr(), n, workspace.data_ptr(),
+    check(lib.mtam_scatter_add(dst.data_ptr(), R, D, idx.data_ptr(), rows.data_ptr(), rows.stride(0), n,
+                               workspace.data_ptr(),
                                workspace.numel(), uniq.data_ptr() if want_unique else None,
                                nuniq.data_ptr() if want_unique else None,
                                torch.cuda.current_stream(dst.device).cuda_stream), "mtam_scatter_add")

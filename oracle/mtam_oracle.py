@@ -485,8 +485,8 @@ class OracleTrainer:
             self.params[k] = w.astype(self.params[k].dtype)
             self.m[k] = m.astype(self.params[k].dtype)
             self.v[k] = v.astype(self.params[k].dtype)
-        self.last = dict(loss=float(fwd["loss"]), global_norm=gn, scale=sc, grads=grads)
-        return float(fwd["loss"])
+        self.last = dict(loss=float(fwd["loss"].detach()), global_norm=gn, scale=sc, grads=grads)
+        return float(fwd["loss"].detach())
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,139 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances (fp32 kernels vs fp64 oracle): loss rel 1e-5, pred 1e-5,
+gradients norm-wise rel 1e-4, weights after 3 Adam steps rel 1e-4; indices exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mtam_oracle as O  # noqa: E402
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def make(D, L, N, H, B, items, users, cats, seed=7, min_len=2):
+    from mtamrecommender_b200 import engine as E
+    cfg = O.OracleConfig(kind=O.MTAM, L=L, D=D, H=H, N=N, user_count=users, item_count=items, category_count=cats)
+    P = O.init_params(cfg, seed)
+    rng = np.random.default_rng(seed + 1)
+    for k in P:   # non-trivial biases so their gradients are exercised
+        if k.endswith("/bias") or k.endswith("/beta"):
+            P[k] = (P[k] + 0.1 * rng.standard_normal(P[k].shape)).astype(np.float32)
+    feed = O.synth_batch(cfg, B, seed + 2, min_len=min_len)
+    eng = E.Engine(E.ModelConfig(kind="MTAM", max_batch=B, L=L, D=D, H=H, N=N, user_count=users, item_count=items,
+                                 category_count=cats))
+    eng.set_params(P)
+    return cfg, P, feed, eng
+
+
+CASES = [dict(D=64, L=12, N=2, H=1, B=37, items=500, users=50, cats=11),
+         dict(D=128, L=50, N=3, H=8, B=64, items=3706, users=300, cats=301),     # ml-1m-shaped (cfg1), 8 heads
+         dict(D=32, L=7, N=1, H=4, B=5, items=90, users=9, cats=4),
+         dict(D=64, L=50, N=6, H=1, B=130, items=5000, users=1000, cats=100)]    # cfg3-shaped hops, ragged tiles
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_parity(case):
+    cfg, P, feed, eng = make(**case)
+    fwd = O.forward(cfg, {k: __import__("torch").tensor(v, dtype=__import__("torch").float64) for k, v in P.items()}, feed)
+    out = eng.forward(feed)
+    assert abs(out["loss"] - float(fwd["loss"])) <= 1e-5 * abs(float(fwd["loss"]))
+    assert abs(out["l2_norm"] - float(fwd["l2_norm"])) <= 1e-5 * float(fwd["l2_norm"])
+    assert rel(out["loss_origin"], fwd["loss_origin"].numpy()) < 1e-5
+    assert rel(out["pred"], fwd["pred"].numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_gradient_parity(case):
+    cfg, P, feed, eng = make(**case)
+    fwd, grads, pieces = O.loss_and_grads(cfg, P, feed)
+    g = eng.gradients(feed)
+    gn = O.global_norm(pieces)
+    assert abs(np.sqrt(g["__norm_sq__"]) - gn) <= 1e-5 * gn          # un-deduplicated global norm (trap T1)
+    for k, v in grads.items():
+        if v is None:
+            assert not np.any(g[k]), f"{k}: dead parameter received a gradient"
+        else:
+            assert rel(g[k], v) < 1e-4, (k, rel(g[k], v))
+
+
+@pytest.mark.parametrize("case", CASES[:3])
+def test_three_train_steps(case):
+    cfg, P, feed, eng = make(**case)
+    tr = O.OracleTrainer(cfg, P)
+    for s in range(3):
+        lo, lc = tr.train_step(feed, 1e-3), eng.train_step(feed, 1e-3)
+        assert abs(lo - lc) <= 2e-5 * abs(lo), (s, lo, lc)
+    newp = eng.get_params()
+    for k, v in tr.params.items():
+        assert rel(newp[k], v) < 1e-4, (k, rel(newp[k], v))
+    assert eng.adam_step() == 3
+
+
+def test_min_length_two_and_full_length():
+    """seq_length == 2 (one real event + mask step) and == L."""
+    cfg, P, feed, eng = make(D=64, L=6, N=2, H=2, B=8, items=50, users=9, cats=4)
+    feed["seq_length"][:4] = 2
+    for k in ("item_list", "category_list", "position_list", "time_list", "timelast_list", "timenow_list"):
+        feed[k][:4, 2:] = 0
+    feed["item_list"][:4, 1] = cfg.item_count + 1
+    feed["category_list"][:4, 1] = cfg.category_count + 1
+    feed["position_list"][:4, 1] = 1
+    fwd, grads, pieces = O.loss_and_grads(cfg, P, feed)
+    g = eng.gradients(feed)
+    for k, v in grads.items():
+        if v is not None:
+            assert rel(g[k], v) < 1e-4, k
+
+
+def test_train_step_is_deterministic():
+    cfg, P, feed, eng = make(D=64, L=20, N=2, H=1, B=50, items=800, users=60, cats=13)
+    eng.train_step(feed, 1e-3)
+    a = eng.params.clone()
+    eng.set_params(P); eng.adam_m.zero_(); eng.adam_v.zero_(); eng.set_adam_step(0)
+    eng.train_step(feed, 1e-3)
+    assert bool((a == eng.params).all()), "two identical steps from identical state differ bitwise"
+
+
+def test_topk_matches_oracle_and_metrics():
+    cfg, P, feed, eng = make(D=64, L=12, N=2, H=1, B=40, items=3000, users=50, cats=11)
+    b = eng.upload(feed)
+    idx, sc = eng.eval_topk_device(b, 50)
+    m, oidx, oscores = O.metrics_topk(cfg, P, feed)
+    # gap condition: only rows whose oracle scores at ranks <= 51 are separated by more
+    # than the fp32 error bound are required to match exactly; report how many that is.
+    srt = -np.sort(-oscores, axis=1)[:, :51]
+    gap_ok = (np.abs(np.diff(srt, axis=1)).min(axis=1) > 1e-5)
+    assert gap_ok.mean() > 0.9
+    assert np.array_equal(idx.cpu().numpy()[gap_ok], oidx[gap_ok])
+    got = eng.hr_ndcg_device(idx, b.t["target_item_id"]).cpu().numpy()
+    assert np.allclose(got, np.array(m), atol=1e-6)
+
+
+def test_cuda_graph_step_matches_eager():
+    import torch
+    cfg, P, feed, eng = make(D=64, L=12, N=2, H=1, B=32, items=500, users=50, cats=11)
+    eng.train_step(feed, 1e-3); eng.train_step(feed, 5e-4)
+    ref = eng.params.clone()
+    eng.set_params(P); eng.adam_m.zero_(); eng.adam_v.zero_(); eng.set_adam_step(0); eng.grads.zero_()
+    eng.upload(feed)
+    eng.capture_train_graph(32)
+    eng.set_params(P); eng.adam_m.zero_(); eng.adam_v.zero_(); eng.set_adam_step(0); eng.grads.zero_()
+    eng.upload(feed)
+    eng.train_step_graph(1e-3); eng.train_step_graph(5e-4)
+    torch.cuda.synchronize()
+    assert bool((ref == eng.params).all())
+    assert eng.adam_step() == 2
+
+
+def test_errors_are_loud():
+    from mtamrecommender_b200 import engine as E, _lib
+    with pytest.raises(_lib.MtamError):
+        E.Engine(E.ModelConfig(kind="MTAM", max_batch=4, L=5, D=48, H=1, N=1, user_count=3, item_count=9, category_count=2))
+    cfg, P, feed, eng = make(D=32, L=7, N=1, H=4, B=5, items=90, users=9, cats=4)
+    big = {k: np.concatenate([v, v]) for k, v in feed.items()}
+    with pytest.raises(ValueError):
+        eng.train_step(big, 1e-3)
