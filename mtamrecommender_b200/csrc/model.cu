@@ -16,13 +16,6 @@
 
 namespace mtam {
 
-struct ParamDesc {
-  std::string name;
-  int rows, cols, ndim, ld;
-  size_t off;
-  int flags;
-};
-
 static const char* kGruLive[8] = {"_time_kernel_w1", "_time_kernel_b1", "_time_history_w1", "_time_w1",
                                   "_time_b1", "_time_kernel_w2", "_time_w12", "_time_b12"};
 static const char* kGruDead[6] = {"_time_history_b1", "_time_kernel_b2", "_time_history_w2",
@@ -36,6 +29,7 @@ struct Layout {
   size_t user = 0, cat = 0, pos = 0, dense_begin = 0, item = 0, Wemb = 0, Wgru = 0, bgru = 0, gruvec = 0, Wq = 0,
          bq = 0, Wkv = 0, bkv = 0, Wt = 0, gate = 0, gate_dead = 0, lnb = 0, lng = 0, lnfb = 0, lnfg = 0, item_b = 0,
          total = 0;
+  SaLayout sa;
   std::vector<ParamDesc> params;
 };
 
@@ -157,7 +151,9 @@ static int build_layout(const mtam_config& c, Layout& l) {
     return 0;
   }
   // self-attention family (PISTRec / SASRec / TA-SASRec / TiSASRec)
-  MTAM_TRY(sa_build_layout(c, o, l.params, l.lnfb, l.lnfg));
+  MTAM_TRY(sa_build_layout(c, o, l.params, l.sa));
+  l.lnfb = l.sa.lnfb;
+  l.lnfg = l.sa.lnfg;
   l.total = a4(o);
   return 0;
 }
@@ -223,7 +219,7 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
     w.sa_ws_bytes = sa_workspace_bytes(c);
     w.sa_ws = b.take<char>(w.sa_ws_bytes);
     G(D, 3 * D, T); G(D, D, T);
-    CS(T, 3 * D); CS(T, D); CS(B, D); CS(B, L * L); CS(T, L);
+    CS(T, 3 * D); CS(T, D); CS(B, D); CS(B, 5 * L * L); CS(T, L);
   }
   w.ce_ws_bytes = ce_workspace_bytes(B, D, c.item_rows);
   w.ce_ws = b.take<char>(w.ce_ws_bytes);
@@ -444,6 +440,52 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// self-attention family: PISTRec / SASRec / TA-SASRec / TiSASRec
+// ---------------------------------------------------------------------------------------------
+static SaCtx sa_ctx(mtam_model* h, const mtam_batch* bt) {
+  SaCtx c;
+  c.cfg = h->cfg; c.sl = h->lay.sa; c.params = h->params; c.grads = h->grads; c.bt = bt;
+  c.X = h->ws.X; c.dX = h->ws.dX; c.pred = h->ws.pred; c.dpred = h->ws.dpred; c.XHF = h->ws.XHF; c.RSTDF = h->ws.RSTDF;
+  c.ws = h->ws.sa_ws; c.ws_bytes = h->ws.sa_ws_bytes;
+  c.gemm_ws = h->ws.gemm_ws; c.gemm_ws_bytes = h->ws.gemm_ws_bytes;
+  c.colsum_ws = h->ws.colsum_ws; c.colsum_ws_bytes = h->ws.colsum_ws_bytes;
+  return c;
+}
+
+static int sa_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float* scalars_out, bool with_loss,
+                  cudaStream_t st) {
+  const mtam_config& c = h->cfg;
+  Workspace& w = h->ws;
+  const int include_user = c.kind != MTAM_KIND_PISTREC;   // PISTRec_model.py:56-60 omits the user L2 term
+  int n_l2 = 0, n_ce = 0;
+  phase(h, MTAM_PH_EMBED_FWD, st);
+  MTAM_TRY(embed_forward(h, bt, include_user, &n_l2, st));
+  phase(h, MTAM_PH_HOP_FWD, st);
+  MTAM_TRY(sa_forward(sa_ctx(h, bt), st));
+  phase(h, MTAM_PH_CE_FWD, st);
+  if (!with_loss) return 0;
+  MTAM_CUDA_CHECK(cudaMemsetAsync(w.tlogit, 0, (size_t)bt->B * sizeof(float), st));
+  MTAM_TRY(ce_forward(c.D, w.pred, h->params + h->lay.item, bt->target_item_id, bt->B, c.item_rows, w.ce_ws, w.tlogit,
+                      w.lse, w.loss_origin, w.ce_partial, &n_ce, st));
+  MTAM_TRY(loss_scalars(h, n_l2, n_ce, global_batch, scalars_out, st));
+  return 0;
+}
+
+static int sa_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float* norm_sq_sparse, cudaStream_t st) {
+  const mtam_config& c = h->cfg;
+  Workspace& w = h->ws;
+  phase(h, MTAM_PH_CE_BWD, st);
+  MTAM_TRY(ce_backward(c.D, w.pred, h->params + h->lay.item, bt->target_item_id, w.lse, bt->B, c.item_rows,
+                       1.0f / (float)global_batch, w.ce_ws, h->grads + h->lay.item, w.dpred, st));
+  phase(h, MTAM_PH_HOP_BWD, st);
+  MTAM_TRY(sa_backward(sa_ctx(h, bt), st));
+  phase(h, MTAM_PH_EMBED_BWD, st);
+  MTAM_TRY(embed_backward(h, bt, c.kind != MTAM_KIND_PISTREC, norm_sq_sparse, st));
+  phase(h, MTAM_PH_DENSE_NORM, st);
+  return 0;
+}
+
 static int check_batch(mtam_model* h, const mtam_batch* bt) {
   if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
   if (!bt) return set_error(MTAM_ERR_INVALID, "null batch");
@@ -460,13 +502,14 @@ static int fwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* scal
   switch (h->cfg.kind) {
     case MTAM_KIND_MTAM: return mtam_fwd(h, bt, gb, scalars_out, with_loss, st);
     case MTAM_KIND_BPRMF: return set_error(MTAM_ERR_UNSUPPORTED, "BPRMF is not built yet");
-    default: return set_error(MTAM_ERR_UNSUPPORTED, "self-attention models are not built yet");
+    default: return sa_fwd(h, bt, gb, scalars_out, with_loss, st);
   }
 }
 static int bwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* nsq, cudaStream_t st) {
   switch (h->cfg.kind) {
     case MTAM_KIND_MTAM: return mtam_bwd(h, bt, gb, nsq, st);
-    default: return set_error(MTAM_ERR_UNSUPPORTED, "model kind %d backward is not built yet", h->cfg.kind);
+    case MTAM_KIND_BPRMF: return set_error(MTAM_ERR_UNSUPPORTED, "BPRMF is not built yet");
+    default: return sa_bwd(h, bt, gb, nsq, st);
   }
 }
 
