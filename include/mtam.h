@@ -183,6 +183,10 @@ int mtam_forward_backward(mtam_handle h, const mtam_batch* batch, int32_t global
 int mtam_finish_grads(mtam_handle h, float* norm_sq, int32_t scatter_local, void* stream);
 int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_out, void* stream);
 
+/* BPR-MF only: fixes the negative item id that `tf.random_uniform([1], 0, item_count)` (BPRMF.py:43) would
+ * draw, so a run can be reproduced; item_id < 0 restores the per-step draw from the handle's own generator. */
+int mtam_set_bpr_negative(mtam_handle h, int32_t item_id);
+
 /* Host-only half of mtam_apply: advances the Adam step and publishes lr_t in pinned memory.  Call it
  * before replaying a CUDA graph that captured mtam_train_step / mtam_apply (the captured copy reads
  * the pinned slot at replay time).  mtam_apply calls it itself when it has not been called. */

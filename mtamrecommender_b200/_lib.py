@@ -73,6 +73,7 @@ SIGNATURES = {
     "mtam_forward_backward": (C.c_int, [_VP, C.POINTER(Batch), _I32, _VP, _VP, _VP]),
     "mtam_finish_grads": (C.c_int, [_VP, _VP, _I32, _VP]),
     "mtam_apply": (C.c_int, [_VP, C.c_double, _VP, _VP, _VP]),
+    "mtam_set_bpr_negative": (C.c_int, [_VP, _I32]),
     "mtam_prepare_step": (C.c_int, [_VP, C.c_double]),
     "mtam_sparse_pieces": (C.c_int, [_VP, C.POINTER(SparseView)]),
     "mtam_profile_enable": (C.c_int, [_VP, _I32]),

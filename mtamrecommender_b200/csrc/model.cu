@@ -42,6 +42,8 @@ struct Workspace {
   float *dpred, *dX, *dKV, *DOUT, *DQP, *DQT, *GB, *dq0, *WqT, *WtT, *dGX, *vec_partial, *dR, *dE2, *dEp, *dEu;
   // partial-sum buffers and device scalars
   float *l2_partial, *sq_partial, *ce_partial, *norm_partial, *dev_scalars;  // dev_scalars: [16]
+  float *bU, *bIP, *bdot, *bbpos, *browsum, *bcolsum, *bloss, *bdU, *bdIP, *bdINp, *bdIN, *bdbneg, *bl2, *bsq;  // BPRMF
+  int32_t* bneg_idx;
   void *ce_ws, *gemm_ws, *colsum_ws, *scatter_ws, *sa_ws, *topk_ws;
   size_t ce_ws_bytes, gemm_ws_bytes, colsum_ws_bytes, scatter_ws_bytes, sa_ws_bytes, topk_ws_bytes;
   size_t total_bytes;
@@ -64,6 +66,9 @@ struct mtam_model {
   float* lr_host = nullptr;          // pinned: lr_t of the current step (read by a captured H2D copy)
   bool step_prepared = false;        // mtam_prepare_step already advanced the Adam state for this step
   bool prof = false;
+  int bpr_neg = -1;                  // injected negative item id (mtam_set_bpr_negative); -1: draw one per step
+  int bpr_neg_used = 0;
+  uint64_t rng = 1234;
   cudaEvent_t ev[MTAM_PHASE_COUNT + 1] = {};
   bool ev_valid[MTAM_PHASE_COUNT + 1] = {};
   std::string err;
@@ -215,7 +220,13 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
     w.vec_partial = b.take<float>((int64_t)gru_num_blocks(B) * 8 * D);
     G(D, 2 * N * D, T); G(D, 3 * D, T); G(D, 2 * D, T); G(D, D, T); G(D, D, B);
     CS(T, 2 * N * D); CS(T, 3 * D); CS(B, 5 * N * L); CS(B, N * D); CS(gru_num_blocks(B), 8 * D); CS(B, D);
-  } else if (c.kind != MTAM_KIND_BPRMF) {
+  } else if (c.kind == MTAM_KIND_BPRMF) {
+    w.bU = b.take<float>(B * D); w.bIP = b.take<float>(B * D); w.bdU = b.take<float>(B * D);
+    w.bdIP = b.take<float>(B * D); w.bdINp = b.take<float>(B * D); w.bdIN = b.take<float>(D);
+    w.bdot = b.take<float>(B); w.bbpos = b.take<float>(B); w.browsum = b.take<float>(B); w.bcolsum = b.take<float>(B);
+    w.bloss = b.take<float>(B); w.bdbneg = b.take<float>(4); w.bl2 = b.take<float>(cdiv(B, 4) + 2);
+    w.bsq = b.take<float>(cdiv(B, 4) + 2); w.bneg_idx = b.take<int32_t>(4);
+  } else {
     w.sa_ws_bytes = sa_workspace_bytes(c);
     w.sa_ws = b.take<char>(w.sa_ws_bytes);
     G(D, 3 * D, T); G(D, D, T);
@@ -232,6 +243,7 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
   sc = std::max(sc, scatter_add_workspace_bytes(T, c.category_rows, D));
   sc = std::max(sc, scatter_add_workspace_bytes(T, c.position_rows, D));
   sc = std::max(sc, scatter_add_workspace_bytes(B, c.user_rows, D));
+  sc = std::max(sc, scatter_add_workspace_bytes(B, c.item_rows, D));
   w.scatter_ws_bytes = sc;
   w.scatter_ws = b.take<char>(sc);
   w.topk_ws_bytes = score_topk_workspace_bytes((int)B, c.item_rows, std::min(50, c.item_rows));
@@ -486,6 +498,70 @@ static int sa_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float* 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// BPR-MF
+// ---------------------------------------------------------------------------------------------
+static BprArgs bpr_args(mtam_model* h, const mtam_batch* bt) {
+  Workspace& w = h->ws;
+  const Layout& l = h->lay;
+  BprArgs a;
+  a.B = bt->B; a.D = h->cfg.D; a.neg = h->bpr_neg_used;
+  a.Tu = h->params + l.user; a.Ti = h->params + l.item; a.Tb = h->params + l.item_b;
+  a.user = bt->user_id; a.target = bt->target_item_id;
+  a.U = w.bU; a.IP = w.bIP; a.dot = w.bdot; a.bpos = w.bbpos; a.rowsum = w.browsum; a.colsum = w.bcolsum;
+  a.loss_partial = w.bloss; a.dU = w.bdU; a.dIP = w.bdIP; a.dINpart = w.bdINp; a.dIN = w.bdIN; a.dbneg = w.bdbneg;
+  a.l2_partial = w.bl2; a.sq_partial = w.bsq;
+  return a;
+}
+
+static int bpr_fwd(mtam_model* h, const mtam_batch* bt, float* scalars_out, bool with_loss, cudaStream_t st) {
+  Workspace& w = h->ws;
+  if (h->bpr_neg >= 0) {
+    h->bpr_neg_used = h->bpr_neg;
+  } else {   // tf.random_uniform([1], 0, item_count) (BPRMF.py:43): a fresh negative per step
+    h->rng = h->rng * 6364136223846793005ULL + 1442695040888963407ULL;
+    h->bpr_neg_used = (int)((h->rng >> 33) % (uint64_t)std::max(1, h->cfg.item_rows - 3));
+  }
+  int n_l2 = 0, n_loss = 0;
+  MTAM_TRY(bpr_forward(bpr_args(h, bt), &n_l2, &n_loss, st));
+  MTAM_CUDA_CHECK(cudaMemcpyAsync(w.pred, w.bU, (size_t)bt->B * h->cfg.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (!with_loss) return 0;
+  float* ds = w.dev_scalars;
+  MTAM_TRY(finalize_sum(w.bl2, n_l2, 0.5f, ds + MTAM_S_L2_NORM, 0, st));
+  MTAM_TRY(finalize_sum(w.bloss, n_loss, 1.0f / ((float)bt->B * (float)bt->B), ds + MTAM_S_LOSS_ORIGIN, 0, st));
+  MTAM_TRY(finalize_sum(ds + MTAM_S_L2_NORM, 1, 5e-5f, ds + MTAM_S_LOSS, 0, st));
+  MTAM_TRY(finalize_sum(ds + MTAM_S_LOSS_ORIGIN, 1, 1.0f, ds + MTAM_S_LOSS, 1, st));
+  if (scalars_out) MTAM_CUDA_CHECK(cudaMemcpyAsync(scalars_out, ds, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+static int bpr_bwd(mtam_model* h, const mtam_batch* bt, float* norm_sq_sparse, cudaStream_t st) {
+  int n_sq = 0;
+  MTAM_TRY(bpr_backward(bpr_args(h, bt), &n_sq, st));
+  MTAM_TRY(finalize_sum(h->ws.bsq, n_sq, 1.0f, norm_sq_sparse, 1, st));
+  // every piece is sparse: the dense region of the grads arena must read as zero for the norm
+  MTAM_CUDA_CHECK(cudaMemsetAsync(h->grads + h->lay.dense_begin, 0, (h->lay.total - h->lay.dense_begin) * sizeof(float), st));
+  return 0;
+}
+
+static int bpr_scatter(mtam_model* h, cudaStream_t st) {
+  const mtam_config& c = h->cfg;
+  const Layout& l = h->lay;
+  Workspace& w = h->ws;
+  const mtam_batch& bt = h->last_batch;
+  const int B = h->last_B, D = c.D;
+  float* G = h->grads;
+  int32_t neg = h->bpr_neg_used;
+  MTAM_CUDA_CHECK(cudaMemcpyAsync(w.bneg_idx, &h->bpr_neg_used, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  (void)neg;
+  MTAM_TRY(scatter_add_rows(G + l.user, c.user_rows, D, D, bt.user_id, w.bdU, D, B, w.scatter_ws, w.scatter_ws_bytes, nullptr, nullptr, st));
+  MTAM_TRY(scatter_add_rows(G + l.item, c.item_rows, D, D, bt.target_item_id, w.bdIP, D, B, w.scatter_ws, w.scatter_ws_bytes, nullptr, nullptr, st));
+  MTAM_TRY(scatter_add_rows(G + l.item, c.item_rows, D, D, w.bneg_idx, w.bdIN, D, 1, w.scatter_ws, w.scatter_ws_bytes, nullptr, nullptr, st));
+  MTAM_TRY(scatter_add_rows(G + l.item_b, c.item_rows, 1, 1, bt.target_item_id, w.browsum, 1, B, w.scatter_ws, w.scatter_ws_bytes, nullptr, nullptr, st));
+  MTAM_TRY(scatter_add_rows(G + l.item_b, c.item_rows, 1, 1, w.bneg_idx, w.bdbneg, 1, 1, w.scatter_ws, w.scatter_ws_bytes, nullptr, nullptr, st));
+  return 0;
+}
+
 static int check_batch(mtam_model* h, const mtam_batch* bt) {
   if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
   if (!bt) return set_error(MTAM_ERR_INVALID, "null batch");
@@ -501,14 +577,14 @@ static int fwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* scal
                         cudaStream_t st) {
   switch (h->cfg.kind) {
     case MTAM_KIND_MTAM: return mtam_fwd(h, bt, gb, scalars_out, with_loss, st);
-    case MTAM_KIND_BPRMF: return set_error(MTAM_ERR_UNSUPPORTED, "BPRMF is not built yet");
+    case MTAM_KIND_BPRMF: return bpr_fwd(h, bt, scalars_out, with_loss, st);
     default: return sa_fwd(h, bt, gb, scalars_out, with_loss, st);
   }
 }
 static int bwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* nsq, cudaStream_t st) {
   switch (h->cfg.kind) {
     case MTAM_KIND_MTAM: return mtam_bwd(h, bt, gb, nsq, st);
-    case MTAM_KIND_BPRMF: return set_error(MTAM_ERR_UNSUPPORTED, "BPRMF is not built yet");
+    case MTAM_KIND_BPRMF: return bpr_bwd(h, bt, nsq, st);
     default: return sa_bwd(h, bt, gb, nsq, st);
   }
 }
@@ -593,6 +669,13 @@ int mtam_set_adam_step(mtam_handle h, int64_t t) {
   h->adam_t = t;
   h->b1_pow = 1.f; h->b2_pow = 1.f;
   for (int64_t i = 0; i < t; ++i) { h->b1_pow *= h->cfg.beta1; h->b2_pow *= h->cfg.beta2; }
+  return 0;
+}
+
+int mtam_set_bpr_negative(mtam_handle h, int32_t item_id) {
+  if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
+  if (item_id >= h->cfg.item_rows) return set_error(MTAM_ERR_INVALID, "negative item id out of range");
+  h->bpr_neg = item_id;
   return 0;
 }
 
@@ -685,6 +768,7 @@ int mtam_finish_grads(mtam_handle h, float* norm_sq, int32_t scatter_local, void
   MTAM_TRY(finalize_sum(w.norm_partial, np, 1.0f, norm_sq, 1, st));
   phase(h, MTAM_PH_SCATTER, st);
   if (!scatter_local) return 0;
+  if (c.kind == MTAM_KIND_BPRMF) return bpr_scatter(h, st);
   float* G = h->grads;
   MTAM_TRY(scatter_add_rows(G + l.item, c.item_rows, D, D, bt.item_list, w.dE2, 2 * D, T, w.scatter_ws,
                             w.scatter_ws_bytes, nullptr, nullptr, st));

@@ -78,6 +78,21 @@ int hop_forward(const HopArgs& a, cudaStream_t st);
 int hop_backward(const HopArgs& a, const HopGradArgs& g, cudaStream_t st);
 int transpose_dd(const float* src, float* dst, int D, int count, cudaStream_t st);
 
+// ---- bpr.cu ---------------------------------------------------------------------------------
+struct BprArgs {
+  int B, D, neg;
+  const float *Tu, *Ti, *Tb;           // user table, item table, item_b table
+  const int32_t *user, *target;
+  float *U, *IP;                       // [B,D] gathered rows (U doubles as predict_behavior_emb)
+  float *dot, *bpos, *rowsum, *colsum, *loss_partial;   // [B]
+  float *dU, *dIP, *dINpart;           // [B,D] IndexedSlices values
+  float *dIN;                          // [D]   negative item row gradient
+  float *dbneg;                        // [1]   (d b_pos = rowsum)
+  float *l2_partial, *sq_partial;      // [ceil(B/4)+1]
+};
+int bpr_forward(const BprArgs& a, int* n_l2, int* n_loss, cudaStream_t st);
+int bpr_backward(const BprArgs& a, int* n_sq, cudaStream_t st);
+
 // ---- ce.cu ----------------------------------------------------------------------------------
 int ce_grid(int V);
 size_t ce_workspace_bytes(int B, int D, int V);

@@ -183,6 +183,10 @@ class Engine:
         check(self.lib.mtam_get_adam_step(self.h, C.byref(t)), "mtam_get_adam_step")
         return int(t.value)
 
+    def set_bpr_negative(self, item_id: int) -> None:
+        """BPR-MF: fix the shared negative item id (BPRMF.py:43 draws it with tf.random_uniform)."""
+        check(self.lib.mtam_set_bpr_negative(self.h, int(item_id)), "mtam_set_bpr_negative")
+
     def set_adam_step(self, t: int) -> None:
         check(self.lib.mtam_set_adam_step(self.h, int(t)), "mtam_set_adam_step")
 

@@ -328,7 +328,12 @@ def forward(cfg: OracleConfig, params: Dict[str, torch.Tensor], feed: Dict[str, 
             if t.requires_grad:
                 t.retain_grad()
         ib = p["embedding_layer/item_b"]
-        x = ib[pos_id] - ib[neg_id] + (Eu * (ip - ineg)).sum(1)        # [B,1]+[B] broadcast -> [B,B] in TF
+        bp, bn = ib[pos_id], ib[neg_id]
+        for t in (bp, bn):
+            if t.requires_grad:
+                t.retain_grad()
+        out.update(bpos=bp, bneg=bn)
+        x = bp - bn + (Eu * (ip - ineg)).sum(1)                        # [B,1]+[B] broadcast -> [B,B] in TF
         l2 = 0.5 * (Eu ** 2).sum() + 0.5 * (ip ** 2).sum() + 0.5 * (ineg ** 2).sum()
         loss = 5e-5 * l2 - torch.log(torch.sigmoid(x)).mean()
         out.update(loss=loss, pred=Eu, l2_norm=l2, loss_origin=None, ipos=ip, ineg=ineg)
@@ -426,10 +431,13 @@ def loss_and_grads(cfg: OracleConfig, params_np: Dict[str, np.ndarray], feed, dt
                 grads[name] = None
             else:
                 g = t.grad.detach().numpy().astype(np.float64)
-                if cfg.kind == BPRMF and name == "embedding_layer/item_b":
-                    pass
                 grads[name] = g
-                pieces.append(g)
+                if cfg.kind == BPRMF and name == "embedding_layer/item_b":
+                    # two embedding_lookups on item_b -> IndexedSlices: un-deduplicated values in the norm
+                    pieces.append(fwd["bpos"].grad.detach().numpy().astype(np.float64))
+                    pieces.append(fwd["bneg"].grad.detach().numpy().astype(np.float64))
+                else:
+                    pieces.append(g)
     if cfg.kind == BPRMF:   # dense4emb etc. are unused in BPRMF: tf.gradients gives None
         for name in list(grads):
             if grads[name] is not None and not np.any(grads[name]) and name not in TABLES \
