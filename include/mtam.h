@@ -187,10 +187,12 @@ int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_ou
  * draw, so a run can be reproduced; item_id < 0 restores the per-step draw from the handle's own generator. */
 int mtam_set_bpr_negative(mtam_handle h, int32_t item_id);
 
-/* Host-only half of mtam_apply: advances the Adam step and publishes lr_t in pinned memory.  Call it
- * before replaying a CUDA graph that captured mtam_train_step / mtam_apply (the captured copy reads
- * the pinned slot at replay time).  mtam_apply calls it itself when it has not been called. */
-int mtam_prepare_step(mtam_handle h, double lr);
+/* Per-step host half of mtam_apply: advances the Adam step (beta powers) and enqueues a one-thread
+ * kernel on `stream` that stores lr_t = lr*sqrt(1-b2^t)/(1-b1^t) in device memory (the value travels as
+ * a kernel argument).  mtam_apply calls it itself unless it was already called for this step.  To replay
+ * a CUDA graph of mtam_train_step: call mtam_prepare_step eagerly right before the capture (so the
+ * captured step does not contain it) and before every replay. */
+int mtam_prepare_step(mtam_handle h, double lr, void* stream);
 
 /* Where the sparse gradient pieces (IndexedSlices values) of the last forward_backward live. */
 typedef struct {

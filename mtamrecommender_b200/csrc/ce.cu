@@ -127,26 +127,38 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ p
   }
 }
 
-// lse[b], loss_origin[b] = lse - tlogit, block partial sums of loss_origin
+// lse[b], loss_origin[b] = lse - tlogit, block partial sums of loss_origin.
+// One warp per row (lanes across the G per-CTA partials), 32 rows per block.
+constexpr int CF_ROWS = 32;
 __global__ void __launch_bounds__(256) ce_finalize_kernel(const float2* __restrict__ ms_partial, int G, int B,
                                                           const float* __restrict__ tlogit, float* __restrict__ lse,
                                                           float* __restrict__ loss_origin,
                                                           float* __restrict__ block_partial) {
   __shared__ float red[32];
-  int b = blockIdx.x * 256 + threadIdx.x;
-  float lo = 0.f;
-  if (b < B) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float lo_sum = 0.f;
+  for (int r = warp; r < CF_ROWS; r += 8) {
+    int b = blockIdx.x * CF_ROWS + r;
+    if (b >= B) continue;   // warp-uniform
     float m = -INFINITY, s = 0.f;
-    for (int g = 0; g < G; ++g) {
+    for (int g = lane; g < G; g += 32) {
       float2 p = ms_partial[(int64_t)g * B + b];
       lse_merge(m, s, p.x, p.y);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      lse_merge(m, s, m2, s2);
+    }
     float l = m + logf(s);
-    lse[b] = l;
-    lo = l - tlogit[b];
-    loss_origin[b] = lo;
+    if (lane == 0) {
+      lse[b] = l;
+      float lo = l - tlogit[b];
+      loss_origin[b] = lo;
+      lo_sum += lo;
+    }
   }
-  float tot = block_sum(lo, red);
+  float tot = block_sum(lo_sum, red);
   if (threadIdx.x == 0) block_partial[blockIdx.x] = tot;
 }
 
@@ -274,7 +286,7 @@ int ce_grid(int V) { return std::max(1, std::min(cdiv(V, CT), 2 * kNumSMs)); }
 size_t ce_workspace_bytes(int B, int D, int V) {
   int G = ce_grid(V);
   return align_up((size_t)G * B * sizeof(float2), 256) + align_up((size_t)G * B * D * sizeof(float), 256) +
-         align_up((size_t)cdiv(B, 256) * sizeof(float), 256) + 1024;
+         align_up((size_t)cdiv(B, CF_ROWS) * sizeof(float), 256) + 1024;
 }
 
 template <int D>
@@ -286,7 +298,7 @@ static int ce_fwd_launch(const float* pred, const float* table, const int32_t* t
   size_t smem = (size_t)2 * D * CPAD * sizeof(float);
   MTAM_CUDA_CHECK(cudaFuncSetAttribute(ce_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ce_fwd_kernel<D><<<G, 256, smem, st>>>(pred, table, target, B, V, ms, tlogit);
-  int nb = cdiv(B, 256);
+  int nb = cdiv(B, CF_ROWS);
   ce_finalize_kernel<<<nb, 256, 0, st>>>(ms, G, B, tlogit, lse, loss_origin, block_partial);
   MTAM_LAUNCHES(1);
   MTAM_LAUNCH_CHECK();

@@ -72,6 +72,22 @@ __device__ __forceinline__ float group_sum(float v) {
   for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Predicated loads that return 0 when `pred` is false.  Written as inline PTX because the C++ form
+// `pred ? __ldg(p) : 0.f` compiles to a predicated LDG into a temporary followed by a dependent MOV,
+// which stalls on every load and serialises what should be a batch of independent loads.
+__device__ __forceinline__ float ld_nc_pred(const float* p, bool pred) {
+  float v;
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n mov.f32 %0, 0f00000000;\n @q ld.global.nc.f32 %0, [%1];\n}"
+               : "=f"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+__device__ __forceinline__ float ld_cg_pred(const float* p, bool pred) {
+  float v;
+  asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n mov.f32 %0, 0f00000000;\n @q ld.global.cg.f32 %0, [%1];\n}"
+               : "=f"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // block-wide sum for blockDim.x <= 1024 (result valid in all threads)

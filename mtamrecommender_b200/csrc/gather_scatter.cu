@@ -146,6 +146,11 @@ int exclusive_scan_i32(const int* in, int* out, int64_t n, int* tmp, int* total_
     if (total_out) MTAM_CUDA_CHECK(cudaMemsetAsync(total_out, 0, sizeof(int), st));
     return 0;
   }
+  if (n <= 16 * SC_THREADS && in == out) {   // short arrays: one block, one launch
+    scan_small_kernel<<<1, SC_THREADS, 0, st>>>(out, (int)n, total_out);
+    MTAM_LAUNCH_CHECK();
+    return 0;
+  }
   int nb = cdiv(n, SC_TILE);
   scan_reduce_kernel<<<nb, SC_THREADS, 0, st>>>(in, n, tmp);
   scan_small_kernel<<<1, SC_THREADS, 0, st>>>(tmp, nb, total_out);
@@ -166,10 +171,13 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const int32_t* __re
   h[threadIdx.x] = 0;
   __syncthreads();
   int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < RS_ITEMS; ++i) {
     int64_t j = base + i * RS_THREADS + threadIdx.x;
-    if (j < n) atomicAdd(&h[(keys[j] >> shift) & 255], 1);
+    int d = (j < n) ? ((keys[j] >> shift) & 255) : 256;
+    unsigned m = __match_any_sync(0xffffffffu, d);           // one shared-memory atomic per distinct digit per warp
+    if (d < 256 && lane == (__ffs(m) - 1)) atomicAdd(&h[d], __popc(m));
   }
   __syncthreads();
   hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
@@ -299,7 +307,80 @@ int sort_by_row(const int32_t* idx, int64_t n, int table_rows, void* ws, size_t 
 // =============================================================================================
 constexpr int SR_CH = 64;
 constexpr int SR_WARPS = 4;
+constexpr int SR_G = 8;   // entries whose row loads are in flight together
 
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using T = float; };
+template <> struct VecT<2> { using T = float2; };
+template <> struct VecT<4> { using T = float4; };
+
+__device__ __forceinline__ void vzero(float& a) { a = 0.f; }
+__device__ __forceinline__ void vzero(float2& a) { a = make_float2(0.f, 0.f); }
+__device__ __forceinline__ void vzero(float4& a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void vadd(float& a, const float& b) { a += b; }
+__device__ __forceinline__ void vadd(float2& a, const float2& b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ void vadd(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+// fire-and-forget reduction into global memory (RED.ADD, no return value, no load latency on the
+// critical path).  Deterministic here because a destination row receives at most one add per level.
+__device__ __forceinline__ void vred(float* p, const float& a) { atomicAdd(p, a); }
+__device__ __forceinline__ void vred(float* p, const float2& a) { atomicAdd(reinterpret_cast<float2*>(p), a); }
+__device__ __forceinline__ void vred(float* p, const float4& a) { atomicAdd(reinterpret_cast<float4*>(p), a); }
+
+// D == 32*VEC: each lane owns VEC contiguous floats of a row (one 128-bit / 64-bit / 32-bit access).
+template <int VEC>
+__global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_vec_kernel(
+    const int32_t* __restrict__ keys, const float* __restrict__ src, int ld_src,
+    const int32_t* __restrict__ perm, int64_t n, int ld_dst, float* __restrict__ dst,
+    int32_t* __restrict__ carry_keys, float* __restrict__ carry_rows) {
+  using V = typename VecT<VEC>::T;
+  constexpr int D = 32 * VEC;
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (int64_t)blockIdx.x * SR_WARPS + (threadIdx.x >> 5);
+  const int64_t ntiles = (n + SR_CH - 1) / SR_CH;
+  if (tile >= ntiles) return;
+  const int64_t start = tile * SR_CH;
+  const int cnt = (int)min((int64_t)SR_CH, n - start);
+  // tile keys / source rows: two coalesced loads, broadcast later with shuffles
+  const int l0 = min(lane, cnt - 1), l1 = min(lane + 32, cnt - 1);   // clamp: entries past the end alias the last one
+  int32_t k0 = keys[start + l0], k1 = keys[start + l1];
+  int32_t r0 = perm ? perm[start + l0] : (int32_t)(start + l0);
+  int32_t r1 = perm ? perm[start + l1] : (int32_t)(start + l1);
+  V acc;
+  vzero(acc);
+  int32_t cur = __shfl_sync(0xffffffffu, k0, 0);
+  for (int i0 = 0; i0 < cnt; i0 += SR_G) {
+    V x[SR_G];
+    int32_t kk[SR_G];
+#pragma unroll
+    for (int u = 0; u < SR_G; ++u) {     // unconditional, independent loads: SR_G rows in flight
+      int i = i0 + u;
+      int32_t ka = __shfl_sync(0xffffffffu, k0, i & 31), kb = __shfl_sync(0xffffffffu, k1, i & 31);
+      int32_t ra = __shfl_sync(0xffffffffu, r0, i & 31), rb = __shfl_sync(0xffffffffu, r1, i & 31);
+      kk[u] = (i < 32) ? ka : kb;
+      int32_t row = (i < 32) ? ra : rb;
+      x[u] = __ldg(reinterpret_cast<const V*>(src + (int64_t)row * ld_src) + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < SR_G; ++u) {
+      if (i0 + u < cnt) {
+        if (kk[u] != cur) {              // warp-uniform: the run of `cur` ended
+          vred(dst + (int64_t)cur * ld_dst + lane * VEC, acc);
+          vzero(acc);
+          cur = kk[u];
+        }
+        vadd(acc, x[u]);
+      }
+    }
+  }
+  if (tile == ntiles - 1) {
+    vred(dst + (int64_t)cur * ld_dst + lane * VEC, acc);
+  } else {
+    if (lane == 0) carry_keys[tile] = cur;
+    reinterpret_cast<V*>(carry_rows + tile * D)[lane] = acc;
+  }
+}
+
+// any D <= 256: lanes stride across the row
 template <int MAXV>
 __global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_level_kernel(
     const int32_t* __restrict__ keys, const float* __restrict__ src, int ld_src,
@@ -311,17 +392,14 @@ __global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_level_kernel(
   if (tile >= ntiles) return;
   const int64_t start = tile * SR_CH;
   const int cnt = (int)min((int64_t)SR_CH, n - start);
-  // tile keys / source rows: two coalesced loads, broadcast later with shuffles
-  int32_t k0 = (lane < cnt) ? keys[start + lane] : -1;
-  int32_t k1 = (lane + 32 < cnt) ? keys[start + 32 + lane] : -1;
-  int32_t r0 = (lane < cnt) ? (perm ? perm[start + lane] : (int32_t)(start + lane)) : 0;
-  int32_t r1 = (lane + 32 < cnt) ? (perm ? perm[start + 32 + lane] : (int32_t)(start + 32 + lane)) : 0;
-
+  const int l0 = min(lane, cnt - 1), l1 = min(lane + 32, cnt - 1);
+  int32_t k0 = keys[start + l0], k1 = keys[start + l1];
+  int32_t r0 = perm ? perm[start + l0] : (int32_t)(start + l0);
+  int32_t r1 = perm ? perm[start + l1] : (int32_t)(start + l1);
   float acc[MAXV];
 #pragma unroll
   for (int v = 0; v < MAXV; ++v) acc[v] = 0.f;
   int32_t cur = __shfl_sync(0xffffffffu, k0, 0);
-
   for (int i0 = 0; i0 < cnt; i0 += 4) {
     float x[4][MAXV];
     int32_t kk[4];
@@ -334,20 +412,16 @@ __global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_level_kernel(
       int32_t row = (i < 32) ? ra : rb;
       const float* p = src + (int64_t)row * ld_src;
 #pragma unroll
-      for (int v = 0; v < MAXV; ++v) {
-        int d = lane + 32 * v;
-        x[u][v] = (i < cnt && d < D) ? __ldg(p + d) : 0.f;
-      }
+      for (int v = 0; v < MAXV; ++v) x[u][v] = __ldg(p + min(lane + 32 * v, D - 1));   // clamped, masked at use
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (i0 + u < cnt) {
-        if (kk[u] != cur) {  // warp-uniform branch
-          float* q = dst + (int64_t)cur * ld_dst;
+        if (kk[u] != cur) {
 #pragma unroll
           for (int v = 0; v < MAXV; ++v) {
             int d = lane + 32 * v;
-            if (d < D) q[d] += acc[v];
+            if (d < D) atomicAdd(dst + (int64_t)cur * ld_dst + d, acc[v]);
             acc[v] = 0.f;
           }
           cur = kk[u];
@@ -358,19 +432,17 @@ __global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_level_kernel(
     }
   }
   if (tile == ntiles - 1) {
-    float* q = dst + (int64_t)cur * ld_dst;
 #pragma unroll
     for (int v = 0; v < MAXV; ++v) {
       int d = lane + 32 * v;
-      if (d < D) q[d] += acc[v];
+      if (d < D) atomicAdd(dst + (int64_t)cur * ld_dst + d, acc[v]);
     }
   } else {
     if (lane == 0) carry_keys[tile] = cur;
-    float* q = carry_rows + tile * D;
 #pragma unroll
     for (int v = 0; v < MAXV; ++v) {
       int d = lane + 32 * v;
-      if (d < D) q[d] = acc[v];
+      if (d < D) carry_rows[tile * D + d] = acc[v];
     }
   }
 }
@@ -410,7 +482,15 @@ int seg_reduce_sorted(const int32_t* keys_sorted, const int32_t* perm, const flo
     }
     int blocks = cdiv(nt, SR_WARPS);
     int maxv = (D + 31) / 32;
-    if (maxv <= 1)
+    const bool vec_ok = (D == 32 || D == 64 || D == 128) && (lds % (D / 32) == 0) && (ld_dst % (D / 32) == 0) &&
+                        ((uintptr_t)s % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+    if (vec_ok && D == 32)
+      seg_reduce_vec_kernel<1><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, ld_dst, dst, ck, cr);
+    else if (vec_ok && D == 64)
+      seg_reduce_vec_kernel<2><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, ld_dst, dst, ck, cr);
+    else if (vec_ok && D == 128)
+      seg_reduce_vec_kernel<4><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, ld_dst, dst, ck, cr);
+    else if (maxv <= 1)
       seg_reduce_level_kernel<1><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);
     else if (maxv <= 2)
       seg_reduce_level_kernel<2><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int row = rg1 * 4 + i;
-      g1[i] = (t < steps[row]) ? __ldg(GX + ((int64_t)(b0 + row) * L + t) * (3 * D) + n1) : 0.f;
+      g1[i] = ld_nc_pred(GX + ((int64_t)(b0 + row) * L + t) * (3 * D) + n1, t < steps[row]);
     }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
@@ -89,9 +89,9 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
       int row = rg2 * 2 + i;
       bool live = t < steps[row];
       int64_t tok = (int64_t)(b0 + row) * L + t;
-      g2[i] = live ? __ldg(GX + tok * (3 * D) + 2 * D + n2) : 0.f;
-      xv[i] = live ? __ldg(X + tok * D + n2) : 0.f;
-      dl[i] = live ? __ldg(timelast + tok) : 0.f;
+      g2[i] = ld_nc_pred(GX + tok * (3 * D) + 2 * D + n2, live);
+      xv[i] = ld_nc_pred(X + tok * D + n2, live);
+      dl[i] = ld_nc_pred(timelast + tok, live);
     }
     float acc2[2] = {0.f, 0.f};
 #pragma unroll 8

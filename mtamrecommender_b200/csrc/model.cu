@@ -44,8 +44,9 @@ struct Workspace {
   float *l2_partial, *sq_partial, *ce_partial, *norm_partial, *dev_scalars;  // dev_scalars: [16]
   float *bU, *bIP, *bdot, *bbpos, *browsum, *bcolsum, *bloss, *bdU, *bdIP, *bdINp, *bdIN, *bdbneg, *bl2, *bsq;  // BPRMF
   int32_t* bneg_idx;
-  void *ce_ws, *gemm_ws, *colsum_ws, *scatter_ws, *sa_ws, *topk_ws;
-  size_t ce_ws_bytes, gemm_ws_bytes, colsum_ws_bytes, scatter_ws_bytes, sa_ws_bytes, topk_ws_bytes;
+  void *ce_ws, *gemm_ws, *colsum_ws, *scatter_ws, *sa_ws, *topk_ws, *sort_ws[4], *seg_ws;
+  size_t ce_ws_bytes, gemm_ws_bytes, colsum_ws_bytes, scatter_ws_bytes, sa_ws_bytes, topk_ws_bytes, sort_ws_bytes[4],
+      seg_ws_bytes;
   size_t total_bytes;
 };
 
@@ -66,6 +67,10 @@ struct mtam_model {
   float* lr_host = nullptr;          // pinned: lr_t of the current step (read by a captured H2D copy)
   bool step_prepared = false;        // mtam_prepare_step already advanced the Adam state for this step
   bool prof = false;
+  cudaStream_t side = nullptr;       // index sorts run here, concurrently with forward/backward
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool sort_pending = false;
+  const int32_t *sk[4] = {}, *sp[4] = {};   // sorted keys / permutations: item, category, position, user
   int bpr_neg = -1;                  // injected negative item id (mtam_set_bpr_negative); -1: draw one per step
   int bpr_neg_used = 0;
   uint64_t rng = 1234;
@@ -185,7 +190,7 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
   w.dEu = b.take<float>(B * D);
   w.l2_partial = b.take<float>(kEmbedMaxBlocks);
   w.sq_partial = b.take<float>(kEmbedMaxBlocks);
-  w.ce_partial = b.take<float>(cdiv(B, 256) + 1);
+  w.ce_partial = b.take<float>(cdiv(B, 32) + 1);
   w.norm_partial = b.take<float>(kNumSMs * 4 + 4);
   w.dev_scalars = b.take<float>(16);
   size_t gemm_ws = 0, colsum_ws = 0;
@@ -246,6 +251,15 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
   sc = std::max(sc, scatter_add_workspace_bytes(B, c.item_rows, D));
   w.scatter_ws_bytes = sc;
   w.scatter_ws = b.take<char>(sc);
+  {
+    const int rows[4] = {c.item_rows, c.category_rows, c.position_rows, c.user_rows};
+    for (int k = 0; k < 4; ++k) {
+      w.sort_ws_bytes[k] = sort_workspace_bytes(k == 3 ? B : T, rows[k]);
+      w.sort_ws[k] = b.take<char>(w.sort_ws_bytes[k]);
+    }
+    w.seg_ws_bytes = seg_reduce_workspace_bytes(T, (int)D);
+    w.seg_ws = b.take<char>(w.seg_ws_bytes);
+  }
   w.topk_ws_bytes = score_topk_workspace_bytes((int)B, c.item_rows, std::min(50, c.item_rows));
   w.topk_ws = b.take<char>(w.topk_ws_bytes);
   w.total_bytes = b.off + 1024;
@@ -634,6 +648,13 @@ int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam
     return set_error(MTAM_ERR_CUDA, "cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   memset(&h->last_batch, 0, sizeof(h->last_batch));
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    int e = set_error(MTAM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    mtam_destroy(h);
+    return e;
+  }
   *out = h;
   return 0;
 }
@@ -641,6 +662,9 @@ int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam
 int mtam_destroy(mtam_handle h) {
   if (h) {
     if (h->lr_host) cudaFreeHost(h->lr_host);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (int i = 0; i <= MTAM_PHASE_COUNT; ++i)
       if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   }
@@ -679,13 +703,16 @@ int mtam_set_bpr_negative(mtam_handle h, int32_t item_id) {
   return 0;
 }
 
-int mtam_prepare_step(mtam_handle h, double lr) {
+int mtam_prepare_step(mtam_handle h, double lr, void* stream) {
   if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
   h->adam_t += 1;
   h->b1_pow *= h->cfg.beta1;
   h->b2_pow *= h->cfg.beta2;
   const float lr32 = (float)lr;  // float64 placeholder cast to fp32 (base_model.py:25)
-  *h->lr_host = lr32 * sqrtf(1.f - h->b2_pow) / (1.f - h->b1_pow);
+  const float lr_t = lr32 * sqrtf(1.f - h->b2_pow) / (1.f - h->b1_pow);
+  // lr_t travels as a kernel argument (captured by value at launch): no host buffer can be overwritten
+  // before the device has read it, however far the host runs ahead.
+  MTAM_TRY(set_scalar(h->ws.dev_scalars + 9, lr_t, (cudaStream_t)stream));
   h->step_prepared = true;
   return 0;
 }
@@ -743,6 +770,22 @@ int mtam_forward_backward(mtam_handle h, const mtam_batch* batch, int32_t global
   if (!norm_sq_sparse) return set_error(MTAM_ERR_INVALID, "norm_sq_sparse is null");
   if (global_batch < batch->B) return set_error(MTAM_ERR_INVALID, "global_batch < local batch");
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->cfg.kind != MTAM_KIND_BPRMF) {
+    // The scatter-add's sort depends on the batch indices only: run it on the side stream, concurrently
+    // with forward/backward (fork/join with events, so it is also captured into a CUDA graph).
+    const mtam_config& c = h->cfg;
+    Workspace& w = h->ws;
+    const int64_t T = (int64_t)batch->B * c.L;
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_fork, st));
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    MTAM_TRY(sort_by_row(batch->item_list, T, c.item_rows, w.sort_ws[0], w.sort_ws_bytes[0], &h->sk[0], &h->sp[0], h->side));
+    MTAM_TRY(sort_by_row(batch->category_list, T, c.category_rows, w.sort_ws[1], w.sort_ws_bytes[1], &h->sk[1], &h->sp[1], h->side));
+    MTAM_TRY(sort_by_row(batch->position_list, T, c.position_rows, w.sort_ws[2], w.sort_ws_bytes[2], &h->sk[2], &h->sp[2], h->side));
+    if (c.kind != MTAM_KIND_PISTREC)
+      MTAM_TRY(sort_by_row(batch->user_id, batch->B, c.user_rows, w.sort_ws[3], w.sort_ws_bytes[3], &h->sk[3], &h->sp[3], h->side));
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_join, h->side));
+    h->sort_pending = true;
+  }
   MTAM_TRY(fwd_dispatch(h, batch, global_batch, scalars_out, true, st));
   MTAM_TRY(bwd_dispatch(h, batch, global_batch, norm_sq_sparse, st));
   h->last_batch = *batch;
@@ -767,18 +810,19 @@ int mtam_finish_grads(mtam_handle h, float* norm_sq, int32_t scatter_local, void
   MTAM_TRY(sumsq_partials(h->grads + l.dense_begin, (int64_t)(l.total - l.dense_begin), w.norm_partial, &np, st));
   MTAM_TRY(finalize_sum(w.norm_partial, np, 1.0f, norm_sq, 1, st));
   phase(h, MTAM_PH_SCATTER, st);
+  if (h->sort_pending) {   // always re-join the side stream (also closes the fork inside a graph capture)
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    h->sort_pending = false;
+  }
   if (!scatter_local) return 0;
   if (c.kind == MTAM_KIND_BPRMF) return bpr_scatter(h, st);
   float* G = h->grads;
-  MTAM_TRY(scatter_add_rows(G + l.item, c.item_rows, D, D, bt.item_list, w.dE2, 2 * D, T, w.scatter_ws,
-                            w.scatter_ws_bytes, nullptr, nullptr, st));
-  MTAM_TRY(scatter_add_rows(G + l.cat, c.category_rows, D, D, bt.category_list, w.dE2 + D, 2 * D, T, w.scatter_ws,
-                            w.scatter_ws_bytes, nullptr, nullptr, st));
-  MTAM_TRY(scatter_add_rows(G + l.pos, c.position_rows, D, D, bt.position_list, w.dEp, D, T, w.scatter_ws,
-                            w.scatter_ws_bytes, nullptr, nullptr, st));
+  MTAM_TRY(seg_reduce_sorted(h->sk[0], h->sp[0], w.dE2, 2 * D, T, D, G + l.item, D, w.seg_ws, w.seg_ws_bytes, st));
+  MTAM_TRY(seg_reduce_sorted(h->sk[1], h->sp[1], w.dE2 + D, 2 * D, T, D, G + l.cat, D, w.seg_ws, w.seg_ws_bytes, st));
+  MTAM_TRY(seg_reduce_sorted(h->sk[2], h->sp[2], w.dEp, D, T, D, G + l.pos, D, w.seg_ws, w.seg_ws_bytes, st));
   if (c.kind != MTAM_KIND_PISTREC)
-    MTAM_TRY(scatter_add_rows(G + l.user, c.user_rows, D, D, bt.user_id, w.dEu, D, B, w.scatter_ws,
-                              w.scatter_ws_bytes, nullptr, nullptr, st));
+    MTAM_TRY(seg_reduce_sorted(h->sk[3], h->sp[3], w.dEu, D, B, D, G + l.user, D, w.seg_ws, w.seg_ws_bytes, st));
+  (void)bt;
   return 0;
 }
 
@@ -792,9 +836,8 @@ int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_ou
   float* ds = w.dev_scalars;
   MTAM_TRY(clip_scale(norm_sq, c.clip, ds + MTAM_S_GLOBAL_NORM, ds + MTAM_S_CLIP_SCALE, st));
   phase(h, MTAM_PH_ADAM, st);
-  if (!h->step_prepared) MTAM_TRY(mtam_prepare_step(h, lr));
+  if (!h->step_prepared) MTAM_TRY(mtam_prepare_step(h, lr, stream));
   h->step_prepared = false;
-  MTAM_CUDA_CHECK(cudaMemcpyAsync(ds + 9, h->lr_host, sizeof(float), cudaMemcpyHostToDevice, st));
   MTAM_TRY(adam_apply(h->params, h->m, h->v, h->grads, (int64_t)l.total, ds + MTAM_S_CLIP_SCALE, ds + 9, c.beta1, c.beta2,
                       c.eps, st));
   // restore the invariant "sparse-only table regions of the grads arena are zero"

@@ -52,6 +52,13 @@ int clip_scale(const float* norm_sq, float clip, float* gn_out, float* scale_out
   return 0;
 }
 
+__global__ void set_scalar_kernel(float* p, float v) { p[0] = v; }
+int set_scalar(float* p, float v, cudaStream_t st) {
+  set_scalar_kernel<<<1, 1, 0, st>>>(p, v);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v,
                                                    const float4* __restrict__ g, int64_t n4, const float* __restrict__ scale_p,
                                                    const float* __restrict__ lr_t_p, float b1, float b2, float eps) {

@@ -303,6 +303,8 @@ class Engine:
         torch.cuda.synchronize(self.device)
         raise_if = None
         g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):   # eager: keeps the per-step lr_t store out of the captured step
+            check(self.lib.mtam_prepare_step(self.h, 0.0, s.cuda_stream), "mtam_prepare_step")
         with torch.cuda.graph(g, stream=s):
             self.train_step_device(batch, 0.0)
         self.set_adam_step(t0)
@@ -310,7 +312,7 @@ class Engine:
         return raise_if
 
     def train_step_graph(self, lr: float) -> None:
-        check(self.lib.mtam_prepare_step(self.h, float(lr)), "mtam_prepare_step")
+        check(self.lib.mtam_prepare_step(self.h, float(lr), self._stream()), "mtam_prepare_step")
         self._graph.replay()
 
     def eval_topk_device(self, batch: DeviceBatch, k: int = 50):
