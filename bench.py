@@ -173,7 +173,8 @@ def run_cuda(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     mc = E.ModelConfig(kind=w["kind"], max_batch=w["B"], L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
-                       item_count=w["items"], category_count=w["cats"])
+                       item_count=w["items"], category_count=w["cats"],
+                       gemm_mode=_lib.GEMM_TF32X3 if args.gemm_mode == "tf32x3" else _lib.GEMM_FP32)
     eng = E.Engine(mc, device=dev, seed=1234)           # same seed on every rank: replicas start identical
     dp = None
     if world > 1:
@@ -283,11 +284,11 @@ def run_cuda(args, w):
         bw = bandwidth_kernels(eng, dev, pk)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic",
+               "dtype": "f32 (tcgen05 3xTF32 split, fp32 accumulate)" if args.gemm_mode == "tf32x3" else "f32", "data": "synthetic",
                "config": {"workload": args.workload, "model": "MTAM", "batch_per_gpu": w["B"], "global_batch": w["B"] * world,
                           "seq_len": w["L"], "num_units": w["D"], "num_blocks": w["N"], "num_heads": w["H"],
                           "item_count": w["items"], "user_count": w["users"], "category_count": w["cats"],
-                          "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
+                          "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "gemm_mode": args.gemm_mode,
                           "l2": "4 rotating batches; every step streams the 4 parameter/Adam arenas "
                                 f"({4 * 4 * eng.n_floats / 1e6:.0f} MB) through HBM, > 126 MB L2"},
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
@@ -353,6 +354,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--gemm-mode", default="tf32x3", choices=["tf32x3", "fp32"],
+                    help="dense contractions: tcgen05 3-term-split TF32 (fp32-class accuracy) or exact fp32 FFMA")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU arm (bounded sample)")
     args = ap.parse_args()

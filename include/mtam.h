@@ -215,6 +215,14 @@ enum {
 int mtam_profile_enable(mtam_handle h, int32_t on);
 int mtam_profile_read(mtam_handle h, float* ms_out, int32_t n);   /* ms_out[MTAM_PHASE_COUNT]; host sync */
 
+/* Stand-alone GEMM (diagnostic / tests): C[M,N] = act(op(A) op(B) + bias), row-major with leading dimensions;
+ * transA: A stored [K,M]; transB: B stored [N,K]; mode = mtam_gemm_mode.  Replaces tf.matmul / tf.layers.dense
+ * call sites (time_aware_attention.py:249-253, Behavior_...py:95-103). */
+int mtam_gemm(int32_t mode, int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K, const float* A,
+              int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, const float* bias, int32_t relu,
+              int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+size_t mtam_gemm_workspace(int32_t M, int32_t N, int32_t K);
+
 /* Kernels launched by the library since it was loaded (diagnostic). */
 long long mtam_launch_count(void);
 

@@ -78,6 +78,8 @@ SIGNATURES = {
     "mtam_sparse_pieces": (C.c_int, [_VP, C.POINTER(SparseView)]),
     "mtam_profile_enable": (C.c_int, [_VP, _I32]),
     "mtam_profile_read": (C.c_int, [_VP, _VP, _I32]),
+    "mtam_gemm": (C.c_int, [_I32] * 6 + [_VP, _I32, _VP, _I32, _VP, _I32, _VP, _I32, _I32, _VP, _SZ, _VP]),
+    "mtam_gemm_workspace": (_SZ, [_I32, _I32, _I32]),
     "mtam_launch_count": (C.c_longlong, []),
     "mtam_eval_topk": (C.c_int, [_VP, C.POINTER(Batch), _I32, _VP, _VP, _VP]),
     "mtam_score_topk": (C.c_int, [_VP, _I32, _I32, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _SZ, _VP]),

@@ -8,30 +8,13 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemm_epi.cuh"
 #include "kernels.h"
 #include "../../include/mtam.h"
 
 namespace mtam {
 
 constexpr int GM = 64, GN = 64, GK = 16, GT = 256;
-
-struct EpiDev {
-  const float* bias;
-  const float* mask_pos;
-  const float* add;
-  int ld_mask, ld_add, relu, accumulate;
-  float alpha;
-};
-
-__device__ __forceinline__ float apply_epi(float v, int m, int n, const EpiDev& e, const float* C, int ldc) {
-  v *= e.alpha;
-  if (e.bias) v += e.bias[n];
-  if (e.relu) v = fmaxf(v, 0.f);
-  if (e.mask_pos) v = (e.mask_pos[(int64_t)m * e.ld_mask + n] > 0.f) ? v : 0.f;
-  if (e.add) v += e.add[(int64_t)m * e.ld_add + n];
-  if (e.accumulate) v += C[(int64_t)m * ldc + n];
-  return v;
-}
 
 template <int TA, int TB, int VA, int VB>
 __global__ void __launch_bounds__(GT) gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
@@ -160,6 +143,13 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, i
   C[(int64_t)m * ldc + n] = apply_epi(s, m, n, epi, C, ldc);
 }
 
+int splitk_reduce(const float* partial, int S, int M, int N, float* C, int ldc, const EpiDev& epi, cudaStream_t st) {
+  int64_t tot = (int64_t)M * N;
+  splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, st>>>(partial, S, M, N, C, ldc, epi);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
 static int pick_splits(int M, int N, int K) {
   int tiles = cdiv(M, GM) * cdiv(N, GN);
   if (tiles >= kNumSMs || K < 1024) return 1;
@@ -219,20 +209,37 @@ int gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int ld
 }
 
 // ---- deterministic column sums: out[n] = sum_m A[m,n] * (Bmul ? Bmul[m,n] : 1) -----------------
-constexpr int CS_ROWS = 256;  // rows per partial block
+// Two stages (per-row-block partials, then a fixed-order sum over the blocks).  The number of row blocks is
+// chosen so that the grid covers the machine whatever the shape (tall-skinny [B*L, D] or short-wide).
+static int colsum_rows_per_block(int M, int N) {
+  int colblocks = cdiv(N, 128);
+  int want_rowblocks = std::max(1, cdiv(4 * kNumSMs, colblocks));
+  int rows = std::max(16, cdiv(M, want_rowblocks));
+  return std::min(rows, 256);
+}
 
-__global__ void colsum_partial_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
-                                      int M, int N, float* __restrict__ partial) {
+__global__ void __launch_bounds__(128) colsum_partial_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+                                      int M, int N, int rows_per_block, float* __restrict__ partial) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  int m0 = blockIdx.y * CS_ROWS, m1 = min(M, m0 + CS_ROWS);
-  float s = 0.f;
+  int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int m = m0;
   if (Bm) {
-    for (int m = m0; m < m1; ++m) s += A[(int64_t)m * lda + n] * Bm[(int64_t)m * ldb + n];
+    for (; m + 3 < m1; m += 4) {
+      float a0 = A[(int64_t)m * lda + n], a1 = A[(int64_t)(m + 1) * lda + n], a2 = A[(int64_t)(m + 2) * lda + n], a3 = A[(int64_t)(m + 3) * lda + n];
+      float b0 = Bm[(int64_t)m * ldb + n], b1 = Bm[(int64_t)(m + 1) * ldb + n], b2 = Bm[(int64_t)(m + 2) * ldb + n], b3 = Bm[(int64_t)(m + 3) * ldb + n];
+      s0 = fmaf(a0, b0, s0); s1 = fmaf(a1, b1, s1); s2 = fmaf(a2, b2, s2); s3 = fmaf(a3, b3, s3);
+    }
+    for (; m < m1; ++m) s0 = fmaf(A[(int64_t)m * lda + n], Bm[(int64_t)m * ldb + n], s0);
   } else {
-    for (int m = m0; m < m1; ++m) s += A[(int64_t)m * lda + n];
+    for (; m + 3 < m1; m += 4) {
+      float a0 = A[(int64_t)m * lda + n], a1 = A[(int64_t)(m + 1) * lda + n], a2 = A[(int64_t)(m + 2) * lda + n], a3 = A[(int64_t)(m + 3) * lda + n];
+      s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+    }
+    for (; m < m1; ++m) s0 += A[(int64_t)m * lda + n];
   }
-  partial[(int64_t)blockIdx.y * N + n] = s;
+  partial[(int64_t)blockIdx.y * N + n] = (s0 + s1) + (s2 + s3);
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int P, int N, float* __restrict__ out,
                                     int accumulate) {
@@ -242,15 +249,18 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int P, in
   for (int p = 0; p < P; ++p) s += partial[(int64_t)p * N + n];
   out[n] = accumulate ? out[n] + s : s;
 }
-size_t colsum_workspace_bytes(int M, int N) { return (size_t)cdiv(M, CS_ROWS) * N * sizeof(float) + 256; }
+size_t colsum_workspace_bytes(int M, int N) {
+  return (size_t)cdiv(std::max(M, 1), colsum_rows_per_block(M, N)) * N * sizeof(float) + 256;
+}
 
 int colsum_f32(const float* A, int lda, const float* Bmul, int ldb, int M, int N, float* out, int accumulate,
                void* ws, size_t ws_bytes, cudaStream_t st) {
   if (N <= 0) return 0;
-  int P = std::max(1, cdiv(M, CS_ROWS));
+  int rpb = colsum_rows_per_block(M, N);
+  int P = std::max(1, cdiv(M, rpb));
   if (ws_bytes < (size_t)P * N * sizeof(float)) return set_error(MTAM_ERR_WORKSPACE, "colsum workspace too small");
   dim3 grid(cdiv(N, 128), P);
-  colsum_partial_kernel<<<grid, 128, 0, st>>>(A, lda, Bmul, ldb, M, N, (float*)ws);
+  colsum_partial_kernel<<<grid, 128, 0, st>>>(A, lda, Bmul, ldb, M, N, rpb, (float*)ws);
   colsum_final_kernel<<<cdiv(N, 128), 128, 0, st>>>((const float*)ws, P, N, out, accumulate);
   MTAM_LAUNCHES(1);
   MTAM_LAUNCH_CHECK();

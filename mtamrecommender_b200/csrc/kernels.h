@@ -40,6 +40,12 @@ size_t gemm_splitk_workspace_bytes(int M, int N, int K);
 int gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const GemmEpilogue& epi, void* splitk_ws, size_t splitk_ws_bytes,
              cudaStream_t st);
+// tc_gemm.cu: same contract on tcgen05 (3xTF32), and the mode dispatcher
+int gemm_tf32x3(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                float* C, int ldc, const GemmEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st);
+int gemm_any(int mode, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+             float* C, int ldc, const GemmEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t gemm_any_workspace_bytes(int M, int N, int K);
 // out[n] (+)= sum_m A[m,n]   (deterministic two-stage column sum); optional second operand: sum A*Bm
 int colsum_f32(const float* A, int lda, const float* Bmul, int ldb, int M, int N, float* out, int accumulate,
                void* ws, size_t ws_bytes, cudaStream_t st);

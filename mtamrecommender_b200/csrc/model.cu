@@ -194,7 +194,7 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
   w.norm_partial = b.take<float>(kNumSMs * 4 + 4);
   w.dev_scalars = b.take<float>(16);
   size_t gemm_ws = 0, colsum_ws = 0;
-  auto G = [&](int M, int Nn, int K) { gemm_ws = std::max(gemm_ws, gemm_splitk_workspace_bytes(M, Nn, K)); };
+  auto G = [&](int M, int Nn, int K) { gemm_ws = std::max(gemm_ws, gemm_any_workspace_bytes(M, Nn, K)); };
   auto CS = [&](int M, int Nn) { colsum_ws = std::max(colsum_ws, colsum_workspace_bytes(M, Nn)); };
   G(2 * D, D, T);  // dWemb
   if (c.kind == MTAM_KIND_MTAM) {
@@ -279,8 +279,8 @@ static int validate(const mtam_config* c) {
     return set_error(MTAM_ERR_INVALID, "num_heads=%d must divide 32 and num_units", c->H);
   if (c->user_rows < 1 || c->item_rows < 1 || c->category_rows < 1 || c->position_rows < 1)
     return set_error(MTAM_ERR_INVALID, "table row counts must be positive");
-  if (c->gemm_mode != MTAM_GEMM_FP32)
-    return set_error(MTAM_ERR_UNSUPPORTED, "gemm_mode %d not built in this version", c->gemm_mode);
+  if (c->gemm_mode != MTAM_GEMM_FP32 && c->gemm_mode != MTAM_GEMM_TF32X3)
+    return set_error(MTAM_ERR_INVALID, "unknown gemm_mode %d", c->gemm_mode);
   return 0;
 }
 
@@ -289,7 +289,7 @@ static int validate(const mtam_config* c) {
 // ---------------------------------------------------------------------------------------------
 static int gemm(mtam_model* h, int tA, int tB, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb,
                 float* C, int ldc, const GemmEpilogue& e, cudaStream_t st) {
-  return gemm_f32(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, e, h->ws.gemm_ws, h->ws.gemm_ws_bytes, st);
+  return gemm_any(h->cfg.gemm_mode, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, e, h->ws.gemm_ws, h->ws.gemm_ws_bytes, st);
 }
 static int colsum(mtam_model* h, const float* A, int lda, const float* Bm, int ldb, int M, int N, float* out,
                   cudaStream_t st) {

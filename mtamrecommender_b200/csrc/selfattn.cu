@@ -413,7 +413,7 @@ int sa_forward(const SaCtx& c, cudaStream_t st) {
     GemmEpilogue e;
     e.bias = c.params + c.sl.b3 + (size_t)i * 3 * D;
     e.relu = 1;
-    MTAM_TRY(gemm_f32(0, 0, (int)T, 3 * D, D, enc, D, c.params + c.sl.W3 + (size_t)i * D * 3 * D, 3 * D, qkv, 3 * D, e,
+    MTAM_TRY(gemm_any(g.gemm_mode, 0, 0, (int)T, 3 * D, D, enc, D, c.params + c.sl.W3 + (size_t)i * D * 3 * D, 3 * D, qkv, 3 * D, e,
                       c.gemm_ws, c.gemm_ws_bytes, st));
     SaBlockArgs a{};
     a.B = B; a.L = L; a.D = D; a.H = H; a.mode = mode;
@@ -421,7 +421,7 @@ int sa_forward(const SaCtx& c, cudaStream_t st) {
     if (mode == 1) {
       float* et = w.ET + (size_t)i * Tm * D;
       GemmEpilogue e2;
-      MTAM_TRY(gemm_f32(0, 0, (int)T, D, D, enc, D, c.params + c.sl.Wt + (size_t)i * D * D, D, et, D, e2, c.gemm_ws,
+      MTAM_TRY(gemm_any(g.gemm_mode, 0, 0, (int)T, D, D, enc, D, c.params + c.sl.Wt + (size_t)i * D * D, D, et, D, e2, c.gemm_ws,
                         c.gemm_ws_bytes, st));
       a.ET = et;
       a.gate = c.params + c.sl.gate + (size_t)i * 5 * L * L;
@@ -504,14 +504,14 @@ int sa_backward(const SaCtx& c, cudaStream_t st) {
     const float* W3 = c.params + c.sl.W3 + (size_t)i * D * 3 * D;
     MTAM_TRY(colsum_f32(w.dQKV, 3 * D, nullptr, 0, (int)T, 3 * D, G + c.sl.b3 + (size_t)i * 3 * D, 0, c.colsum_ws,
                         c.colsum_ws_bytes, st));
-    MTAM_TRY(gemm_f32(1, 0, D, 3 * D, (int)T, enc, D, w.dQKV, 3 * D, G + c.sl.W3 + (size_t)i * D * 3 * D, 3 * D, e0,
+    MTAM_TRY(gemm_any(g.gemm_mode, 1, 0, D, 3 * D, (int)T, enc, D, w.dQKV, 3 * D, G + c.sl.W3 + (size_t)i * D * 3 * D, 3 * D, e0,
                       c.gemm_ws, c.gemm_ws_bytes, st));
-    MTAM_TRY(gemm_f32(0, 1, (int)T, D, 3 * D, w.dQKV, 3 * D, W3, 3 * D, dEnc, D, eacc, c.gemm_ws, c.gemm_ws_bytes, st));
+    MTAM_TRY(gemm_any(g.gemm_mode, 0, 1, (int)T, D, 3 * D, w.dQKV, 3 * D, W3, 3 * D, dEnc, D, eacc, c.gemm_ws, c.gemm_ws_bytes, st));
     if (mode == 1) {
       const float* Wt = c.params + c.sl.Wt + (size_t)i * D * D;
-      MTAM_TRY(gemm_f32(1, 0, D, D, (int)T, enc, D, w.dET, D, G + c.sl.Wt + (size_t)i * D * D, D, e0, c.gemm_ws,
+      MTAM_TRY(gemm_any(g.gemm_mode, 1, 0, D, D, (int)T, enc, D, w.dET, D, G + c.sl.Wt + (size_t)i * D * D, D, e0, c.gemm_ws,
                         c.gemm_ws_bytes, st));
-      MTAM_TRY(gemm_f32(0, 1, (int)T, D, D, w.dET, D, Wt, D, dEnc, D, eacc, c.gemm_ws, c.gemm_ws_bytes, st));
+      MTAM_TRY(gemm_any(g.gemm_mode, 0, 1, (int)T, D, D, w.dET, D, Wt, D, dEnc, D, eacc, c.gemm_ws, c.gemm_ws_bytes, st));
       MTAM_TRY(colsum_f32(w.GB, 5 * L * L, nullptr, 0, B, 5 * L * L, G + c.sl.gate + (size_t)i * 5 * L * L, 0,
                           c.colsum_ws, c.colsum_ws_bytes, st));
     }

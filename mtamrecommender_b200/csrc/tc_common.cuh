@@ -1,0 +1,126 @@
+// tcgen05 / TMEM / mbarrier primitives for sm_100a (inline PTX) and the shared-memory tile format
+// used by every tensor-core kernel of this library.
+//
+// Tile format ("row128"): a tile is R rows of 128 bytes (32 fp32), 1024-byte aligned; the 16-byte
+// chunk c of row r is stored at chunk position c ^ (r & 7) (the SWIZZLE_128B pattern).  The same bytes
+// serve two descriptor views:
+//   K-major  operand: row = M/N index, the 32 floats of a row are 32 consecutive K values;
+//   MN-major operand: row = K index,   the 32 floats of a row are 32 consecutive M/N values.
+// Descriptor bit layout follows cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+//
+// Precision: kind::tf32 reads fp32 containers and uses 10 mantissa bits.  Every operand is therefore
+// stored twice, hi = x with the low 13 mantissa bits cleared (exactly representable in tf32, so the
+// hardware's truncation/rounding is a no-op) and lo = x - hi (exact in fp32); a product is issued as
+// lo*hi + hi*lo + hi*hi with fp32 accumulation in TMEM ("3xTF32": ~2^-21 relative error per product).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mtam {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// Bounded spin: a protocol error traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+
+// ---- TMEM ---------------------------------------------------------------------------------------
+// one full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *slot (smem)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (tensor core reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i), columns [c, c+16)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors --------------------------------------------------------------------------------
+// shared-memory matrix descriptor, version 1 (Blackwell); layout_type: 2 = SWIZZLE_128B,
+// 1 = SWIZZLE_128B_BASE32B (the only layout the hardware accepts for MN-major 32-bit operands)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// K-major view of a row128 tile (rows = M/N index, 16-byte chunk c of row r at position c ^ (r & 7)):
+// 8-row groups are 1024 B apart; LBO unused for swizzled K-major (set 16 B)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_saddr, int kstep /*8 floats = 32 B*/) {
+  return smem_desc(tile_saddr + kstep * 32, 16, 1024, 2);
+}
+// MN-major view of a row128 tile (rows = K index, 32-byte unit u of row r at position u ^ (r & 3), i.e.
+// Swizzle<2,5,2>, atoms of 4 K-rows): MN blocks of 32 floats are `block_stride` bytes apart, the two
+// 4-row atoms of one MMA (K = 8) are 512 B apart, consecutive MMAs advance by 1024 B.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, int kstep, uint32_t block_stride) {
+  return smem_desc(tile_saddr + kstep * 1024, block_stride, 512, 1);
+}
+// instruction descriptor, kind::tf32, fp32 accumulate (cute UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- row128 tile stores ---------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ int chunk_pos_k(int row, int chunk) { return chunk ^ (row & 7); }
+__device__ __forceinline__ int chunk_pos_mn(int row, int chunk) { return ((((chunk >> 1) ^ (row & 3)) << 1) | (chunk & 1)); }
+// writes the 16-byte chunk `chunk` of row `row` of the hi and lo tiles (MN: the MN-major swizzle)
+template <bool MN>
+__device__ __forceinline__ void store_chunk_split(float* hi_tile, float* lo_tile, int row, int chunk, float4 v) {
+  const int off = row * 32 + ((MN ? chunk_pos_mn(row, chunk) : chunk_pos_k(row, chunk)) << 2);
+  float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
+}  // namespace tc
+}  // namespace mtam

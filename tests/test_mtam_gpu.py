@@ -14,7 +14,7 @@ def rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-def make(D, L, N, H, B, items, users, cats, seed=7, min_len=2):
+def make(D, L, N, H, B, items, users, cats, seed=7, min_len=2, gemm_mode=0):
     from mtamrecommender_b200 import engine as E
     cfg = O.OracleConfig(kind=O.MTAM, L=L, D=D, H=H, N=N, user_count=users, item_count=items, category_count=cats)
     P = O.init_params(cfg, seed)
@@ -24,7 +24,7 @@ def make(D, L, N, H, B, items, users, cats, seed=7, min_len=2):
             P[k] = (P[k] + 0.1 * rng.standard_normal(P[k].shape)).astype(np.float32)
     feed = O.synth_batch(cfg, B, seed + 2, min_len=min_len)
     eng = E.Engine(E.ModelConfig(kind="MTAM", max_batch=B, L=L, D=D, H=H, N=N, user_count=users, item_count=items,
-                                 category_count=cats))
+                                 category_count=cats, gemm_mode=gemm_mode))
     eng.set_params(P)
     return cfg, P, feed, eng
 
@@ -147,3 +147,33 @@ def test_errors_are_loud():
     big = {k: np.concatenate([v, v]) for k, v in feed.items()}
     with pytest.raises(ValueError):
         eng.train_step(big, 1e-3)
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[3]])
+def test_tensor_core_mode_parity(case):
+    """MTAM_GEMM_TF32X3: dense contractions on tcgen05 (3-term split TF32).  Same fp32-class tolerances."""
+    import torch
+    cfg, P, feed, eng = make(**case, gemm_mode=1)
+    fwd, grads, pieces = O.loss_and_grads(cfg, P, feed)
+    _, g32, _ = O.loss_and_grads(cfg, P, feed, torch.float32)
+    out = eng.forward(feed)
+    assert abs(out["loss"] - float(fwd["loss"].detach())) <= 1e-5 * abs(float(fwd["loss"].detach()))
+    assert rel(out["pred"], fwd["pred"].detach().numpy()) < 1e-5
+    g = eng.gradients(feed)
+    assert abs(np.sqrt(g["__norm_sq__"]) - O.global_norm(pieces)) <= 1e-5 * O.global_norm(pieces)
+    for k, v in grads.items():
+        if v is None:
+            assert not np.any(g[k]), k
+        else:
+            tol = max(1e-4, 3.0 * rel(g32[k], v))
+            assert rel(g[k], v) < tol, (k, rel(g[k], v), tol)
+    tr = O.OracleTrainer(cfg, P)
+    tr32 = O.OracleTrainer(cfg, P, dtype=torch.float32)
+    for s in range(2):
+        lo, lc = tr.train_step(feed, 1e-3), eng.train_step(feed, 1e-3)
+        tr32.train_step(feed, 1e-3)
+        assert abs(lo - lc) <= 2e-5 * abs(lo), (s, lo, lc)
+    newp = eng.get_params()
+    for k, v in tr.params.items():
+        tol = max(1e-4, 3.0 * rel(tr32.params[k], v))
+        assert rel(newp[k], v) < tol, (k, rel(newp[k], v), tol)
