@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "model_kernels.h"
+#include "../../include/mtam.h"
 
 namespace mtam {
 
@@ -283,6 +284,21 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int G,
 
 int ce_grid(int V) { return std::max(1, std::min(cdiv(V, CT), 2 * kNumSMs)); }
 
+// shared with the tensor-core path (ce_tc.cu)
+int ce_finalize(const float2* ms_partial, int G, int B, const float* tlogit, float* lse, float* loss_origin,
+                float* block_partial, int* n_partial, cudaStream_t st) {
+  int nb = cdiv(B, CF_ROWS);
+  ce_finalize_kernel<<<nb, 256, 0, st>>>(ms_partial, G, B, tlogit, lse, loss_origin, block_partial);
+  MTAM_LAUNCH_CHECK();
+  *n_partial = nb;
+  return 0;
+}
+int ce_reduce_partials(const float* partial, int G, int64_t n, float* out, cudaStream_t st) {
+  reduce_partials_kernel<<<cdiv(n, 256), 256, 0, st>>>(partial, G, n, out);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
 size_t ce_workspace_bytes(int B, int D, int V) {
   int G = ce_grid(V);
   return align_up((size_t)G * B * sizeof(float2), 256) + align_up((size_t)G * B * D * sizeof(float), 256) +
@@ -298,15 +314,11 @@ static int ce_fwd_launch(const float* pred, const float* table, const int32_t* t
   size_t smem = (size_t)2 * D * CPAD * sizeof(float);
   MTAM_CUDA_CHECK(cudaFuncSetAttribute(ce_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ce_fwd_kernel<D><<<G, 256, smem, st>>>(pred, table, target, B, V, ms, tlogit);
-  int nb = cdiv(B, CF_ROWS);
-  ce_finalize_kernel<<<nb, 256, 0, st>>>(ms, G, B, tlogit, lse, loss_origin, block_partial);
-  MTAM_LAUNCHES(1);
   MTAM_LAUNCH_CHECK();
-  *n_partial = nb;
-  return 0;
+  return ce_finalize(ms, G, B, tlogit, lse, loss_origin, block_partial, n_partial, st);
 }
 
-int ce_forward(int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
+int ce_forward_f32(int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
                float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial,
                cudaStream_t st) {
   switch (D) {
@@ -325,14 +337,11 @@ static int ce_bwd_launch(const float* pred, const float* table, const int32_t* t
   size_t smem = (size_t)(2 * D * CPAD + 2 * CT * (D + 4) + CT * CPAD) * sizeof(float);
   MTAM_CUDA_CHECK(cudaFuncSetAttribute(ce_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ce_bwd_kernel<D><<<G, 256, smem, st>>>(pred, table, target, lse, B, V, inv_batch, dTable, dpp);
-  int64_t n = (int64_t)B * D;
-  reduce_partials_kernel<<<cdiv(n, 256), 256, 0, st>>>(dpp, G, n, dpred);
-  MTAM_LAUNCHES(1);
   MTAM_LAUNCH_CHECK();
-  return 0;
+  return ce_reduce_partials(dpp, G, (int64_t)B * D, dpred, st);
 }
 
-int ce_backward(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
+int ce_backward_f32(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
                 float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st) {
   switch (D) {
     case 32: return ce_bwd_launch<32>(pred, table, target, lse, B, V, inv_batch, ws, dTable, dpred, st);
@@ -340,6 +349,19 @@ int ce_backward(int D, const float* pred, const float* table, const int32_t* tar
     case 128: return ce_bwd_launch<128>(pred, table, target, lse, B, V, inv_batch, ws, dTable, dpred, st);
   }
   return set_error(-1, "softmax CE: num_units=%d not supported (32, 64, 128)", D);
+}
+
+int ce_forward(int mode, int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
+               float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st) {
+  if (mode == MTAM_GEMM_TF32X3 && ce_tc_supported(D))
+    return ce_forward_tc(D, pred, table, target, B, V, ws, tlogit, lse, loss_origin, block_partial, n_partial, st);
+  return ce_forward_f32(D, pred, table, target, B, V, ws, tlogit, lse, loss_origin, block_partial, n_partial, st);
+}
+int ce_backward(int mode, int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B,
+                int V, float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st) {
+  if (mode == MTAM_GEMM_TF32X3 && ce_tc_supported(D))
+    return ce_backward_tc(D, pred, table, target, lse, B, V, inv_batch, ws, dTable, dpred, st);
+  return ce_backward_f32(D, pred, table, target, lse, B, V, inv_batch, ws, dTable, dpred, st);
 }
 
 }  // namespace mtam

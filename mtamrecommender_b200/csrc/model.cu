@@ -377,7 +377,7 @@ static int mtam_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   phase(h, MTAM_PH_CE_FWD, st);
   if (!with_loss) return 0;
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.tlogit, 0, (size_t)B * sizeof(float), st));
-  MTAM_TRY(ce_forward(D, w.pred, P + l.item, bt->target_item_id, B, c.item_rows, w.ce_ws, w.tlogit, w.lse,
+  MTAM_TRY(ce_forward(c.gemm_mode, D, w.pred, P + l.item, bt->target_item_id, B, c.item_rows, w.ce_ws, w.tlogit, w.lse,
                       w.loss_origin, w.ce_partial, &n_ce, st));
   MTAM_TRY(loss_scalars(h, n_l2, n_ce, global_batch, scalars_out, st));
   return 0;
@@ -417,7 +417,7 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   eacc.accumulate = 1;
   // softmax CE: dense item-table gradient straight into the arena, dpred
   phase(h, MTAM_PH_CE_BWD, st);
-  MTAM_TRY(ce_backward(D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
+  MTAM_TRY(ce_backward(c.gemm_mode, D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
                        w.ce_ws, G + l.item, w.dpred, st));
   // hops
   phase(h, MTAM_PH_HOP_BWD, st);
@@ -492,7 +492,7 @@ static int sa_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float* 
   phase(h, MTAM_PH_CE_FWD, st);
   if (!with_loss) return 0;
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.tlogit, 0, (size_t)bt->B * sizeof(float), st));
-  MTAM_TRY(ce_forward(c.D, w.pred, h->params + h->lay.item, bt->target_item_id, bt->B, c.item_rows, w.ce_ws, w.tlogit,
+  MTAM_TRY(ce_forward(c.gemm_mode, c.D, w.pred, h->params + h->lay.item, bt->target_item_id, bt->B, c.item_rows, w.ce_ws, w.tlogit,
                       w.lse, w.loss_origin, w.ce_partial, &n_ce, st));
   MTAM_TRY(loss_scalars(h, n_l2, n_ce, global_batch, scalars_out, st));
   return 0;
@@ -502,7 +502,7 @@ static int sa_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float* 
   const mtam_config& c = h->cfg;
   Workspace& w = h->ws;
   phase(h, MTAM_PH_CE_BWD, st);
-  MTAM_TRY(ce_backward(c.D, w.pred, h->params + h->lay.item, bt->target_item_id, w.lse, bt->B, c.item_rows,
+  MTAM_TRY(ce_backward(c.gemm_mode, c.D, w.pred, h->params + h->lay.item, bt->target_item_id, w.lse, bt->B, c.item_rows,
                        1.0f / (float)global_batch, w.ce_ws, h->grads + h->lay.item, w.dpred, st));
   phase(h, MTAM_PH_HOP_BWD, st);
   MTAM_TRY(sa_backward(sa_ctx(h, bt), st));

@@ -96,10 +96,19 @@ int bpr_backward(const BprArgs& a, int* n_sq, cudaStream_t st);
 // ---- ce.cu ----------------------------------------------------------------------------------
 int ce_grid(int V);
 size_t ce_workspace_bytes(int B, int D, int V);
-int ce_forward(int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
+// mode = mtam_gemm_mode: exact-fp32 FFMA tiles (ce.cu) or tcgen05 3xTF32 (ce_tc.cu; num_units 32 / 64)
+int ce_forward(int mode, int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
                float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st);
-int ce_backward(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
-                float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st);
+int ce_backward(int mode, int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B,
+                int V, float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st);
+int ce_finalize(const float2* ms_partial, int G, int B, const float* tlogit, float* lse, float* loss_origin,
+                float* block_partial, int* n_partial, cudaStream_t st);
+int ce_reduce_partials(const float* partial, int G, int64_t n, float* out, cudaStream_t st);
+bool ce_tc_supported(int D);
+int ce_forward_tc(int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
+                  float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st);
+int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
+                   float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st);
 
 // ---- optim.cu -------------------------------------------------------------------------------
 int sumsq_num_partials(int64_t n);
