@@ -299,8 +299,12 @@ int ce_reduce_partials(const float* partial, int G, int64_t n, float* out, cudaS
   return 0;
 }
 
+// partial-result slots of the workspace: enough for either path
+static int ce_ws_ranges(int B, int V) { return std::max(ce_grid(V), 2 * ce_tc_ranges(B, V)); }
+size_t ce_ms_region_bytes(int B, int V) { return align_up((size_t)ce_ws_ranges(B, V) * B * sizeof(float2), 256); }
+
 size_t ce_workspace_bytes(int B, int D, int V) {
-  int G = ce_grid(V);
+  int G = ce_ws_ranges(B, V);
   return align_up((size_t)G * B * sizeof(float2), 256) + align_up((size_t)G * B * D * sizeof(float), 256) +
          align_up((size_t)cdiv(B, CF_ROWS) * sizeof(float), 256) + 1024;
 }
@@ -333,7 +337,7 @@ template <int D>
 static int ce_bwd_launch(const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
                          float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st) {
   int G = ce_grid(V);
-  float* dpp = (float*)((char*)ws + align_up((size_t)G * B * sizeof(float2), 256));
+  float* dpp = (float*)((char*)ws + ce_ms_region_bytes(B, V));
   size_t smem = (size_t)(2 * D * CPAD + 2 * CT * (D + 4) + CT * CPAD) * sizeof(float);
   MTAM_CUDA_CHECK(cudaFuncSetAttribute(ce_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ce_bwd_kernel<D><<<G, 256, smem, st>>>(pred, table, target, lse, B, V, inv_batch, dTable, dpp);

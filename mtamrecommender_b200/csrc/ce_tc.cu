@@ -29,10 +29,16 @@ using namespace tc;
 namespace {
 
 constexpr int QM = 128;          // Q tile rows = UMMA M
-constexpr int BX = 64;           // X tile rows = UMMA N of S, K of O
-constexpr int kEpi = 128, kProd = 128, kThreads = 288;
+constexpr int kEpiWarps = 8, kProdWarps = 4;
+constexpr int kEpi = kEpiWarps * 32, kProd = kProdWarps * 32;
+constexpr int kWarpS = kEpiWarps + kProdWarps, kWarpPV = kWarpS + 1;   // the two MMA-issuing warps
+constexpr int kWarpLd = kWarpPV + 1;                                    // bulk-copy issuing warp
+constexpr int kThreads = (kWarpLd + 1) * 32;
 constexpr float kLog2e = 1.4426950408889634f;
 enum { CE_FWD = 0, CE_DP = 1, CE_DT = 2 };
+// X tile rows = UMMA N of S (and K of O).  The forward pass has no second product and room in TMEM for
+// 128-column S buffers; a 128-wide MMA keeps the tensor pipe ahead of the issuing thread.
+__host__ __device__ constexpr int ce_bx(int mode) { return mode == CE_FWD ? 128 : 64; }
 
 // 2^x on the MUFU pipe (ex2.approx: 2 ulp; -inf -> 0)
 __device__ __forceinline__ float ex2(float x) {
@@ -41,8 +47,22 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// TMEM columns
-constexpr uint32_t COL_S0 = 0, COL_S1 = 64, COL_GL0 = 128, COL_GL1 = 192, COL_O = 256, TMEM_COLS = 512;
+// developer timeline (tools/ce_trace.cu builds this file with -DMTAM_CE_TRACE): clock64 of pipeline events of CTA (0,0)
+#ifdef MTAM_CE_TRACE
+__device__ long long g_ce_trace[16 * 64];
+#define CE_TRACE(slot, i)                                                                         \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (i) < 64) g_ce_trace[(slot) * 64 + (i)] = clock64(); \
+  } while (0)
+#else
+#define CE_TRACE(slot, i) ((void)0)
+#endif
+
+// TMEM columns: Q hi/lo (A operand of S); S double-buffered (G hi overwrites S in place); G lo double-buffered;
+// O accumulator.  Forward: S buffers are 128 columns wide and nothing else follows.
+constexpr uint32_t COL_QH = 0, COL_QL = 64, COL_S0 = 128, TMEM_COLS = 512;
+constexpr uint32_t COL_GL0 = 256, COL_O = 384;     // PV modes (S buffers 64 wide: 128, 192; G lo: 256, 320)
+constexpr int MAXST = 4;
 
 struct CeTcArgs {
   const float* pred;
@@ -51,32 +71,36 @@ struct CeTcArgs {
   const float* lse;
   int B, V;
   float inv_batch;
-  int tiles_per_cta;        // FWD/DP: X tiles (of BX items) per CTA
-  float2* ms_partial;       // FWD: [gridDim.x][B]
+  int tiles_per_cta;        // FWD/DP: X tiles (of ce_bx items) per CTA
+  float2* ms_partial;       // FWD: [2*gridDim.x][B]
   float* tlogit;            // FWD: [B]
   float* dpred_partial;     // DP : [gridDim.x][B][D]
   float* dTable;            // DT : [V][D]
 };
 
 struct Bars {
-  uint64_t xk_full[2], xk_empty[2], xm_full[2], xm_empty[2], s_full[2], s_empty[2], g_full[2], o_full;
+  uint64_t xk_full[MAXST], xk_empty[MAXST], xm_full[MAXST], xm_empty[MAXST], stg_full[MAXST], stg_empty[MAXST], s_full[2],
+      s_empty[2], g_full[2], sg_empty[2], o_full;
 };
 
 template <int D, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
+  constexpr int BX = ce_bx(MODE);
   constexpr int KC = D / 32;                      // 32-float (128-byte) chunks of D
-  constexpr int QT = QM * 32, XT = BX * 32;       // floats per chunk tile
+  constexpr int XT = BX * 32;                     // floats per chunk tile
   constexpr bool PV = MODE != CE_FWD;
-  constexpr int STAGE = (PV ? 4 : 2) * KC * XT;   // floats per X stage: K-major hi, lo (, MN-major hi, lo)
+  constexpr int NST = 2;                          // operand stages in shared memory
+  constexpr int STAGE = (PV ? 4 : 2) * KC * XT;   // floats per operand stage: K-major hi, lo (, MN-major hi, lo)
+  constexpr int NSG = PV ? 3 : 4;                 // raw fp32 staging slots (64 X rows each) filled by bulk copies
+  constexpr int SLOT = 64 * D;                    // floats per staging slot
+  constexpr uint32_t SW = BX;                     // S buffer width in TMEM columns
   extern __shared__ uint8_t smem_raw[];
-  float* sm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* Qhi = sm;
-  float* Qlo = Qhi + KC * QT;
-  float* Xs = Qlo + KC * QT;
+  float* Xs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* Stg = Xs + NST * STAGE;
   __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float nl2_s[2][BX];     // CE_DT: -lse*log2(e) of the X tile's pred rows (+inf past B)
-  __shared__ __align__(16) int tgt_s[2][BX];       // CE_DT: their target item ids
+  __shared__ __align__(16) float nl2_s[MAXST][64];   // CE_DT: -lse*log2(e) of the X tile's pred rows (-inf past B)
+  __shared__ __align__(16) int tgt_s[MAXST][64];     // CE_DT: their target item ids
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* Qsrc;
@@ -93,62 +117,104 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < MAXST; ++s) {
       mbar_init(&bars.xk_full[s], kProd);
       mbar_init(&bars.xm_full[s], kProd);
       mbar_init(&bars.xk_empty[s], 1);
       mbar_init(&bars.xm_empty[s], 1);
+      mbar_init(&bars.stg_full[s], 1);
+      mbar_init(&bars.stg_empty[s], kProd);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&bars.s_full[s], 1);
       mbar_init(&bars.s_empty[s], kEpi);
       mbar_init(&bars.g_full[s], kEpi);
+      mbar_init(&bars.sg_empty[s], 1);
     }
     mbar_init(&bars.o_full, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(&tmem_slot, TMEM_COLS);
-  // stationary Q tile: split into hi/lo, K-major swizzled chunk tiles
-  for (int q = tid; q < QM * (D / 4); q += kThreads) {
-    const int row = q / (D / 4), c4 = q % (D / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + row < qmax) v = __ldg(reinterpret_cast<const float4*>(Qsrc + (int64_t)(q0 + row) * D + c4 * 4));
-    store_chunk_split<false>(Qhi + (c4 >> 3) * QT, Qlo + (c4 >> 3) * QT, row, c4 & 7, v);
-  }
-  fence_proxy_async();
+  if (warp == kWarpS) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
-    // ================= producers: global -> registers -> split -> swizzled shared tiles =================
-    const int pt = tid - 128;
-    constexpr int PER = BX * (D / 4) / kProd;
-    float4 r[PER];
-    auto fetch = [&](int i) {
-      const int x0 = (xt_begin + i) * BX;
+  // epilogue thread geometry: TMEM lane quadrant = warp % 4; the two warps of a quadrant split the columns
+  const int quad = warp & 3, half = (warp >> 2) & 1;
+  const int qrow = q0 + quad * 32 + lane;
+  const bool qvalid = qrow < qmax;
+  const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+
+  if (warp < kEpiWarps) {
+    // stationary Q tile -> TMEM (hi / lo split): thread = row, D/2 columns each
+    constexpr int QC = D / 2;
 #pragma unroll
-      for (int j = 0; j < PER; ++j) {
-        const int q = pt + j * kProd;
-        const int row = q / (D / 4), c4 = q % (D / 4);
-        r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x0 + row < xmax) r[j] = __ldg(reinterpret_cast<const float4*>(Xsrc + (int64_t)(x0 + row) * D + c4 * 4));
+    for (int c = 0; c < QC; c += 16) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qvalid) v = __ldg(reinterpret_cast<const float4*>(Qsrc + (int64_t)qrow * D + half * QC + c + j));
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float h = tf32_hi(e[u]);
+          hi[j + u] = __float_as_uint(h);
+          lo[j + u] = __float_as_uint(e[u] - h);
+        }
       }
-    };
-    fetch(0);
-    for (int i = 0; i < n; ++i) {
-      const int st = i & 1, use = i >> 1;
-      float* xs = Xs + st * STAGE;
-      if (i >= 2) mbar_wait(&bars.xk_empty[st], (use - 1) & 1);
+      tmem_st16(lane_base + COL_QH + half * QC + c, hi);
+      tmem_st16(lane_base + COL_QL + half * QC + c, lo);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp >= kEpiWarps && warp < kWarpS) {
+    // ================= producers: global -> registers -> split -> swizzled shared tiles =================
+    // work unit = 64 X rows (a whole tile in the PV modes, half a tile in the forward pass); two units are in
+    // flight in registers so that the loads of unit u+1 are issued before unit u is stored
+    const int pt = tid - kEpi;
+    constexpr int UPT = BX / 64;                        // units per tile
+    constexpr int PER = 64 * (D / 4) / kProd;
+    const int nu = n * UPT;
+    float4 ra[PER];
+    // unit u: wait for its bulk copy, pull this thread's pieces out of the staging slot, hand the slot back
+    auto fetch = [&](float4 (&r)[PER], int u) {
+      const int sl = u % NSG;
+      const int x0 = xt_begin * BX + u * 64;
+      mbar_wait(&bars.stg_full[sl], (u / NSG) & 1);
+      const float4* src = reinterpret_cast<const float4*>(Stg + sl * SLOT);
 #pragma unroll
       for (int j = 0; j < PER; ++j) {
         const int q = pt + j * kProd;
-        const int row = q / (D / 4), c4 = q % (D / 4);
+        r[j] = src[q];
+        if (x0 + q / (D / 4) >= xmax) r[j] = make_float4(0.f, 0.f, 0.f, 0.f);   // rows the copy did not cover
+      }
+      mbar_arrive(&bars.stg_empty[sl]);
+    };
+    auto stash = [&](const float4 (&r)[PER], int u) {
+      const int i = u / UPT, hrow = (u % UPT) * 64;
+      const int st = i % NST, use = i / NST;
+      float* xs = Xs + st * STAGE;
+      if (hrow == 0 && i >= NST) mbar_wait(&bars.xk_empty[st], (use - 1) & 1);
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int q = pt + j * kProd;
+        const int row = hrow + q / (D / 4), c4 = q % (D / 4);
         store_chunk_split<false>(xs + (c4 >> 3) * XT, xs + KC * XT + (c4 >> 3) * XT, row, c4 & 7, r[j]);
       }
-      fence_proxy_async();
-      mbar_arrive(&bars.xk_full[st]);
+      if (hrow + 64 == BX) {
+        fence_proxy_async();
+        mbar_arrive(&bars.xk_full[st]);
+        if (pt == 0) CE_TRACE(0, i);
+      }
       if (PV) {
-        if (i >= 2) mbar_wait(&bars.xm_empty[st], (use - 1) & 1);
+        if (i >= NST) mbar_wait(&bars.xm_empty[st], (use - 1) & 1);
         float* xm = xs + 2 * KC * XT;
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
@@ -156,168 +222,221 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
           const int row = q / (D / 4), c4 = q % (D / 4);
           store_chunk_split<true>(xm + (c4 >> 3) * XT, xm + KC * XT + (c4 >> 3) * XT, row, c4 & 7, r[j]);
         }
-        if (MODE == CE_DT && pt < BX) {
+        if (MODE == CE_DT && pt < 64) {
           const int gr = (xt_begin + i) * BX + pt;
           nl2_s[st][pt] = gr < a.B ? -__ldg(a.lse + gr) * kLog2e : -INFINITY;
           tgt_s[st][pt] = gr < a.B ? __ldg(a.target + gr) : -1;
         }
         fence_proxy_async();
         mbar_arrive(&bars.xm_full[st]);
+        if (pt == 0) CE_TRACE(7, i);
       }
-      if (i + 1 < n) fetch(i + 1);
+    };
+    for (int u = 0; u < nu; ++u) {
+      fetch(ra, u);
+      stash(ra, u);
     }
-  } else if (warp == 8) {
-    // ================= MMA issuer (one thread) =================
+  } else if (warp == kWarpLd) {
+    // ================= loader (one thread): bulk copies of 64 contiguous X rows into the staging ring =================
     if (lane == 0) {
-      const uint32_t qh = smem_u32(Qhi), ql = smem_u32(Qlo);
-      constexpr uint32_t idS = idesc_tf32(QM, BX, 0, 0);
-      constexpr uint32_t idO = idesc_tf32(QM, D, 0, 1);
-      for (int i = 0; i <= n; ++i) {
-        if (i < n) {   // S(i) = Q X(i)^T
-          const int st = i & 1, use = i >> 1;
-          mbar_wait(&bars.xk_full[st], use & 1);
-          if (!PV && i >= 2) mbar_wait(&bars.s_empty[st], (use - 1) & 1);
-          tc_fence_after();
-          const uint32_t xh = smem_u32(Xs + st * STAGE), xl = xh + KC * XT * 4;
-          const uint32_t sacc = tmem + (st ? COL_S1 : COL_S0);
-#pragma unroll
-          for (int kc = 0; kc < KC; ++kc) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ah = desc_kmajor(qh + kc * QT * 4, ks), al = desc_kmajor(ql + kc * QT * 4, ks);
-              const uint64_t bh = desc_kmajor(xh + kc * XT * 4, ks), bl = desc_kmajor(xl + kc * XT * 4, ks);
-              mma_tf32(sacc, al, bh, idS, (kc | ks) != 0);   // small terms first
-              mma_tf32(sacc, ah, bl, idS, true);
-              mma_tf32(sacc, ah, bh, idS, true);
-            }
-          }
-          mma_commit(&bars.s_full[st]);
-          mma_commit(&bars.xk_empty[st]);
-        }
-        if (PV && i >= 1) {   // O += G(j) X(j)
-          const int j = i - 1, st = j & 1, use = j >> 1;
-          mbar_wait(&bars.xm_full[st], use & 1);
-          mbar_wait(&bars.g_full[st], use & 1);
-          tc_fence_after();
-          const uint32_t xmh = smem_u32(Xs + st * STAGE + 2 * KC * XT), xml = xmh + KC * XT * 4;
-          const uint32_t ghi = tmem + (st ? COL_S1 : COL_S0), glo = tmem + (st ? COL_GL1 : COL_GL0);
-#pragma unroll
-          for (int ks = 0; ks < BX / 8; ++ks) {
-            const uint64_t bh = desc_mnmajor(xmh, ks, BX * 128), bl = desc_mnmajor(xml, ks, BX * 128);
-            mma_tf32_ts(tmem + COL_O, glo + ks * 8, bh, idO, (j | ks) != 0);
-            mma_tf32_ts(tmem + COL_O, ghi + ks * 8, bl, idO, true);
-            mma_tf32_ts(tmem + COL_O, ghi + ks * 8, bh, idO, true);
-          }
-          mma_commit(&bars.xm_empty[st]);
-        }
+      const int nu = n * (BX / 64);
+      for (int u = 0; u < nu; ++u) {
+        const int sl = u % NSG;
+        const int x0 = xt_begin * BX + u * 64;
+        if (u >= NSG) mbar_wait(&bars.stg_empty[sl], ((u / NSG) - 1) & 1);
+        const int rows = min(64, xmax - x0);
+        const uint32_t bytes = rows > 0 ? (uint32_t)rows * D * 4 : 0;
+        mbar_arrive_expect_tx(&bars.stg_full[sl], bytes);
+        if (bytes) bulk_g2s(Stg + sl * SLOT, Xsrc + (int64_t)x0 * D, bytes, &bars.stg_full[sl]);
       }
-      if (PV) mma_commit(&bars.o_full);
+    }
+  } else if (warp == kWarpS) {
+    // ================= S issuer (one thread): S(i) = Q X(i)^T, Q read from TMEM =================
+    if (lane == 0) {
+      constexpr uint32_t idS = idesc_tf32(QM, BX, 0, 0);
+      for (int i = 0; i < n; ++i) {
+        const int st = i % NST, use = i / NST, b = i & 1;
+        mbar_wait(&bars.xk_full[st], use & 1);
+        if (i >= 2) mbar_wait(PV ? &bars.sg_empty[b] : &bars.s_empty[b], ((i >> 1) - 1) & 1);   // buffer b consumed
+        tc_fence_after();
+        CE_TRACE(1, i);
+        const uint32_t xh = desc_lo(smem_u32(Xs + st * STAGE), 16);
+        const uint32_t sacc = tmem + COL_S0 + b * SW;
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t qh = tmem + COL_QH + kc * 32 + ks * 8, ql = tmem + COL_QL + kc * 32 + ks * 8;
+            const uint64_t bh = desc_join(xh + ((kc * XT * 4 + ks * 32) >> 4), kDescHiK);
+            const uint64_t bl = desc_join(xh + (((KC + kc) * XT * 4 + ks * 32) >> 4), kDescHiK);
+            mma_tf32_ts(sacc, ql, bh, idS, (kc | ks) != 0);   // small terms first
+            mma_tf32_ts(sacc, qh, bl, idS, true);
+            mma_tf32_ts(sacc, qh, bh, idS, true);
+          }
+        }
+        mma_commit(&bars.s_full[b]);
+        mma_commit(&bars.xk_empty[st]);
+        CE_TRACE(2, i);
+      }
+    }
+  } else if (warp == kWarpPV) {
+    // ================= O issuer (one thread): O += G(j) X(j), G read from TMEM =================
+    if (PV && lane == 0) {
+      constexpr uint32_t idO = idesc_tf32(QM, D, 0, 1);
+      for (int j = 0; j < n; ++j) {
+        const int st = j % NST, use = j / NST, b = j & 1;
+        mbar_wait(&bars.xm_full[st], use & 1);
+        mbar_wait(&bars.g_full[b], (j >> 1) & 1);
+        tc_fence_after();
+        CE_TRACE(5, j);
+        const uint32_t xmh = desc_lo(smem_u32(Xs + st * STAGE + 2 * KC * XT), BX * 128);
+        const uint32_t ghi = tmem + COL_S0 + b * SW, glo = tmem + COL_GL0 + b * SW;
+#pragma unroll
+        for (int ks = 0; ks < BX / 8; ++ks) {
+          const uint64_t bh = desc_join(xmh + ((ks * 1024) >> 4), kDescHiMN);
+          const uint64_t bl = desc_join(xmh + ((KC * XT * 4 + ks * 1024) >> 4), kDescHiMN);
+          mma_tf32_ts(tmem + COL_O, glo + ks * 8, bh, idO, (j | ks) != 0);
+          mma_tf32_ts(tmem + COL_O, ghi + ks * 8, bl, idO, true);
+          mma_tf32_ts(tmem + COL_O, ghi + ks * 8, bh, idO, true);
+        }
+        mma_commit(&bars.xm_empty[st]);
+        mma_commit(&bars.sg_empty[b]);
+        CE_TRACE(6, j);
+      }
+      mma_commit(&bars.o_full);
     }
   } else {
-    // ================= epilogue warps: thread = one Q row (TMEM lane) =================
-    const int qrow = q0 + warp * 32 + lane;
-    const bool qvalid = qrow < qmax;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // ================= epilogue warps: thread = one Q row (TMEM lane) x half of the tile's columns =================
+    constexpr int HC = BX / 2;    // columns per thread per tile
     int tg = -1;
-    float nl2 = 0.f;          // CE_DP: -lse[row]*log2(e)
+    float nl2 = 0.f;              // CE_DP: -lse[row]*log2(e)
     float m = -INFINITY, s = 0.f;
     if (MODE != CE_DT && qvalid) {
       tg = __ldg(a.target + qrow);
       if (MODE == CE_DP) nl2 = -__ldg(a.lse + qrow) * kLog2e;
     }
+    const float gscale = qvalid ? a.inv_batch : 0.f;
     for (int i = 0; i < n; ++i) {
-      const int st = i & 1, use = i >> 1;
-      const int x0 = (xt_begin + i) * BX;
-      mbar_wait(&bars.s_full[st], use & 1);
-      if (MODE == CE_DT) mbar_wait(&bars.xm_full[st], use & 1);
+      const int st = i % NST, b = i & 1, ub = i >> 1;
+      const int x0 = (xt_begin + i) * BX + half * HC;
+      mbar_wait(&bars.s_full[b], ub & 1);
+      if (MODE == CE_DT) mbar_wait(&bars.xm_full[st], (i / NST) & 1);
       tc_fence_after();
-      const uint32_t scol = lane_base + (st ? COL_S1 : COL_S0), gcol = lane_base + (st ? COL_GL1 : COL_GL0);
-#pragma unroll 1
-      for (int c = 0; c < BX; c += 16) {
+      if (lane == 0 && quad == 0) CE_TRACE(3 + 5 * half, i);
+      const uint32_t scol = lane_base + COL_S0 + b * SW + half * HC, gcol = lane_base + COL_GL0 + b * SW + half * HC;
+      const bool ragged = x0 + HC > xmax;          // only the catalogue's last tile (warp-uniform)
+      if (MODE == CE_FWD) {
+        // pull this thread's 64 logits out of TMEM in one go and hand the S buffer straight back to the tensor core
+        uint32_t r[HC];
+        {
+          uint32_t (&r0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
+          uint32_t (&r1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[HC - 32]);
+          tmem_ld32_nowait(scol, r0);
+          if (HC > 32) tmem_ld32_nowait(scol + 32, r1);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(&bars.s_empty[b]);
+        if (lane == 0 && quad == 0) CE_TRACE(4 + 5 * half, i);
+        float v[HC];
+#pragma unroll
+        for (int j = 0; j < HC; ++j) v[j] = __uint_as_float(r[j]);
+        if ((unsigned)(tg - x0) < (unsigned)HC) {
+#pragma unroll
+          for (int j = 0; j < HC; ++j)
+            if (x0 + j == tg) a.tlogit[qrow] = v[j];
+        }
+        if (ragged) {
+#pragma unroll
+          for (int j = 0; j < HC; ++j)
+            if (x0 + j >= xmax) v[j] = -INFINITY;
+        }
+        float c0 = v[0], c1 = v[1], c2 = v[2], c3 = v[3];
+#pragma unroll
+        for (int j = 4; j < HC; j += 4) {
+          c0 = fmaxf(c0, v[j]); c1 = fmaxf(c1, v[j + 1]); c2 = fmaxf(c2, v[j + 2]); c3 = fmaxf(c3, v[j + 3]);
+        }
+        const float mn = fmaxf(fmaxf(m, fmaxf(c0, c1)), fmaxf(c2, c3));
+        if (mn > -INFINITY) {          // false only while every column so far was masked
+          s *= ex2((m - mn) * kLog2e); // m = -inf: s is 0 and 2^-inf = 0
+          m = mn;
+          const float nm2 = -mn * kLog2e;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < HC; j += 4) {
+            a0 += ex2(fmaf(v[j], kLog2e, nm2));
+            a1 += ex2(fmaf(v[j + 1], kLog2e, nm2));
+            a2 += ex2(fmaf(v[j + 2], kLog2e, nm2));
+            a3 += ex2(fmaf(v[j + 3], kLog2e, nm2));
+          }
+          s += (a0 + a1) + (a2 + a3);
+        }
+        continue;
+      }
+#pragma unroll
+      for (int c = 0; c < HC; c += 16) {
         float v[16];
         tmem_ld16(scol + c, v);
         const int col0 = x0 + c;
-        if (MODE == CE_FWD) {
-          if ((unsigned)(tg - col0) < 16u) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col0 + j == tg) a.tlogit[qrow] = v[j];
-          }
-          if (col0 + 16 > xmax) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col0 + j >= xmax) v[j] = -INFINITY;
-          }
-          float cm = v[0];
-#pragma unroll
-          for (int j = 1; j < 16; ++j) cm = fmaxf(cm, v[j]);
-          if (cm > m) {
-            s *= ex2((m - cm) * kLog2e);     // m = -inf: s is 0 and exp2(-inf) = 0
-            m = cm;
-          }
-          if (m > -INFINITY) {
-            const float nm2 = -m * kLog2e;
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc += ex2(fmaf(v[j], kLog2e, nm2));
-            s += acc;
-          }
-        } else {
+        {
           uint32_t hi[16], lo[16];
           if (MODE == CE_DP) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float p = ex2(fmaf(v[j], kLog2e, nl2));
-              if (col0 + j == tg) p -= 1.f;
-              float g = (qvalid && col0 + j < xmax) ? p * a.inv_batch : 0.f;
-              v[j] = g;
+            for (int j = 0; j < 16; ++j) v[j] = ex2(fmaf(v[j], kLog2e, nl2));
+            if ((unsigned)(tg - col0) < 16u) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j == tg) v[j] -= 1.f;
+            }
+            if (ragged) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + j >= xmax) v[j] = 0.f;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 l4 = *reinterpret_cast<const float4*>(&nl2_s[st][c + j]);
-              const int4 t4 = *reinterpret_cast<const int4*>(&tgt_s[st][c + j]);
+              const float4 l4 = *reinterpret_cast<const float4*>(&nl2_s[st][half * HC + c + j]);
+              const int4 t4 = *reinterpret_cast<const int4*>(&tgt_s[st][half * HC + c + j]);
               const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
               const int ts[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                float p = ex2(fmaf(v[j + u], kLog2e, ls[u]));   // rows past B: exp2(-inf) = 0
+                float p = ex2(fmaf(v[j + u], kLog2e, ls[u]));   // pred rows past B: 2^-inf = 0
                 if (ts[u] == qrow) p -= 1.f;
-                v[j + u] = qvalid ? p * a.inv_batch : 0.f;
+                v[j + u] = p;
               }
             }
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float h = tf32_hi(v[j]);
+            const float g = v[j] * gscale;          // rows past the Q range: 0
+            const float h = tf32_hi(g);
             hi[j] = __float_as_uint(h);
-            lo[j] = __float_as_uint(v[j] - h);
+            lo[j] = __float_as_uint(g - h);
           }
           tmem_st16(scol + c, hi);
           tmem_st16(gcol + c, lo);
         }
       }
-      if (MODE == CE_FWD) {
-        tc_fence_before();
-        mbar_arrive(&bars.s_empty[st]);
-      } else {
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bars.g_full[st]);
-      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bars.g_full[b]);
+      if (lane == 0 && quad == 0) CE_TRACE(4 + 5 * half, i);
     }
     if (MODE == CE_FWD) {
-      if (qvalid) a.ms_partial[(int64_t)blockIdx.x * a.B + qrow] = make_float2(m, s);
+      if (qvalid) a.ms_partial[(int64_t)(blockIdx.x * 2 + half) * a.B + qrow] = make_float2(m, s);
     } else {
+      constexpr int OC = D / 2;
       mbar_wait(&bars.o_full, 0);
       tc_fence_after();
       float* dst = nullptr;
       if (qvalid)
-        dst = (MODE == CE_DP) ? a.dpred_partial + ((int64_t)blockIdx.x * a.B + qrow) * D : a.dTable + (int64_t)qrow * D;
-#pragma unroll 1
-      for (int c = 0; c < D; c += 16) {
+        dst = ((MODE == CE_DP) ? a.dpred_partial + ((int64_t)blockIdx.x * a.B + qrow) * D : a.dTable + (int64_t)qrow * D) + half * OC;
+#pragma unroll
+      for (int c = 0; c < OC; c += 16) {
         float v[16];
-        tmem_ld16(lane_base + COL_O + c, v);
+        tmem_ld16(lane_base + COL_O + half * OC + c, v);
         if (dst) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
@@ -328,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kWarpS) {
     __syncwarp();
     tmem_dealloc(tmem, TMEM_COLS);
   }
@@ -337,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
 template <int D, int MODE>
 int ce_tc_launch(dim3 grid, const CeTcArgs& a, cudaStream_t st) {
   constexpr int KC = D / 32;
-  const size_t smem = (size_t)(2 * KC * QM * 32 + 2 * (MODE == CE_FWD ? 2 : 4) * KC * BX * 32) * sizeof(float) + 1024;
+  const size_t smem = (size_t)(2 * (MODE == CE_FWD ? 2 : 4) * KC * ce_bx(MODE) * 32 + (MODE == CE_FWD ? 4 : 3) * 64 * D) * sizeof(float) + 1024;
   MTAM_CUDA_CHECK(cudaFuncSetAttribute(ce_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ce_tc_kernel<D, MODE><<<grid, kThreads, smem, st>>>(a);
   MTAM_LAUNCH_CHECK();
@@ -345,8 +464,8 @@ int ce_tc_launch(dim3 grid, const CeTcArgs& a, cudaStream_t st) {
 }
 
 // FWD / DP: the catalogue is cut into gridDim.x ranges of `tiles_per_cta` X tiles, one CTA per (range, row tile)
-void ce_tc_partition(int B, int V, int* G, int* tiles_per_cta) {
-  const int total = cdiv(V, BX), rowtiles = cdiv(B, QM);
+void ce_tc_partition(int mode, int B, int V, int* G, int* tiles_per_cta) {
+  const int total = cdiv(V, ce_bx(mode)), rowtiles = cdiv(B, QM);
   const int want = std::max(1, kNumSMs / rowtiles);
   *tiles_per_cta = cdiv(total, want);
   *G = cdiv(total, *tiles_per_cta);
@@ -357,9 +476,10 @@ void ce_tc_partition(int B, int V, int* G, int* tiles_per_cta) {
 bool ce_tc_supported(int D) { return D == 32 || D == 64; }
 
 int ce_tc_ranges(int B, int V) {
-  int G, tpc;
-  ce_tc_partition(B, V, &G, &tpc);
-  return G;
+  int G0, G1, tpc;
+  ce_tc_partition(CE_FWD, B, V, &G0, &tpc);
+  ce_tc_partition(CE_DP, B, V, &G1, &tpc);
+  return std::max(G0, G1);
 }
 
 int ce_forward_tc(int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
@@ -367,14 +487,14 @@ int ce_forward_tc(int D, const float* pred, const float* table, const int32_t* t
   CeTcArgs a{};
   a.pred = pred; a.table = table; a.target = target; a.B = B; a.V = V;
   int G;
-  ce_tc_partition(B, V, &G, &a.tiles_per_cta);
+  ce_tc_partition(CE_FWD, B, V, &G, &a.tiles_per_cta);
   a.ms_partial = (float2*)ws;
   a.tlogit = tlogit;
   dim3 grid(G, cdiv(B, QM));
   if (D == 64) MTAM_TRY((ce_tc_launch<64, CE_FWD>(grid, a, st)));
   else if (D == 32) MTAM_TRY((ce_tc_launch<32, CE_FWD>(grid, a, st)));
   else return set_error(-1, "tensor-core softmax CE: num_units=%d not supported (32, 64)", D);
-  return ce_finalize(a.ms_partial, G, B, tlogit, lse, loss_origin, block_partial, n_partial, st);
+  return ce_finalize(a.ms_partial, 2 * G, B, tlogit, lse, loss_origin, block_partial, n_partial, st);
 }
 
 int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
@@ -382,8 +502,8 @@ int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* 
   CeTcArgs a{};
   a.pred = pred; a.table = table; a.target = target; a.lse = lse; a.B = B; a.V = V; a.inv_batch = inv_batch;
   int G;
-  ce_tc_partition(B, V, &G, &a.tiles_per_cta);
-  a.dpred_partial = (float*)((char*)ws + align_up((size_t)ce_grid(V) * B * sizeof(float2), 256));
+  ce_tc_partition(CE_DP, B, V, &G, &a.tiles_per_cta);
+  a.dpred_partial = (float*)((char*)ws + ce_ms_region_bytes(B, V));
   a.dTable = dTable;
   dim3 grid_dp(G, cdiv(B, QM)), grid_dt(cdiv(V, QM));
   if (D == 64) {

@@ -105,6 +105,8 @@ int ce_finalize(const float2* ms_partial, int G, int B, const float* tlogit, flo
                 float* block_partial, int* n_partial, cudaStream_t st);
 int ce_reduce_partials(const float* partial, int G, int64_t n, float* out, cudaStream_t st);
 bool ce_tc_supported(int D);
+int ce_tc_ranges(int B, int V);
+size_t ce_ms_region_bytes(int B, int V);
 int ce_forward_tc(int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
                   float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st);
 int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,

@@ -92,6 +92,17 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_saddr, int kstep /
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, int kstep, uint32_t block_stride) {
   return smem_desc(tile_saddr + kstep * 1024, block_stride, 512, 1);
 }
+// The two 32-bit halves of a descriptor, so that an issue loop can advance the address field with one 32-bit add
+// (the address field is the low 14 bits of `lo` in 16-byte units; offsets inside one allocation never carry out of it).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+constexpr uint32_t kDescHiK = desc_hi(1024, 2);    // K-major SWIZZLE_128B
+constexpr uint32_t kDescHiMN = desc_hi(512, 1);    // MN-major SWIZZLE_128B_BASE32B
 // instruction descriptor, kind::tf32, fp32 accumulate (cute UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -140,6 +151,16 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ---- bulk asynchronous copy (TMA engine, no tensor map): global -> shared, completion on an mbarrier ----
+// the issuing thread first announces the byte count, then starts the copy; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // plain arrive (count 1) by a thread of this CTA
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -1,0 +1,57 @@
+// Developer probe: pipeline timeline of the tensor-core CE kernels (events of CTA (0,0), cycles relative to the first).
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -DMTAM_CE_TRACE \
+//   -I mtamrecommender_b200/csrc tools/ce_trace.cu mtamrecommender_b200/csrc/{ce.cu,util.cu} -o tools/ce_trace.bin
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../mtamrecommender_b200/csrc/ce_tc.cu"
+
+int main(int argc, char** argv) {
+  using namespace mtam;
+  const int B = 1024, V = 100003, D = 64;
+  const int mode = argc > 1 ? atoi(argv[1]) : 0;
+  std::vector<float> hp((size_t)B * D), ht((size_t)V * D);
+  for (auto& x : hp) x = (rand() / (float)RAND_MAX - 0.5f) * 2.f;
+  for (auto& x : ht) x = (rand() / (float)RAND_MAX - 0.5f) * 0.6f;
+  std::vector<int> htg(B);
+  for (auto& x : htg) x = rand() % V;
+  float *pred, *table, *tlogit, *lse, *lo, *bp, *dT, *dp;
+  int* tg;
+  void* ws;
+  size_t wsb = ce_workspace_bytes(B, D, V);
+  cudaMalloc(&pred, hp.size() * 4); cudaMalloc(&table, ht.size() * 4); cudaMalloc(&tg, B * 4);
+  cudaMalloc(&tlogit, B * 4); cudaMalloc(&lse, B * 4); cudaMalloc(&lo, B * 4); cudaMalloc(&bp, 4096);
+  cudaMalloc(&dT, ht.size() * 4); cudaMalloc(&dp, hp.size() * 4); cudaMalloc(&ws, wsb);
+  cudaMemcpy(pred, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(table, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(tg, htg.data(), B * 4, cudaMemcpyHostToDevice);
+  int np = 0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    if (mode == 0) ce_forward_tc(D, pred, table, tg, B, V, ws, tlogit, lse, lo, bp, &np, 0);
+    else {
+      if (rep == 0) ce_forward_tc(D, pred, table, tg, B, V, ws, tlogit, lse, lo, bp, &np, 0);
+      ce_backward_tc(D, pred, table, tg, lse, B, V, 1.f / B, ws, dT, dp, 0);
+    }
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("rep %d: %.1f us  %s\n", rep, ms * 1e3, cudaGetErrorString(e));
+  }
+  long long h[16 * 64];
+  cudaMemcpyFromSymbol(h, g_ce_trace, sizeof(h));
+  long long t0 = h[0];
+  const char* names[] = {"prod xk_full", "mma  S wait ok", "mma  S issued", "epi0 s_full ok", "epi0 arrived", "mma  g_full ok",
+                         "mma  PV issued", "prod xm_full", "epi1 s_full ok", "epi1 arrived"};
+  printf("%-16s", "tile");
+  for (int i = 0; i < 12; ++i) printf("%8d", i + 20);
+  printf("\n");
+  for (int s = 0; s < 10; ++s) {
+    printf("%-16s", names[s]);
+    for (int i = 20; i < 32; ++i) printf("%8lld", h[s * 64 + i] ? h[s * 64 + i] - h[0 * 64 + 20] : -1);
+    printf("\n");
+  }
+  return 0;
+}
