@@ -16,16 +16,29 @@ namespace mtam {
 
 constexpr int GM = 64, GN = 64, GK = 16, GT = 256;
 
+struct GemmBatch {
+  int S;                 // > 0: blockIdx.z = problem * S + split
+  int64_t sA, sB, sC;    // element strides between problems
+};
+
 template <int TA, int TB, int VA, int VB>
 __global__ void __launch_bounds__(GT) gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                       const float* __restrict__ B, int ldb, float* __restrict__ C,
-                                                      int ldc, EpiDev epi, int kchunk, float* __restrict__ partial) {
+                                                      int ldc, EpiDev epi, int kchunk, float* __restrict__ partial,
+                                                      GemmBatch bt) {
   __shared__ __align__(16) float As[GK][GM + 4];
   __shared__ __align__(16) float Bs[GK][GN + 4];
   const int t = threadIdx.x;
   const int tx = t & 15, ty = t >> 4;
   const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
-  const int kbeg = blockIdx.z * kchunk;
+  int zsplit = blockIdx.z;
+  if (bt.S > 0) {   // batched: blockIdx.z = problem * S + split
+    const int p = zsplit / bt.S;
+    zsplit -= p * bt.S;
+    A += p * bt.sA; B += p * bt.sB; C += p * bt.sC;
+    if (partial) partial += (int64_t)p * bt.S * M * N;
+  }
+  const int kbeg = zsplit * kchunk;
   const int kend = min(K, kbeg + kchunk);
   float acc[4][4];
 #pragma unroll
@@ -126,7 +139,7 @@ __global__ void __launch_bounds__(GT) gemm_f32_kernel(int M, int N, int K, const
       int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       if (partial)
-        partial[((int64_t)blockIdx.z * M + m) * N + n] = acc[i][j];
+        partial[((int64_t)zsplit * M + m) * N + n] = acc[i][j];
       else
         C[(int64_t)m * ldc + n] = apply_epi(acc[i][j], m, n, epi, C, ldc);
     }
@@ -134,9 +147,11 @@ __global__ void __launch_bounds__(GT) gemm_f32_kernel(int M, int N, int K, const
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, int M, int N, float* __restrict__ C,
-                                     int ldc, EpiDev epi) {
+                                     int ldc, EpiDev epi, int64_t sC) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * N) return;
+  partial += (int64_t)blockIdx.y * S * M * N;   // batched: one problem per blockIdx.y
+  C += (int64_t)blockIdx.y * sC;
   int m = (int)(i / N), n = (int)(i % N);
   float s = 0.f;
   for (int z = 0; z < S; ++z) s += partial[(int64_t)z * M * N + i];  // fixed order: deterministic
@@ -145,7 +160,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, i
 
 int splitk_reduce(const float* partial, int S, int M, int N, float* C, int ldc, const EpiDev& epi, cudaStream_t st) {
   int64_t tot = (int64_t)M * N;
-  splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, st>>>(partial, S, M, N, C, ldc, epi);
+  splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, st>>>(partial, S, M, N, C, ldc, epi, 0);
   MTAM_LAUNCH_CHECK();
   return 0;
 }
@@ -185,7 +200,7 @@ int gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int ld
   // with split-K the chunk starts are multiples of GK=16 so alignment of k offsets is preserved
   dim3 grid(cdiv(N, GN), cdiv(M, GM), S);
 #define LAUNCH(TA, TB, VA, VB) \
-  gemm_f32_kernel<TA, TB, VA, VB><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, epi, kchunk, partial)
+  gemm_f32_kernel<TA, TB, VA, VB><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, epi, kchunk, partial, bt)
 #define DISPATCH_V(TA, TB)                     \
   do {                                         \
     if (va && vb) LAUNCH(TA, TB, 1, 1);        \
@@ -193,20 +208,54 @@ int gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int ld
     else if (vb) LAUNCH(TA, TB, 0, 1);         \
     else LAUNCH(TA, TB, 0, 0);                 \
   } while (0)
+  GemmBatch bt{0, 0, 0, 0};
   if (!transA && !transB) DISPATCH_V(0, 0);
   else if (!transA && transB) DISPATCH_V(0, 1);
   else if (transA && !transB) DISPATCH_V(1, 0);
   else DISPATCH_V(1, 1);
-#undef DISPATCH_V
-#undef LAUNCH
   MTAM_LAUNCH_CHECK();
   if (S > 1) {
     int64_t tot = (int64_t)M * N;
-    splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, st>>>(partial, S, M, N, C, ldc, epi);
+    splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, st>>>(partial, S, M, N, C, ldc, epi, 0);
     MTAM_LAUNCH_CHECK();
   }
   return 0;
 }
+
+// P independent products C_p = A_p^T B_p of the same shape (A_p = A + p*sA stored [K,M], B_p = B + p*sB stored
+// [K,N], C_p = C + p*sC), always split along K so that the P small problems fill the machine; partials are summed
+// in a fixed order.  Used for the per-hop weight gradients (M = N = num_units, K = batch).
+static int batched_splits(int P, int M, int N, int K) {
+  int tiles = P * cdiv(M, GM) * cdiv(N, GN);
+  int S = std::max(1, std::min(cdiv(2 * kNumSMs, tiles), std::max(1, K / 64)));
+  int kchunk = cdiv(cdiv(K, S), GK) * GK;
+  return cdiv(K, kchunk);
+}
+size_t gemm_atb_batched_workspace_bytes(int P, int M, int N, int K) {
+  return (size_t)P * batched_splits(P, M, N, K) * M * N * sizeof(float) + 256;
+}
+int gemm_atb_batched_f32(int P, int M, int N, int K, const float* A, int lda, int64_t sA, const float* B, int ldb,
+                         int64_t sB, float* C, int ldc, int64_t sC, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (P <= 0 || M <= 0 || N <= 0) return 0;
+  EpiDev epi{nullptr, nullptr, nullptr, 0, 0, 0, 0, 1.f};
+  const int S = batched_splits(P, M, N, std::max(K, 1));
+  const int kchunk = K > 0 ? cdiv(cdiv(K, S), GK) * GK : GK;
+  const size_t need = (size_t)P * S * M * N * sizeof(float);
+  if (!ws || ws_bytes < need) return set_error(MTAM_ERR_WORKSPACE, "batched gemm workspace %zu < %zu", ws_bytes, need);
+  float* partial = (float*)ws;
+  const bool va = ((uintptr_t)A % 16 == 0) && (lda % 4 == 0) && (sA % 4 == 0);
+  const bool vb = ((uintptr_t)B % 16 == 0) && (ldb % 4 == 0) && (sB % 4 == 0);
+  GemmBatch bt{S, sA, sB, sC};
+  dim3 grid(cdiv(N, GN), cdiv(M, GM), P * S);
+  DISPATCH_V(1, 0);
+  MTAM_LAUNCH_CHECK();
+  dim3 rgrid(cdiv((int64_t)M * N, 256), P);
+  splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(partial, S, M, N, C, ldc, epi, sC);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+#undef DISPATCH_V
+#undef LAUNCH
 
 // ---- deterministic column sums: out[n] = sum_m A[m,n] * (Bmul ? Bmul[m,n] : 1) -----------------
 // Two stages (per-row-block partials, then a fixed-order sum over the blocks).  The number of row blocks is

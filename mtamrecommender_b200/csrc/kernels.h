@@ -40,6 +40,10 @@ size_t gemm_splitk_workspace_bytes(int M, int N, int K);
 int gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const GemmEpilogue& epi, void* splitk_ws, size_t splitk_ws_bytes,
              cudaStream_t st);
+// P small products C_p = A_p^T B_p (A_p stored [K,M], B_p stored [K,N]) in one launch, split along K
+size_t gemm_atb_batched_workspace_bytes(int P, int M, int N, int K);
+int gemm_atb_batched_f32(int P, int M, int N, int K, const float* A, int lda, int64_t sA, const float* B, int ldb,
+                         int64_t sB, float* C, int ldc, int64_t sC, void* ws, size_t ws_bytes, cudaStream_t st);
 // tc_gemm.cu: same contract on tcgen05 (3xTF32), and the mode dispatcher
 int gemm_tf32x3(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const GemmEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -224,6 +224,7 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
     w.dGX = b.take<float>(T * 3 * D);
     w.vec_partial = b.take<float>((int64_t)gru_num_blocks(B) * 8 * D);
     G(D, 2 * N * D, T); G(D, 3 * D, T); G(D, 2 * D, T); G(D, D, T); G(D, D, B);
+    gemm_ws = std::max(gemm_ws, gemm_atb_batched_workspace_bytes(N, (int)D, (int)D, (int)B));
     CS(T, 2 * N * D); CS(T, 3 * D); CS(B, 5 * N * L); CS(B, N * D); CS(gru_num_blocks(B), 8 * D); CS(B, D);
   } else if (c.kind == MTAM_KIND_BPRMF) {
     w.bU = b.take<float>(B * D); w.bIP = b.take<float>(B * D); w.bdU = b.take<float>(B * D);
@@ -439,11 +440,11 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   MTAM_TRY(colsum(h, w.DOUT, N * D, w.XH, N * D, B, N * D, G + l.lng, st));
   MTAM_TRY(colsum(h, w.DQP, N * D, nullptr, 0, B, N * D, G + l.bq, st));
   MTAM_TRY(colsum(h, w.GB, 5 * N * L, nullptr, 0, B, 5 * N * L, G + l.gate, st));
-  for (int i = 0; i < N; ++i) {
-    const float* qin = w.Qin + (size_t)i * B * D;
-    MTAM_TRY(gemm(h, 1, 0, D, D, B, qin, D, w.DQP + (size_t)i * D, N * D, G + l.Wq + (size_t)i * D * D, D, e0, st));
-    MTAM_TRY(gemm(h, 1, 0, D, D, B, qin, D, w.DQT + (size_t)i * D, N * D, G + l.Wt + (size_t)i * D * D, D, e0, st));
-  }
+  // dWq_i = Qin_i^T dQpre_i, dWt_i = Qin_i^T dQt_i: the N hops of each in one batched split-K launch
+  MTAM_TRY(gemm_atb_batched_f32(N, D, D, B, w.Qin, D, (int64_t)B * D, w.DQP, N * D, D, G + l.Wq, D, (int64_t)D * D,
+                                w.gemm_ws, w.gemm_ws_bytes, st));
+  MTAM_TRY(gemm_atb_batched_f32(N, D, D, B, w.Qin, D, (int64_t)B * D, w.DQT, N * D, D, G + l.Wt, D, (int64_t)D * D,
+                                w.gemm_ws, w.gemm_ws_bytes, st));
   MTAM_TRY(colsum(h, w.dKV, 2 * N * D, nullptr, 0, (int)T, 2 * N * D, G + l.bkv, st));
   MTAM_TRY(gemm(h, 1, 0, D, 2 * N * D, (int)T, w.X, D, w.dKV, 2 * N * D, G + l.Wkv, 2 * N * D, e0, st));
   MTAM_TRY(gemm(h, 0, 1, (int)T, D, 2 * N * D, w.dKV, 2 * N * D, P + l.Wkv, 2 * N * D, w.dX, D, eacc, st));
