@@ -139,6 +139,20 @@ int mtam_scatter_add(float* dst, int32_t table_rows, int32_t D, const int32_t* i
                      int32_t ld_rows, int64_t n, void* workspace, size_t workspace_bytes, int32_t* unique_idx,
                      int32_t* n_unique, void* stream);
 
+/* The two halves of mtam_scatter_add, separately callable: the index sort depends only on the batch's ids, so a
+ * training step runs it off the critical path (and once per id list, however many tables share it); the
+ * segmented reduction is the HBM-bound part.
+ *  mtam_sort_indices: stable LSD radix sort of (keys[i], i), keys in [0, key_bound).  *keys_sorted and *perm
+ *    (perm[j] = original position of the j-th smallest key) point INTO the workspace on return.
+ *  mtam_scatter_add_sorted: dst[keys_sorted[j],:] += rows[perm[j],:] (perm NULL: rows already in sorted order),
+ *    rows of one key added in ascending j.  dst rows are D floats apart. */
+size_t mtam_sort_workspace(int64_t n, int32_t key_bound);
+int mtam_sort_indices(const int32_t* keys, int64_t n, int32_t key_bound, void* workspace, size_t workspace_bytes,
+                      const int32_t** keys_sorted, const int32_t** perm, void* stream);
+size_t mtam_scatter_add_sorted_workspace(int64_t n, int32_t D);
+int mtam_scatter_add_sorted(float* dst, int32_t D, const int32_t* keys_sorted, const int32_t* perm, const float* rows,
+                            int32_t ld_rows, int64_t n, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- model --------------------------------------------------------------------------------- */
 
 int mtam_plan(const mtam_config* cfg, mtam_sizes* out);

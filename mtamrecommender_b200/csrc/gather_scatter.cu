@@ -589,3 +589,28 @@ extern "C" int mtam_scatter_add(float* dst, int32_t table_rows, int32_t D, const
   return mtam::scatter_add_rows(dst, table_rows, D, D, idx, rows, ld_rows, n, workspace, workspace_bytes, unique_idx,
                                 n_unique, (cudaStream_t)stream);
 }
+
+extern "C" size_t mtam_sort_workspace(int64_t n, int32_t key_bound) { return mtam::sort_workspace_bytes(n, key_bound); }
+
+extern "C" int mtam_sort_indices(const int32_t* keys, int64_t n, int32_t key_bound, void* workspace, size_t workspace_bytes,
+                                 const int32_t** keys_sorted, const int32_t** perm, void* stream) {
+  if (n < 0 || key_bound <= 0 || !keys_sorted || !perm || (n > 0 && (!keys || !workspace)))
+    return mtam::set_error(MTAM_ERR_INVALID, "mtam_sort_indices: bad argument");
+  if (n == 0) {
+    *keys_sorted = *perm = nullptr;
+    return 0;
+  }
+  return mtam::sort_by_row(keys, n, key_bound, workspace, workspace_bytes, keys_sorted, perm, (cudaStream_t)stream);
+}
+
+extern "C" size_t mtam_scatter_add_sorted_workspace(int64_t n, int32_t D) { return mtam::seg_reduce_workspace_bytes(n, D); }
+
+extern "C" int mtam_scatter_add_sorted(float* dst, int32_t D, const int32_t* keys_sorted, const int32_t* perm,
+                                       const float* rows, int32_t ld_rows, int64_t n, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  if (!dst || n < 0 || (n > 0 && (!keys_sorted || !rows || !workspace)))
+    return mtam::set_error(MTAM_ERR_INVALID, "mtam_scatter_add_sorted: null/negative argument");
+  if (ld_rows < D) return mtam::set_error(MTAM_ERR_INVALID, "mtam_scatter_add_sorted: ld_rows < D");
+  return mtam::seg_reduce_sorted(keys_sorted, perm, rows, ld_rows, n, D, dst, D, workspace, workspace_bytes,
+                                 (cudaStream_t)stream);
+}

@@ -362,3 +362,76 @@ def scatter_add(dst: torch.Tensor, idx: torch.Tensor, rows: torch.Tensor, worksp
     if want_unique:
         return dst, uniq, nuniq
     return dst
+
+
+class SortedIndices:
+    """Result of `sort_indices`: sorted keys and the permutation, as int32 views into the sort workspace."""
+
+    def __init__(self, keys_sorted: torch.Tensor, perm: torch.Tensor, workspace: torch.Tensor):
+        self.keys_sorted, self.perm, self.workspace = keys_sorted, perm, workspace
+
+
+def sort_indices(keys: torch.Tensor, key_bound: int, workspace: Optional[torch.Tensor] = None) -> SortedIndices:
+    """Stable radix sort of (keys[i], i) on the device (mtam_sort_indices)."""
+    lib = _lib.load()
+    n = keys.numel()
+    need = max(int(lib.mtam_sort_workspace(n, key_bound)), 16)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=keys.device)
+    ks, pm = C.c_void_p(), C.c_void_p()
+    check(lib.mtam_sort_indices(keys.data_ptr(), n, key_bound, workspace.data_ptr(), workspace.numel(), C.byref(ks),
+                                C.byref(pm), torch.cuda.current_stream(keys.device).cuda_stream), "mtam_sort_indices")
+
+    def view(ptr):
+        if n == 0:
+            return torch.empty(0, dtype=torch.int32, device=keys.device)
+        off = ptr.value - workspace.data_ptr()
+        return workspace[off: off + 4 * n].view(torch.int32)
+    return SortedIndices(view(ks), view(pm), workspace)
+
+
+def scatter_add_sorted(dst: torch.Tensor, sorted_idx: SortedIndices, rows: torch.Tensor,
+                       workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dst[keys_sorted[j]] += rows[perm[j]] -- the segmented-reduction half of scatter_add."""
+    lib = _lib.load()
+    n = sorted_idx.keys_sorted.numel()
+    R, D = dst.shape
+    need = max(int(lib.mtam_scatter_add_sorted_workspace(n, D)), 16)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dst.device)
+    check(lib.mtam_scatter_add_sorted(dst.data_ptr(), D, sorted_idx.keys_sorted.data_ptr(), sorted_idx.perm.data_ptr(),
+                                      rows.data_ptr(), rows.stride(0), n, workspace.data_ptr(), workspace.numel(),
+                                      torch.cuda.current_stream(dst.device).cuda_stream), "mtam_scatter_add_sorted")
+    return dst
+
+
+def score_topk(pred: torch.Tensor, table: torch.Tensor, k: int, row_begin: int = 0, row_end: Optional[int] = None,
+               index_base: int = 0, workspace: Optional[torch.Tensor] = None):
+    """Top-k of pred x table[row_begin:row_end]^T (mtam_score_topk): sorted descending, ties -> lower index.
+    `table` holds rows [index_base, index_base + table.shape[0]) of the catalogue; indices returned are global."""
+    lib = _lib.load()
+    B, D = pred.shape
+    row_end = index_base + table.shape[0] if row_end is None else row_end
+    rows = row_end - row_begin
+    need = max(int(lib.mtam_score_topk_workspace(B, rows, k)), 16)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=pred.device)
+    idx = torch.empty((B, k), dtype=torch.int32, device=pred.device)
+    sc = torch.empty((B, k), dtype=torch.float32, device=pred.device)
+    # the library indexes item_table by global row number: pass the base shifted back by index_base rows
+    base = table.data_ptr() - index_base * D * 4
+    check(lib.mtam_score_topk(pred.data_ptr(), B, D, base, row_begin, row_end, k, idx.data_ptr(), sc.data_ptr(),
+                              workspace.data_ptr(), workspace.numel(),
+                              torch.cuda.current_stream(pred.device).cuda_stream), "mtam_score_topk")
+    return idx, sc
+
+
+def merge_topk(idx_lists: torch.Tensor, score_lists: torch.Tensor):
+    """Merges [n_lists, B, k] per-shard top-k lists (shard order = index order) into [B, k] (mtam_merge_topk)."""
+    lib = _lib.load()
+    n_lists, B, k = idx_lists.shape
+    out_i = torch.empty((B, k), dtype=torch.int32, device=idx_lists.device)
+    out_s = torch.empty((B, k), dtype=torch.float32, device=idx_lists.device)
+    check(lib.mtam_merge_topk(idx_lists.data_ptr(), score_lists.data_ptr(), n_lists, B, k, out_i.data_ptr(),
+                              out_s.data_ptr(), torch.cuda.current_stream(idx_lists.device).cuda_stream), "mtam_merge_topk")
+    return out_i, out_s

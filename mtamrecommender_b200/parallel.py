@@ -25,7 +25,8 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check
-from .engine import DeviceBatch, Engine, scatter_add, scatter_add_workspace
+from .engine import (DeviceBatch, Engine, gather, merge_topk, scatter_add, scatter_add_workspace, score_topk,
+                     sort_indices)
 
 
 class DataParallel:
@@ -99,3 +100,80 @@ class DataParallel:
     def train_step(self, feed: Dict[str, np.ndarray], lr: float) -> float:
         self.train_step_device(self.eng.upload(feed), lr)
         return float(self.eng.read_scalars()[_lib.S_LOSS])
+
+
+def shard_rows(total_rows: int, world: int) -> int:
+    """Rows per shard of a row-sharded table: rank r owns [r*rows, min((r+1)*rows, total_rows))."""
+    return (total_rows + world - 1) // world
+
+
+class ShardedCatalogue:
+    """Item table row-sharded over the ranks (the large-catalogue regime, SURVEY 8e / BASELINE configs[4]).
+
+    The reference keeps the whole table on one device (Embedding/base_embedding.py:46-60) and scores
+    `pred x table^T` against all of it (Model/base_model.py:194-202).  Here rank r holds rows
+    [r*S, (r+1)*S), S = ceil(V / world):
+      lookup(ids)  : all-to-all of the ids to their owners, local gather (mtam_gather), all-to-all of the rows back;
+      topk(pred,k) : all-gather of pred, every rank scores its shard and keeps a local top-k with GLOBAL row numbers
+                     (mtam_score_topk), all-gather of the [B,k] lists, k-way merge (mtam_merge_topk; ties -> lower
+                     global index is preserved because shard order = index order).
+    Results equal the unsharded ones bit for bit (rows are copies; scores are the same fp32 dot products).
+    """
+
+    def __init__(self, shard: torch.Tensor, total_rows: int, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.total_rows = int(total_rows)
+        self.rows_per_shard = shard_rows(self.total_rows, self.world)
+        self.row_begin = self.rank * self.rows_per_shard
+        self.row_end = min(self.total_rows, self.row_begin + self.rows_per_shard)
+        if shard.shape[0] != max(self.row_end - self.row_begin, 0):
+            raise ValueError(f"rank {self.rank}: shard has {shard.shape[0]} rows, expected {self.row_end - self.row_begin}")
+        self.shard = shard.contiguous()
+        self.D = shard.shape[1]
+
+    @staticmethod
+    def from_full(table: torch.Tensor, group=None) -> "ShardedCatalogue":
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        S = shard_rows(table.shape[0], world)
+        return ShardedCatalogue(table[rank * S: min(table.shape[0], (rank + 1) * S)].clone(), table.shape[0], group)
+
+    def lookup(self, ids: torch.Tensor) -> torch.Tensor:
+        """rows[i] = table[ids[i]] for ids anywhere in the catalogue (int32, any shape) -> [..., D]."""
+        flat = ids.reshape(-1).contiguous()
+        n, W, dev = flat.numel(), self.world, flat.device
+        owner = torch.div(flat, self.rows_per_shard, rounding_mode="floor").to(torch.int32)
+        srt = sort_indices(owner, W)                              # stable: ids of one owner stay in request order
+        send_ids = flat[srt.perm.long()]
+        send_counts = torch.bincount(srt.keys_sorted.long(), minlength=W)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()        # host sync: split sizes of the exchange
+        recv_ids = torch.empty(sum(rc), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(recv_ids, send_ids, rc, sc, group=self.group)
+        local = gather(self.shard, recv_ids - self.row_begin) if recv_ids.numel() else \
+            torch.empty((0, self.D), dtype=torch.float32, device=dev)
+        back = torch.empty((n, self.D), dtype=torch.float32, device=dev)
+        dist.all_to_all_single(back, local, sc, rc, group=self.group)
+        out = torch.empty_like(back)
+        out[srt.perm.long()] = back
+        return out.reshape(*ids.shape, self.D)
+
+    def topk(self, pred: torch.Tensor, k: int = 50):
+        """Full-catalogue top-k for this rank's pred rows [B_local, D] -> (idx [B_local,k] int32 global, score)."""
+        W, Bl = self.world, pred.shape[0]
+        allp = torch.empty((W * Bl, self.D), dtype=torch.float32, device=pred.device)
+        dist.all_gather_into_tensor(allp, pred.contiguous(), group=self.group)
+        kk = min(k, max(self.row_end - self.row_begin, 1))
+        if kk != k:
+            raise ValueError("shard smaller than k")
+        idx, sc = score_topk(allp, self.shard, k, self.row_begin, self.row_end, index_base=self.row_begin)
+        g_idx = torch.empty((W, W * Bl, k), dtype=torch.int32, device=pred.device)
+        g_sc = torch.empty((W, W * Bl, k), dtype=torch.float32, device=pred.device)
+        dist.all_gather_into_tensor(g_idx, idx, group=self.group)
+        dist.all_gather_into_tensor(g_sc, sc, group=self.group)
+        mine = slice(self.rank * Bl, (self.rank + 1) * Bl)
+        return merge_topk(g_idx[:, mine].contiguous(), g_sc[:, mine].contiguous())
