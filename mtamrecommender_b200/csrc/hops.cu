@@ -359,6 +359,418 @@ __global__ void __launch_bounds__(HOP_WARPS * 32) hop_bwd_kernel(HopArgs a, HopG
   stv<VPL>(g.dq0 + (int64_t)b * D + d0, dq);
 }
 
+// =============================================================================================
+// CTA-per-sequence variant (the default): the warp-per-sequence kernels above expose every global
+// load's latency to a single warp (ncu: 52 % long-scoreboard stalls, 7 warps per SM at B = 1024).
+// Here one 128-thread CTA owns a sequence: X (once) and the hop's K, V rows are staged in shared
+// memory with cp.async while the query projections run, the score / dP dot products are split into
+// 16-float chunks over (chunk, key) work items (lanes across keys, conflict-free 128-bit reads), the
+// gate transcendentals are evaluated once per key instead of once per lane, and dX is accumulated in
+// shared memory across the hops.  Needs head width % 16 == 0 and the tiles to fit in shared memory;
+// otherwise the launchers fall back to the kernels above.  Same saved activations, same outputs.
+// =============================================================================================
+constexpr int HC_T = 128;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// rows [0,len) of D floats, global row stride ldg -> shared rows of stride RS (both 16-byte aligned)
+template <int D>
+__device__ __forceinline__ void load_rows_async(float* s, int RS, const float* g, int64_t ldg, int len) {
+  for (int e = threadIdx.x; e < len * (D / 4); e += HC_T) {
+    const int j = e / (D / 4), c = e % (D / 4);
+    cp_async16(s + j * RS + c * 4, g + j * ldg + c * 4);
+  }
+}
+__device__ __forceinline__ float dot16(const float* __restrict__ row, const float4 (&v)[4]) {
+  const float4* r = reinterpret_cast<const float4*>(row);
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; u += 2) {
+    const float4 a = r[u], b = r[u + 1];
+    s0 = fmaf(a.x, v[u].x, s0); s0 = fmaf(a.y, v[u].y, s0); s0 = fmaf(a.z, v[u].z, s0); s0 = fmaf(a.w, v[u].w, s0);
+    s1 = fmaf(b.x, v[u + 1].x, s1); s1 = fmaf(b.y, v[u + 1].y, s1); s1 = fmaf(b.z, v[u + 1].z, s1); s1 = fmaf(b.w, v[u + 1].w, s1);
+  }
+  return s0 + s1;
+}
+
+struct HopCtaSmem {
+  int RS, X, K, V, dX, vec, mv, part, part2, sc, dps, dA, dM, dsum, total;   // offsets in floats
+};
+__host__ __device__ inline HopCtaSmem hop_cta_layout(int D, int H, int L, bool bwd) {
+  HopCtaSmem o;
+  const int C = D / 16, Lp = (L + 3) & ~3;
+  o.RS = D + 4;
+  int p = 0;
+  o.X = p; p += L * o.RS;
+  o.K = p; p += L * o.RS;
+  o.V = p; p += L * o.RS;
+  o.dX = p; p += bwd ? L * D : 0;
+  o.vec = p; p += 6 * D;          // fwd: q, Q, qt;  bwd: dq, dy, Q, qt, dQpre, dqt
+  o.mv = p; p += 2 * HC_T;
+  o.part = p; p += C * Lp;
+  o.part2 = p; p += C * Lp;
+  o.sc = p; p += H * Lp;          // fwd: scores / probabilities;  bwd: probabilities
+  o.dps = p; p += bwd ? H * Lp : 0;
+  o.dA = p; p += bwd ? H * Lp : 0;
+  o.dM = p; p += bwd ? Lp : 0;
+  o.dsum = p; p += 32;
+  o.total = p;
+  return o;
+}
+
+template <int D>
+__global__ void __launch_bounds__(HC_T) hop_fwd_cta_kernel(HopArgs a) {
+  constexpr int C = D / 16, PARTS = HC_T / D, KP = D / PARTS, VPL = D / 32;
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, t = threadIdx.x, w = t >> 5, lane = t & 31;
+  const int L = a.L, H = a.H, N = a.N, dh = D / H, Lp = (L + 3) & ~3;
+  const HopCtaSmem o = hop_cta_layout(D, H, L, false);
+  const int RS = o.RS;
+  float *Xs = sm + o.X, *Ks = sm + o.K, *Vs = sm + o.V, *qv = sm + o.vec, *Qv = qv + D, *qtv = Qv + D, *mv = sm + o.mv,
+        *pa = sm + o.part, *pz = sm + o.part2, *sc = sm + o.sc;
+  const float sqrt_dh = sqrtf((float)dh);
+  const int len = min(max(a.seq_len[b], 0), L);
+  const float tq = a.target_time[b];
+  const int ldkv = 2 * N * D;
+  const int64_t tok0 = (int64_t)b * L;
+  load_rows_async<D>(Xs, RS, a.X + tok0 * D, D, len);
+  if (t < D) qv[t] = a.Qin[(int64_t)b * D + t];
+  for (int i = 0; i < N; ++i) {
+    load_rows_async<D>(Ks, RS, a.KV + tok0 * ldkv + (int64_t)i * 2 * D, ldkv, len);
+    load_rows_async<D>(Vs, RS, a.KV + tok0 * ldkv + (int64_t)i * 2 * D + D, ldkv, len);
+    cp_async_commit();
+    __syncthreads();
+    const int64_t ib = (int64_t)i * a.B + b;
+    {  // Q = relu(q Wq + bq), qt = q Wt   (:249, :320): thread = (output d, k range)
+      const int d = t % D, part = t / D;
+      const float* Wq = a.Wq + (int64_t)i * D * D + (int64_t)part * KP * D + d;
+      const float* Wt = a.Wt + (int64_t)i * D * D + (int64_t)part * KP * D + d;
+      float aq = 0.f, at = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < KP; ++k) {
+        const float qk = qv[part * KP + k];
+        aq = fmaf(qk, __ldg(Wq + k * D), aq);
+        at = fmaf(qk, __ldg(Wt + k * D), at);
+      }
+      mv[t] = aq;
+      mv[HC_T + t] = at;
+    }
+    __syncthreads();
+    if (t < D) {
+      float s1 = __ldg(a.bq + (int64_t)i * D + t), s2 = 0.f;
+#pragma unroll
+      for (int p = 0; p < PARTS; ++p) { s1 += mv[p * D + t]; s2 += mv[HC_T + p * D + t]; }
+      s1 = fmaxf(s1, 0.f);
+      Qv[t] = s1; qtv[t] = s2;
+      a.Qr[ib * D + t] = s1;
+      a.Qt[ib * D + t] = s2;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- partial dot products over 16-float chunks: work item = (chunk c, block of 32 keys) ----
+    const int JB = (len + 31) >> 5;
+    for (int id = w; id < C * JB; id += HC_T / 32) {
+      const int c = id % C, j = (id / C) * 32 + lane;
+      float4 qc[4], tc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        qc[u] = *reinterpret_cast<const float4*>(Qv + c * 16 + u * 4);
+        tc[u] = *reinterpret_cast<const float4*>(qtv + c * 16 + u * 4);
+      }
+      if (j < len) {
+        pa[c * Lp + j] = dot16(Ks + j * RS + c * 16, qc);
+        pz[c * Lp + j] = dot16(Xs + j * RS + c * 16, tc);
+      }
+    }
+    __syncthreads();
+    // ---- gate and scores: thread = key ----
+    const float* w1 = a.gate + ((int64_t)i * 5 + 0) * L;
+    const float* b1 = a.gate + ((int64_t)i * 5 + 1) * L;
+    const float* o1 = a.gate + ((int64_t)i * 5 + 2) * L;
+    const float* o2 = a.gate + ((int64_t)i * 5 + 3) * L;
+    const float* ob = a.gate + ((int64_t)i * 5 + 4) * L;
+    for (int j = t; j < len; j += HC_T) {
+      float z = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) z += pz[c * Lp + j];
+      const float Z = tanhf(z);                                                 // :323
+      const float dlt = logf(fabsf(tq - __ldg(a.time_list + tok0 + j)) + 1.f);  // :339
+      const float Dk = tanhf(fmaf(dlt, __ldg(w1 + j), __ldg(b1 + j)));          // :343
+      const float G = __ldg(o1 + j) * Dk + __ldg(o2 + j) * Z + __ldg(ob + j);   // :350
+      const float gate = sigmoidf_(G);
+      a.ZZ[ib * L + j] = Z;
+      a.DK[ib * L + j] = Dk;
+      a.GT[ib * L + j] = gate;
+      const int cph = dh / 16;
+      for (int h = 0; h < H; ++h) {
+        float av = 0.f;
+        for (int c = h * cph; c < (h + 1) * cph; ++c) av += pa[c * Lp + j];
+        a.AA[(ib * H + h) * L + j] = av;
+        sc[h * Lp + j] = (av * gate) / sqrt_dh;                                  // :381-384
+      }
+    }
+    __syncthreads();
+    // ---- softmax over the len valid keys (masked keys get exactly 0: exp(-2^32 - m) == 0) ----
+    for (int h = w; h < H; h += HC_T / 32) {
+      float m = -INFINITY;
+      for (int j = lane; j < len; j += 32) m = fmaxf(m, sc[h * Lp + j]);
+      m = warp_max(m);
+      float s = 0.f;
+      for (int j = lane; j < len; j += 32) {
+        const float e = expf(sc[h * Lp + j] - m);
+        sc[h * Lp + j] = e;
+        s += e;
+      }
+      s = warp_sum(s);
+      for (int j = lane; j < L; j += 32) {
+        const float p = (j < len) ? sc[h * Lp + j] / s : 0.f;
+        if (j < len) sc[h * Lp + j] = p;
+        a.PA[(ib * H + h) * L + j] = p;
+      }
+    }
+    __syncthreads();
+    {  // ---- O = P V: thread = (d, key subset) ----
+      const int d = t % D, part = t / D, h = d / dh;
+      float acc = 0.f;
+      for (int j = part; j < len; j += PARTS) acc = fmaf(sc[h * Lp + j], Vs[j * RS + d], acc);
+      mv[t] = acc;
+    }
+    __syncthreads();
+    if (w == 0) {  // ---- residual + normalize (eps 1e-8)  :447-454, :7-34 ----
+      const int d0 = lane * VPL;
+      float y[VPL], s1 = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        float ov = 0.f;
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p) ov += mv[p * D + d0 + v];
+        y[v] = ov + qv[d0 + v];
+        s1 += y[v];
+      }
+      const float mean = warp_sum(s1) / D;
+      float s2 = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) { y[v] -= mean; s2 = fmaf(y[v], y[v], s2); }
+      const float var = warp_sum(s2) / D;
+      const float rstd = 1.f / sqrtf(var + 1e-8f);
+      float gm[VPL], bt[VPL], xh[VPL], qn[VPL];
+      ldv<VPL>(gm, a.ln_gamma + (int64_t)i * D + d0);
+      ldv<VPL>(bt, a.ln_beta + (int64_t)i * D + d0);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) { xh[v] = y[v] * rstd; qn[v] = fmaf(gm[v], xh[v], bt[v]); qv[d0 + v] = qn[v]; }
+      stv<VPL>(a.XH + ((int64_t)b * N + i) * D + d0, xh);
+      if (lane == 0) a.RSTD[(int64_t)b * N + i] = rstd;
+      stv<VPL>(a.Qin + ((int64_t)(i + 1) * a.B + b) * D + d0, qn);
+    }
+    __syncthreads();
+  }
+  if (w == 0) {  // ---- final tf.contrib layer_norm (eps 1e-12) ----
+    const int d0 = lane * VPL;
+    float s1 = 0.f, q[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) { q[v] = qv[d0 + v]; s1 += q[v]; }
+    const float mean = warp_sum(s1) / D;
+    float s2 = 0.f, y[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) { y[v] = q[v] - mean; s2 = fmaf(y[v], y[v], s2); }
+    const float var = warp_sum(s2) / D;
+    const float rstd = rsqrtf(var + 1e-12f);
+    float gm[VPL], bt[VPL], xh[VPL], ov[VPL];
+    ldv<VPL>(gm, a.lnf_gamma + d0);
+    ldv<VPL>(bt, a.lnf_beta + d0);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) { xh[v] = y[v] * rstd; ov[v] = fmaf(gm[v], xh[v], bt[v]); }
+    stv<VPL>(a.XHF + (int64_t)b * D + d0, xh);
+    if (lane == 0) a.RSTDF[b] = rstd;
+    stv<VPL>(a.pred + (int64_t)b * D + d0, ov);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(HC_T) hop_bwd_cta_kernel(HopArgs a, HopGradArgs g) {
+  constexpr int C = D / 16, PARTS = HC_T / D, KP = D / PARTS, VPL = D / 32;
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, t = threadIdx.x, w = t >> 5, lane = t & 31;
+  const int L = a.L, H = a.H, N = a.N, dh = D / H, Lp = (L + 3) & ~3;
+  const HopCtaSmem o = hop_cta_layout(D, H, L, true);
+  const int RS = o.RS;
+  float *Xs = sm + o.X, *Ks = sm + o.K, *Vs = sm + o.V, *dXs = sm + o.dX, *dqv = sm + o.vec, *dyv = dqv + D, *Qv = dyv + D,
+        *qtv = Qv + D, *dQpv = qtv + D, *dqtv = dQpv + D, *mv = sm + o.mv, *part = sm + o.part, *ps = sm + o.sc,
+        *dps = sm + o.dps, *dA = sm + o.dA, *dMv = sm + o.dM, *dsum = sm + o.dsum;
+  const float sqrt_dh = sqrtf((float)dh);
+  const int len = min(max(a.seq_len[b], 0), L);
+  const float tq = a.target_time[b];
+  const int ldkv = 2 * N * D;
+  const int64_t tok0 = (int64_t)b * L;
+  load_rows_async<D>(Xs, RS, a.X + tok0 * D, D, len);
+  for (int e = t; e < L * D; e += HC_T) dXs[e] = 0.f;
+  if (w == 0) {   // backward of the final layer norm
+    const int d0 = lane * VPL;
+    float dp[VPL], gm[VPL], xh[VPL], dq[VPL];
+    ldv<VPL>(dp, g.dpred + (int64_t)b * D + d0);
+    ldv<VPL>(gm, a.lnf_gamma + d0);
+    ldv<VPL>(xh, a.XHF + (int64_t)b * D + d0);
+    ln_bwd_row<VPL>(dp, gm, xh, a.RSTDF[b], D, dq);
+    stv<VPL>(dqv + d0, dq);
+  }
+  for (int i = N - 1; i >= 0; --i) {
+    const int64_t ib = (int64_t)i * a.B + b;
+    __syncthreads();     // dqv complete; K/V tiles of the previous hop no longer read
+    load_rows_async<D>(Ks, RS, a.KV + tok0 * ldkv + (int64_t)i * 2 * D, ldkv, len);
+    load_rows_async<D>(Vs, RS, a.KV + tok0 * ldkv + (int64_t)i * 2 * D + D, ldkv, len);
+    cp_async_commit();
+    if (w == 0) {
+      const int d0 = lane * VPL;
+      float dq[VPL], gm[VPL], xh[VPL], dy[VPL];
+      ldv<VPL>(dq, dqv + d0);
+      stv<VPL>(g.DOUT + ((int64_t)b * N + i) * D + d0, dq);   // for d gamma_i / d beta_i column sums
+      ldv<VPL>(gm, a.ln_gamma + (int64_t)i * D + d0);
+      ldv<VPL>(xh, a.XH + ((int64_t)b * N + i) * D + d0);
+      ln_bwd_row<VPL>(dq, gm, xh, a.RSTD[(int64_t)b * N + i], D, dy);
+      stv<VPL>(dyv + d0, dy);
+    } else if (w == 1) {
+      for (int d = lane; d < D; d += 32) { Qv[d] = a.Qr[ib * D + d]; qtv[d] = a.Qt[ib * D + d]; }
+    } else {
+      for (int j = t - 64; j < H * L; j += HC_T - 64) ps[(j / L) * Lp + (j % L)] = a.PA[ib * H * L + j];
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- pass A: dP[h][j] = dO_h . V_hj  (partial dots over 16-float chunks) ----
+    const int JB = (len + 31) >> 5;
+    for (int id = w; id < C * JB; id += HC_T / 32) {
+      const int c = id % C, j = (id / C) * 32 + lane;
+      float4 yc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) yc[u] = *reinterpret_cast<const float4*>(dyv + c * 16 + u * 4);
+      if (j < len) part[c * Lp + j] = dot16(Vs + j * RS + c * 16, yc);
+    }
+    __syncthreads();
+    const int cph = dh / 16;
+    for (int j = t; j < len; j += HC_T)
+      for (int h = 0; h < H; ++h) {
+        float s = 0.f;
+        for (int c = h * cph; c < (h + 1) * cph; ++c) s += part[c * Lp + j];
+        dps[h * Lp + j] = s;
+      }
+    __syncthreads();
+    for (int h = w; h < H; h += HC_T / 32) {
+      float s = 0.f;
+      for (int j = lane; j < len; j += 32) s = fmaf(ps[h * Lp + j], dps[h * Lp + j], s);
+      s = warp_sum(s);
+      if (lane == 0) dsum[h] = s;
+    }
+    __syncthreads();
+    // ---- per key: softmax / gate backward, gate-parameter gradients ----
+    const float* o1 = a.gate + ((int64_t)i * 5 + 2) * L;
+    const float* o2 = a.gate + ((int64_t)i * 5 + 3) * L;
+    float* gb = g.GB + (int64_t)b * (5 * N * L) + (int64_t)i * 5 * L;
+    for (int j = t; j < len; j += HC_T) {
+      const float gate = __ldg(a.GT + ib * L + j), Z = __ldg(a.ZZ + ib * L + j), Dk = __ldg(a.DK + ib * L + j);
+      float dgate = 0.f;
+      for (int h = 0; h < H; ++h) {
+        const float dS = ps[h * Lp + j] * (dps[h * Lp + j] - dsum[h]);
+        dgate = fmaf(dS, __ldg(a.AA + (ib * H + h) * L + j), dgate);
+        dA[h * Lp + j] = dS * gate / sqrt_dh;
+      }
+      dgate /= sqrt_dh;
+      const float dG = dgate * gate * (1.f - gate);
+      const float dDk = dG * __ldg(o1 + j);
+      const float dpre = dDk * (1.f - Dk * Dk);
+      const float dlt = logf(fabsf(tq - __ldg(a.time_list + tok0 + j)) + 1.f);
+      gb[0 * L + j] = dpre * dlt;  // _time_input_w1
+      gb[1 * L + j] = dpre;        // _time_input_b1
+      gb[2 * L + j] = dG * Dk;     // time_output_w1
+      gb[3 * L + j] = dG * Z;      // time_output_w2
+      gb[4 * L + j] = dG;          // time_output_b
+      dMv[j] = dG * __ldg(o2 + j) * (1.f - Z * Z);
+    }
+    __syncthreads();
+    {  // dQ[d] = sum_j dA[h][j] K[j][d],  dqt[d] = sum_j dM[j] X[j][d]: thread = (d, key subset)
+      const int d = t % D, pt = t / D, h = d / dh;
+      float aq = 0.f, at = 0.f;
+      for (int j = pt; j < len; j += PARTS) {
+        aq = fmaf(dA[h * Lp + j], Ks[j * RS + d], aq);
+        at = fmaf(dMv[j], Xs[j * RS + d], at);
+      }
+      mv[t] = aq;
+      mv[HC_T + t] = at;
+    }
+    // dK, dV (relu-masked, written once; masked keys get zeros), dX accumulated in shared memory
+    for (int e = t; e < L * (D / 4); e += HC_T) {
+      const int j = e / (D / 4), d = (e % (D / 4)) * 4, h = d / dh;
+      float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
+      if (j < len) {
+        const float4 kk = *reinterpret_cast<const float4*>(Ks + j * RS + d);
+        const float4 vv = *reinterpret_cast<const float4*>(Vs + j * RS + d);
+        const float4 q4 = *reinterpret_cast<const float4*>(Qv + d);
+        const float4 y4 = *reinterpret_cast<const float4*>(dyv + d);
+        const float4 t4 = *reinterpret_cast<const float4*>(qtv + d);
+        const float da = dA[h * Lp + j], p = ps[h * Lp + j], dm = dMv[j];
+        dk.x = kk.x > 0.f ? da * q4.x : 0.f; dk.y = kk.y > 0.f ? da * q4.y : 0.f;
+        dk.z = kk.z > 0.f ? da * q4.z : 0.f; dk.w = kk.w > 0.f ? da * q4.w : 0.f;
+        dv.x = vv.x > 0.f ? p * y4.x : 0.f; dv.y = vv.y > 0.f ? p * y4.y : 0.f;
+        dv.z = vv.z > 0.f ? p * y4.z : 0.f; dv.w = vv.w > 0.f ? p * y4.w : 0.f;
+        float4* dx = reinterpret_cast<float4*>(dXs + j * D + d);
+        float4 x = *dx;
+        x.x = fmaf(dm, t4.x, x.x); x.y = fmaf(dm, t4.y, x.y); x.z = fmaf(dm, t4.z, x.z); x.w = fmaf(dm, t4.w, x.w);
+        *dx = x;
+      }
+      float* dst = g.dKV + (tok0 + j) * ldkv + (int64_t)i * 2 * D + d;
+      __stcs(reinterpret_cast<float4*>(dst), dk);
+      __stcs(reinterpret_cast<float4*>(dst + D), dv);
+    }
+    __syncthreads();
+    if (t < D) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int p = 0; p < PARTS; ++p) { s1 += mv[p * D + t]; s2 += mv[HC_T + p * D + t]; }
+      s1 = Qv[t] > 0.f ? s1 : 0.f;
+      dQpv[t] = s1; dqtv[t] = s2;
+      g.DQP[((int64_t)b * N + i) * D + t] = s1;
+      g.DQT[((int64_t)b * N + i) * D + t] = s2;
+    }
+    __syncthreads();
+    {  // dq = dy (residual) + dQpre Wq^T + dqt Wt^T   (transposed copies prepared by the host side)
+      const int d = t % D, pt = t / D;
+      const float* WqT = g.WqT + (int64_t)i * D * D + (int64_t)pt * KP * D + d;
+      const float* WtT = g.WtT + (int64_t)i * D * D + (int64_t)pt * KP * D + d;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < KP; ++k)
+        acc = fmaf(dQpv[pt * KP + k], __ldg(WqT + k * D), fmaf(dqtv[pt * KP + k], __ldg(WtT + k * D), acc));
+      mv[t] = acc;
+    }
+    __syncthreads();
+    if (t < D) {
+      float s = dyv[t];
+#pragma unroll
+      for (int p = 0; p < PARTS; ++p) s += mv[p * D + t];
+      dqv[t] = s;
+    }
+  }
+  __syncthreads();
+  if (t < D) g.dq0[(int64_t)b * D + t] = dqv[t];
+  for (int e = t; e < len * (D / 4); e += HC_T) {
+    const int j = e / (D / 4), d = (e % (D / 4)) * 4;
+    *reinterpret_cast<float4*>(g.dX + (tok0 + j) * D + d) = *reinterpret_cast<const float4*>(dXs + j * D + d);
+  }
+}
+
+static bool hop_cta_ok(int D, int H, int L, bool bwd, size_t* smem) {
+  if (D % H != 0 || (D / H) % 16 != 0) return false;
+  *smem = (size_t)hop_cta_layout(D, H, L, bwd).total * sizeof(float);
+  return *smem <= 220 * 1024;
+}
+// hop_backward writes every dKV element itself when it takes the CTA-per-sequence path
+bool hop_backward_writes_all_dkv(int D, int H, int L) {
+  size_t smem;
+  return hop_cta_ok(D, H, L, true, &smem);
+}
+
 size_t hop_smem_bytes(int D, int H, int L, bool bwd) {
   size_t per_warp = bwd ? (size_t)(2 * D + 2 * H * L + 32) : (size_t)(D + 2 * H * L);
   return per_warp * HOP_WARPS * sizeof(float);
@@ -367,6 +779,23 @@ size_t hop_smem_bytes(int D, int H, int L, bool bwd) {
 int hop_forward(const HopArgs& a, cudaStream_t st) {
   if (a.H < 1 || a.H > 32 || (32 % a.H) != 0 || (a.D % a.H) != 0)
     return set_error(-1, "attention: num_heads=%d must divide 32 and num_units", a.H);
+  size_t csmem;
+  if (hop_cta_ok(a.D, a.H, a.L, false, &csmem)) {
+#define HOP_FWD_CTA(DD)                                                                                               \
+  do {                                                                                                                \
+    MTAM_CUDA_CHECK(cudaFuncSetAttribute(hop_fwd_cta_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)); \
+    hop_fwd_cta_kernel<DD><<<a.B, HC_T, csmem, st>>>(a);                                                              \
+  } while (0)
+    switch (a.D) {
+      case 32: HOP_FWD_CTA(32); break;
+      case 64: HOP_FWD_CTA(64); break;
+      case 128: HOP_FWD_CTA(128); break;
+      default: return set_error(-1, "attention: num_units=%d not supported (32, 64, 128)", a.D);
+    }
+#undef HOP_FWD_CTA
+    MTAM_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = hop_smem_bytes(a.D, a.H, a.L, false);
   int blocks = cdiv(a.B, HOP_WARPS);
 #define HOP_FWD(V)                                                                                            \
@@ -386,6 +815,23 @@ int hop_forward(const HopArgs& a, cudaStream_t st) {
 }
 
 int hop_backward(const HopArgs& a, const HopGradArgs& g, cudaStream_t st) {
+  size_t csmem;
+  if (hop_cta_ok(a.D, a.H, a.L, true, &csmem)) {
+#define HOP_BWD_CTA(DD)                                                                                               \
+  do {                                                                                                                \
+    MTAM_CUDA_CHECK(cudaFuncSetAttribute(hop_bwd_cta_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)); \
+    hop_bwd_cta_kernel<DD><<<a.B, HC_T, csmem, st>>>(a, g);                                                           \
+  } while (0)
+    switch (a.D) {
+      case 32: HOP_BWD_CTA(32); break;
+      case 64: HOP_BWD_CTA(64); break;
+      case 128: HOP_BWD_CTA(128); break;
+      default: return set_error(-1, "attention: num_units=%d not supported (32, 64, 128)", a.D);
+    }
+#undef HOP_BWD_CTA
+    MTAM_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = hop_smem_bytes(a.D, a.H, a.L, true);
   int blocks = cdiv(a.B, HOP_WARPS);
 #define HOP_BWD(V)                                                                                            \
