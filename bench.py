@@ -264,22 +264,33 @@ def run_cuda(args, w):
                     phases[k] = phases.get(k, 0.0) + v / reps
         T = w["B"] * w["L"]
         D, V, B, N = w["D"], w["items"] + 3, w["B"], w["N"]
-        flops = {"ce_bwd": 6.0 * B * D * V, "ce_fwd": 2.0 * B * D * V, "kv_gemm": 2.0 * T * D * 2 * N * D}
-        roof = None
-        if phases:
-            dom = max(phases, key=phases.get)
-            if dom in flops:
-                ach = flops[dom] / (phases[dom] * 1e-3) / 1e12
-                roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                        "frac": ach / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
-                        "ms": phases[dom], "share_of_step": phases[dom] / sum(phases.values())}
+        traffic = ncu_traffic()
+        tot = sum(phases.values()) if phases else 0.0
+        # algorithmic work per launch of each phase; tensor phases: useful fp32-equivalent FLOPs
+        # (the 3xTF32 split issues 3x as many tf32 MMA FLOPs), against the measured bf16 sustained peak
+        lf = float(np.mean(feeds[0]["seq_length"])) / w["L"]     # share of real (unmasked) keys
+        work = {"adam": ("hbm", 7.0 * 4 * eng.n_floats),
+                "ce_bwd": ("tensor", 6.0 * B * D * V),            # recompute + dPred + dTable (SURVEY 8d, K8 bwd)
+                "ce_fwd": ("tensor", 2.0 * B * D * V),
+                "kv_gemm": ("tensor", 2.0 * T * D * 2 * N * D),
+                "hop_fwd": ("hbm", 4.0 * T * D * lf * (2 * N + 1)),   # K,V of every hop + X once, real keys only
+                "hop_bwd": ("hbm", 4.0 * T * D * (lf * (2 * N + 1) + 2 * N + lf))}   # + dK,dV of every key, dX
+
+        def roof_of(name):
+            kind, amount = work[name]
+            ms = phases[name]
+            if kind == "hbm":
+                ach, peak, unit = amount / (ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
             else:
-                byts = {"adam": 7.0 * 4 * eng.n_floats, "scatter": (3 * T + B) * (4 + 4 * D) * 2.0}.get(dom)
-                if byts:
-                    ach = byts / (phases[dom] * 1e-3) / 1e9
-                    roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                            "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"], "ms": phases[dom],
-                            "share_of_step": phases[dom] / sum(phases.values())}
+                ach, peak, unit = amount / (ms * 1e-3) / 1e12, pk["tf_sust"], "TFLOP/s"
+            return {"kernel": name, "bound": kind, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                    "traffic": traffic.get(name), "peak_source": pk["src"] + (" bf16 sustained" if kind == "tensor" else " copy"),
+                    "ms": ms, "share_of_step": ms / tot}
+        roof, roofs = None, []
+        if phases:
+            ranked = sorted((k for k in phases if k in work), key=lambda k: -phases[k])
+            roofs = [roof_of(k) for k in ranked[:4]]
+            roof = roofs[0] if roofs else None
         # ---- the two graded bandwidth kernels at cfg-4 shapes (n = 8192*200 rows, D = 64) ----
         bw = bandwidth_kernels(eng, dev, pk)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -294,7 +305,7 @@ def run_cuda(args, w):
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
                        "ms_per_step": ms_e2e / args.steps},
                "gpu_launches": int(launches), "clocks": clk, "phases_ms": phases, "roofline": roof,
-               "bandwidth_kernels": bw}
+               "rooflines_top_phases": roofs, "bandwidth_kernels": bw}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(w)
     if world > 1:
@@ -305,18 +316,21 @@ def run_cuda(args, w):
 
 
 def bandwidth_kernels(eng, dev, pk, n=8192 * 200, D=64, rows=10_000_003):
-    """Gather and scatter-add timed alone at cfg-4 shapes, inputs larger than L2."""
+    """Gather and scatter-add timed alone at cfg-4 shapes: 1.6 M rows of 256 B against a 10 M-row
+    (2.56 GB) table, inputs far larger than L2.  Two id distributions: `uniform` (every row distinct with high
+    probability: no cache reuse, the roofline case) and `zipf_pad` (Zipf(1.05) ids with 45 % pad id 0, the shape of a
+    ragged batch: hot rows are served from L2, so the algorithmic-byte rate can exceed the HBM peak).
+    scatter_add = whole op (index sort + segmented reduce); scatter_add_sorted = the segmented reduce alone on
+    pre-sorted indices, which is how a train step runs it (the sort depends only on the batch ids and is overlapped)."""
     import torch
     from mtamrecommender_b200 import engine as E
     from mtamrecommender_b200.synth import ZipfSampler
     res = {}
     try:
         table = torch.empty((rows, D), dtype=torch.float32, device=dev).uniform_(-0.3, 0.3)
-        rng = np.random.default_rng(5)
-        idx_np = ZipfSampler(rows - 3, 1.05).sample(rng, n)
-        idx_np[rng.random(n) < 0.45] = 0                      # pad id share of a ragged batch
-        idx = torch.from_numpy(idx_np).to(dev)
         out = torch.empty((n, D), dtype=torch.float32, device=dev)
+        dst = torch.zeros((rows, D), dtype=torch.float32, device=dev)
+        ws = torch.empty(E.scatter_add_workspace(n, rows, D), dtype=torch.uint8, device=dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def t(fn, reps=10):
@@ -329,21 +343,50 @@ def bandwidth_kernels(eng, dev, pk, n=8192 * 200, D=64, rows=10_000_003):
             ev1.record()
             torch.cuda.synchronize()
             return ev0.elapsed_time(ev1) / reps
-        ms = t(lambda: E.gather(table, idx, out))
-        b = n * (4 + 2 * D * 4)
-        res["gather"] = {"rows": n, "D": D, "ms": ms, "achieved_GBs": b / ms / 1e6, "frac": b / ms / 1e6 / pk["hbm"],
-                         "algorithmic_bytes": b}
-        ws = torch.empty(E.scatter_add_workspace(n, rows, D), dtype=torch.uint8, device=dev)
-        dst = torch.zeros((rows, D), dtype=torch.float32, device=dev)
-        nu = int(np.unique(idx_np).size)
-        ms = t(lambda: E.scatter_add(dst, idx, out, ws), reps=5)
-        b = n * (4 + D * 4) + nu * D * 4
-        res["scatter_add"] = {"rows": n, "D": D, "unique": nu, "ms": ms, "achieved_GBs": b / ms / 1e6,
-                              "frac": b / ms / 1e6 / pk["hbm"], "algorithmic_bytes": b}
+
+        def entry(b, ms, **kw):
+            return dict(ms=ms, algorithmic_bytes=b, achieved_GBs=b / ms / 1e6, frac=b / ms / 1e6 / pk["hbm"], **kw)
+        rng = np.random.default_rng(5)
+        for dist in ("uniform", "zipf_pad"):
+            if dist == "uniform":
+                idx_np = rng.integers(0, rows, n).astype(np.int32)
+            else:
+                idx_np = ZipfSampler(rows - 3, 1.05).sample(rng, n)
+                idx_np[rng.random(n) < 0.45] = 0                      # pad id share of a ragged batch
+            idx = torch.from_numpy(idx_np).to(dev)
+            nu = int(np.unique(idx_np).size)
+            r = {"rows": n, "D": D, "table_rows": rows, "unique": nu}
+            r["gather"] = entry(n * (4 + 2 * D * 4), t(lambda: E.gather(table, idx, out)))
+            b = n * (4 + D * 4) + nu * D * 4
+            r["scatter_add"] = entry(b, t(lambda: E.scatter_add(dst, idx, out, ws), reps=5))
+            srt = E.sort_indices(idx, rows)
+            ws2 = torch.empty(max(int(_lib_sorted_ws(n, D)), 16), dtype=torch.uint8, device=dev)
+            # dst += needs the touched dst rows read as well as written: the second figure counts that traffic
+            r["scatter_add_sorted"] = entry(b, t(lambda: E.scatter_add_sorted(dst, srt, out, ws2), reps=5),
+                                            bytes_incl_dst_read=b + nu * D * 4)
+            r["scatter_add_sorted"]["achieved_GBs_incl_dst_read"] = (b + nu * D * 4) / r["scatter_add_sorted"]["ms"] / 1e6
+            r["scatter_add_sorted"]["frac_incl_dst_read"] = r["scatter_add_sorted"]["achieved_GBs_incl_dst_read"] / pk["hbm"]
+            res[dist] = r
+            del idx, srt, ws2
         del table, out, dst, ws
     except Exception as e:   # report, never hide
         res["error"] = repr(e)
     return res
+
+
+def _lib_sorted_ws(n, D):
+    from mtamrecommender_b200 import _lib
+    return _lib.load().mtam_scatter_add_sorted_workspace(n, D)
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the kernels named in the rooflines, copied from the committed `ncu --set full`
+    captures (profiles/traffic_r01.json says which report each number came from)."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
 
 
 def main():

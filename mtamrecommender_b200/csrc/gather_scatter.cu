@@ -327,56 +327,105 @@ __device__ __forceinline__ void vred(float* p, const float2& a) { atomicAdd(rein
 __device__ __forceinline__ void vred(float* p, const float4& a) { atomicAdd(reinterpret_cast<float4*>(p), a); }
 
 // D == 32*VEC: each lane owns VEC contiguous floats of a row (one 128-bit / 64-bit / 32-bit access).
-template <int VEC>
-__global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_vec_kernel(
+// A CTA of SRV_WARPS warps owns SRV_WARPS consecutive 64-entry tiles.  Every warp reduces its tile: runs that begin
+// and end inside the tile are added to dst at once; the tile's first run ("head", it may continue the previous
+// tile's last run) and last run ("tail") go to shared memory, where warp 0 stitches the tiles together in order,
+// adds every run that ends inside the CTA to dst (one add per key per CTA) and carries the CTA's last run to the
+// next level.  So a level shrinks the list 64*SRV_WARPS-fold.
+// Entries per warp: 64 on the big first level (8 groups of 8 rows in flight), 8 on the short carry lists of the later
+// levels, where one group per warp keeps the launch a single round of loads deep.
+constexpr int SRV_WARPS = 8;
+
+template <int VEC, int CH>
+__global__ void __launch_bounds__(SRV_WARPS * 32) seg_reduce_vec_kernel(
     const int32_t* __restrict__ keys, const float* __restrict__ src, int ld_src,
     const int32_t* __restrict__ perm, int64_t n, int ld_dst, float* __restrict__ dst,
     int32_t* __restrict__ carry_keys, float* __restrict__ carry_rows) {
   using V = typename VecT<VEC>::T;
   constexpr int D = 32 * VEC;
-  const int lane = threadIdx.x & 31;
-  const int64_t tile = (int64_t)blockIdx.x * SR_WARPS + (threadIdx.x >> 5);
-  const int64_t ntiles = (n + SR_CH - 1) / SR_CH;
-  if (tile >= ntiles) return;
-  const int64_t start = tile * SR_CH;
-  const int cnt = (int)min((int64_t)SR_CH, n - start);
-  // tile keys / source rows: two coalesced loads, broadcast later with shuffles
-  const int l0 = min(lane, cnt - 1), l1 = min(lane + 32, cnt - 1);   // clamp: entries past the end alias the last one
-  int32_t k0 = keys[start + l0], k1 = keys[start + l1];
-  int32_t r0 = perm ? perm[start + l0] : (int32_t)(start + l0);
-  int32_t r1 = perm ? perm[start + l1] : (int32_t)(start + l1);
-  V acc;
-  vzero(acc);
-  int32_t cur = __shfl_sync(0xffffffffu, k0, 0);
-  for (int i0 = 0; i0 < cnt; i0 += SR_G) {
-    V x[SR_G];
-    int32_t kk[SR_G];
+  __shared__ V s_head[SRV_WARPS][32], s_tail[SRV_WARPS][32];
+  __shared__ int32_t s_hkey[SRV_WARPS], s_tkey[SRV_WARPS];
+  __shared__ int s_single[SRV_WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * SRV_WARPS + w;
+  const int64_t ntiles = (n + CH - 1) / CH;
+  if (tile < ntiles) {
+    const int64_t start = tile * CH;
+    const int cnt = (int)min((int64_t)CH, n - start);
+    // tile keys / source rows: two coalesced loads, broadcast later with shuffles
+    const int l0 = min(lane, cnt - 1), l1 = min(lane + 32, cnt - 1);   // clamp: entries past the end alias the last one
+    int32_t k0 = keys[start + l0], k1 = keys[start + l1];
+    int32_t r0 = perm ? perm[start + l0] : (int32_t)(start + l0);
+    int32_t r1 = perm ? perm[start + l1] : (int32_t)(start + l1);
+    V acc, head;
+    vzero(acc);
+    vzero(head);
+    int32_t cur = __shfl_sync(0xffffffffu, k0, 0);
+    const int32_t hkey = cur;
+    bool first_run = true;
+    for (int i0 = 0; i0 < cnt; i0 += SR_G) {
+      V x[SR_G];
+      int32_t kk[SR_G];
 #pragma unroll
-    for (int u = 0; u < SR_G; ++u) {     // unconditional, independent loads: SR_G rows in flight
-      int i = i0 + u;
-      int32_t ka = __shfl_sync(0xffffffffu, k0, i & 31), kb = __shfl_sync(0xffffffffu, k1, i & 31);
-      int32_t ra = __shfl_sync(0xffffffffu, r0, i & 31), rb = __shfl_sync(0xffffffffu, r1, i & 31);
-      kk[u] = (i < 32) ? ka : kb;
-      int32_t row = (i < 32) ? ra : rb;
-      x[u] = __ldg(reinterpret_cast<const V*>(src + (int64_t)row * ld_src) + lane);
-    }
+      for (int u = 0; u < SR_G; ++u) {     // unconditional, independent loads: SR_G rows in flight
+        int i = i0 + u;
+        int32_t ka = __shfl_sync(0xffffffffu, k0, i & 31), kb = __shfl_sync(0xffffffffu, k1, i & 31);
+        int32_t ra = __shfl_sync(0xffffffffu, r0, i & 31), rb = __shfl_sync(0xffffffffu, r1, i & 31);
+        kk[u] = (i < 32) ? ka : kb;
+        int32_t row = (i < 32) ? ra : rb;
+        x[u] = __ldg(reinterpret_cast<const V*>(src + (int64_t)row * ld_src) + lane);
+      }
 #pragma unroll
-    for (int u = 0; u < SR_G; ++u) {
-      if (i0 + u < cnt) {
-        if (kk[u] != cur) {              // warp-uniform: the run of `cur` ended
-          vred(dst + (int64_t)cur * ld_dst + lane * VEC, acc);
-          vzero(acc);
-          cur = kk[u];
+      for (int u = 0; u < SR_G; ++u) {
+        if (i0 + u < cnt) {
+          if (kk[u] != cur) {              // warp-uniform: the run of `cur` ended
+            if (first_run) { head = acc; first_run = false; }
+            else vred(dst + (int64_t)cur * ld_dst + lane * VEC, acc);
+            vzero(acc);
+            cur = kk[u];
+          }
+          vadd(acc, x[u]);
         }
-        vadd(acc, x[u]);
       }
     }
+    s_head[w][lane] = head;
+    s_tail[w][lane] = acc;
+    if (lane == 0) { s_hkey[w] = hkey; s_tkey[w] = cur; s_single[w] = first_run ? 1 : 0; }
   }
-  if (tile == ntiles - 1) {
-    vred(dst + (int64_t)cur * ld_dst + lane * VEC, acc);
+  __syncthreads();
+  if (w != 0) return;
+  const int nw = (int)min((int64_t)SRV_WARPS, ntiles - (int64_t)blockIdx.x * SRV_WARPS);
+  V cacc;
+  vzero(cacc);
+  int32_t ckey = 0;
+  bool cvalid = false;
+  for (int q = 0; q < nw; ++q) {
+    const int32_t hk = s_hkey[q], tk = s_tkey[q];
+    const V ta = s_tail[q][lane];
+    if (s_single[q]) {                      // the whole tile is one run
+      if (cvalid && tk == ckey) vadd(cacc, ta);
+      else {
+        if (cvalid) vred(dst + (int64_t)ckey * ld_dst + lane * VEC, cacc);
+        ckey = tk; cacc = ta; cvalid = true;
+      }
+    } else {
+      V ha = s_head[q][lane];
+      if (cvalid && hk == ckey) {           // the head run continues the pending run and ends here
+        vadd(cacc, ha);
+        vred(dst + (int64_t)ckey * ld_dst + lane * VEC, cacc);
+      } else {
+        if (cvalid) vred(dst + (int64_t)ckey * ld_dst + lane * VEC, cacc);
+        vred(dst + (int64_t)hk * ld_dst + lane * VEC, ha);
+      }
+      ckey = tk; cacc = ta; cvalid = true;
+    }
+  }
+  const int64_t nctas = (ntiles + SRV_WARPS - 1) / SRV_WARPS;
+  if (blockIdx.x == nctas - 1) {
+    vred(dst + (int64_t)ckey * ld_dst + lane * VEC, cacc);
   } else {
-    if (lane == 0) carry_keys[tile] = cur;
-    reinterpret_cast<V*>(carry_rows + tile * D)[lane] = acc;
+    if (lane == 0) carry_keys[blockIdx.x] = ckey;
+    reinterpret_cast<V*>(carry_rows + (int64_t)blockIdx.x * D)[lane] = cacc;
   }
 }
 
@@ -472,7 +521,12 @@ int seg_reduce_sorted(const int32_t* keys_sorted, const int32_t* perm, const flo
   int lds = ld_src;
   int64_t m = n;
   while (m > 0) {
-    int64_t nt = (m + SR_CH - 1) / SR_CH;
+    int maxv = (D + 31) / 32;
+    const bool vec_ok = (D == 32 || D == 64 || D == 128) && (lds % (D / 32) == 0) && (ld_dst % (D / 32) == 0) &&
+                        ((uintptr_t)s % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+    const int wch = (m > 65536) ? 64 : 8;            // entries per warp of the vector kernel at this level
+    const int ch = vec_ok ? wch * SRV_WARPS : SR_CH; // entries folded into one carry at this level
+    int64_t nt = (m + ch - 1) / ch;
     int32_t* ck = nullptr;
     float* cr = nullptr;
     if (nt > 1) {
@@ -480,16 +534,15 @@ int seg_reduce_sorted(const int32_t* keys_sorted, const int32_t* perm, const flo
       cr = b.take<float>((nt - 1) * D);
       if (!b.ok()) return set_error(MTAM_ERR_WORKSPACE, "seg_reduce: workspace %zu < %zu", ws_bytes, b.off);
     }
-    int blocks = cdiv(nt, SR_WARPS);
-    int maxv = (D + 31) / 32;
-    const bool vec_ok = (D == 32 || D == 64 || D == 128) && (lds % (D / 32) == 0) && (ld_dst % (D / 32) == 0) &&
-                        ((uintptr_t)s % 16 == 0) && ((uintptr_t)dst % 16 == 0);
-    if (vec_ok && D == 32)
-      seg_reduce_vec_kernel<1><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, ld_dst, dst, ck, cr);
-    else if (vec_ok && D == 64)
-      seg_reduce_vec_kernel<2><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, ld_dst, dst, ck, cr);
-    else if (vec_ok && D == 128)
-      seg_reduce_vec_kernel<4><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, ld_dst, dst, ck, cr);
+    int blocks = vec_ok ? (int)nt : cdiv(nt, SR_WARPS);
+#define SRV_LAUNCH(VEC_)                                                                                              \
+  do {                                                                                                                \
+    if (wch == 64) seg_reduce_vec_kernel<VEC_, 64><<<blocks, SRV_WARPS * 32, 0, st>>>(k, s, lds, pm, m, ld_dst, dst, ck, cr); \
+    else seg_reduce_vec_kernel<VEC_, 8><<<blocks, SRV_WARPS * 32, 0, st>>>(k, s, lds, pm, m, ld_dst, dst, ck, cr);    \
+  } while (0)
+    if (vec_ok && D == 32) SRV_LAUNCH(1);
+    else if (vec_ok && D == 64) SRV_LAUNCH(2);
+    else if (vec_ok && D == 128) SRV_LAUNCH(4);
     else if (maxv <= 1)
       seg_reduce_level_kernel<1><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);
     else if (maxv <= 2)
@@ -498,6 +551,7 @@ int seg_reduce_sorted(const int32_t* keys_sorted, const int32_t* perm, const flo
       seg_reduce_level_kernel<4><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);
     else
       seg_reduce_level_kernel<8><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);
+#undef SRV_LAUNCH
     MTAM_LAUNCH_CHECK();
     if (nt <= 1) break;
     k = ck;
