@@ -47,6 +47,11 @@ int gemm_atb_batched_f32(int P, int M, int N, int K, const float* A, int lda, in
 // tc_gemm.cu: same contract on tcgen05 (3xTF32), and the mode dispatcher
 int gemm_tf32x3(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const GemmEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st);
+// tc_gemm_ws.cu: warp-specialised persistent variant (A operand staged in TMEM), used whenever its alignment holds
+bool gemm_ws_supported(int transA, int M, int N, int K, const float* A, int lda);
+size_t gemm_ws_splitk_workspace_bytes(int M, int N, int K);
+int gemm_tf32x3_ws(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                   float* C, int ldc, const GemmEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st);
 int gemm_any(int mode, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const GemmEpilogue& epi, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t gemm_any_workspace_bytes(int M, int N, int K);

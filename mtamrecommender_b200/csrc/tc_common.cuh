@@ -21,6 +21,16 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// explicit shared-memory 128-bit accesses (a pointer carved out of dynamic smem can decay to a generic LD/ST)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -173,10 +183,12 @@ __device__ __forceinline__ int chunk_pos_mn(int row, int chunk) { return ((((chu
 // writes the 16-byte chunk `chunk` of row `row` of the hi and lo tiles (MN: the MN-major swizzle)
 template <bool MN>
 __device__ __forceinline__ void store_chunk_split(float* hi_tile, float* lo_tile, int row, int chunk, float4 v) {
-  const int off = row * 32 + ((MN ? chunk_pos_mn(row, chunk) : chunk_pos_k(row, chunk)) << 2);
-  float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
-  *reinterpret_cast<float4*>(lo_tile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  const uint32_t off = (uint32_t)(row * 32 + ((MN ? chunk_pos_mn(row, chunk) : chunk_pos_k(row, chunk)) << 2)) * 4u;
+  const float hx = tf32_hi(v.x), hy = tf32_hi(v.y), hz = tf32_hi(v.z), hw = tf32_hi(v.w);
+  // explicit st.shared: tiles carved out of dynamic shared memory otherwise compile to generic stores
+  sts128(smem_u32(hi_tile) + off, __float_as_uint(hx), __float_as_uint(hy), __float_as_uint(hz), __float_as_uint(hw));
+  sts128(smem_u32(lo_tile) + off, __float_as_uint(v.x - hx), __float_as_uint(v.y - hy), __float_as_uint(v.z - hz),
+         __float_as_uint(v.w - hw));
 }
 
 }  // namespace tc

@@ -10,6 +10,8 @@
 // the operand chunk (coalesced 128-bit loads), one elected thread issues 12 MMAs (4 k-steps x 3
 // split terms), completion is signalled through an mbarrier by tcgen05.commit.  Several CTAs are
 // resident per SM so one CTA's loads overlap another's MMAs.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -211,6 +213,9 @@ int gemm_tf32x3(int transA, int transB, int M, int N, int K, const float* A, int
                 int ldc, const GemmEpilogue& e, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
   if (K <= 0) return gemm_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ws, ws_bytes, st);
+  static const bool ws_on = !(getenv("MTAM_GEMM_WS") && getenv("MTAM_GEMM_WS")[0] == '0');   // developer switch
+  if (ws_on && gemm_ws_supported(transA, M, N, K, A, lda))   // the pipelined, warp-specialised kernel (tc_gemm_ws.cu)
+    return gemm_tf32x3_ws(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ws, ws_bytes, st);
   EpiDev epi{e.bias, e.mask_pos, e.add, e.ld_mask, e.ld_add, e.relu, e.accumulate, e.alpha};
   const int BN = tc_bn(N);
   int S = tc_pick_splits(M, N, K, BN);
@@ -253,7 +258,8 @@ int gemm_any(int mode, int transA, int transB, int M, int N, int K, const float*
   return gemm_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ws, ws_bytes, st);
 }
 size_t gemm_any_workspace_bytes(int M, int N, int K) {
-  return std::max(gemm_splitk_workspace_bytes(M, N, K), tc_gemm_splitk_workspace_bytes(M, N, K));
+  return std::max(std::max(gemm_splitk_workspace_bytes(M, N, K), tc_gemm_splitk_workspace_bytes(M, N, K)),
+                  gemm_ws_splitk_workspace_bytes(M, N, K));
 }
 
 }  // namespace mtam

@@ -8,7 +8,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(128, 128, 32), (128, 64, 64), (256, 768, 64), (200, 70, 100), (51200, 64, 128), (64, 192, 5000),
-          (128, 128, 768), (1, 8, 33), (300, 129, 40)]
+          (128, 128, 768), (1, 8, 33), (300, 129, 40),
+          (64, 768, 6000), (128, 64, 20000), (1000, 192, 70), (700, 333, 45)]
 
 
 @pytest.mark.parametrize("mode", [1, 0])
