@@ -197,6 +197,19 @@ int mtam_forward_backward(mtam_handle h, const mtam_batch* batch, int32_t global
 int mtam_finish_grads(mtam_handle h, float* norm_sq, int32_t scatter_local, void* stream);
 int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_out, void* stream);
 
+/* Data-parallel helpers.
+ *  mtam_set_item_grad_event: `cuda_event` (a cudaEvent_t owned by the caller, or NULL to clear) is recorded on the
+ *    step's stream as soon as the dense item-table gradient is complete (right after the softmax backward, the
+ *    first thing the backward pass does), so a driver can start all-reducing it on another stream while the rest
+ *    of the backward pass runs.
+ *  mtam_scatter_sparse_into: scatter-adds the LOCAL sparse pieces of the last forward_backward (deterministic sort
+ *    + segmented reduce; the sorts ran beside the forward pass) into caller-provided [rows, D] tables instead of the
+ *    grads arena; a NULL destination skips that table.  Used when the tables are small enough that all-reducing a
+ *    densified piece is cheaper than all-gathering the rows (multi-GPU). */
+int mtam_set_item_grad_event(mtam_handle h, void* cuda_event);
+int mtam_scatter_sparse_into(mtam_handle h, float* item_dst, float* category_dst, float* position_dst, float* user_dst,
+                             void* stream);
+
 /* BPR-MF only: fixes the negative item id that `tf.random_uniform([1], 0, item_count)` (BPRMF.py:43) would
  * draw, so a run can be reproduced; item_id < 0 restores the per-step draw from the handle's own generator. */
 int mtam_set_bpr_negative(mtam_handle h, int32_t item_id);

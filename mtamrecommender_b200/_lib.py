@@ -78,6 +78,8 @@ SIGNATURES = {
     "mtam_finish_grads": (C.c_int, [_VP, _VP, _I32, _VP]),
     "mtam_apply": (C.c_int, [_VP, C.c_double, _VP, _VP, _VP]),
     "mtam_set_bpr_negative": (C.c_int, [_VP, _I32]),
+    "mtam_set_item_grad_event": (C.c_int, [_VP, _VP]),
+    "mtam_scatter_sparse_into": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "mtam_prepare_step": (C.c_int, [_VP, C.c_double, _VP]),
     "mtam_sparse_pieces": (C.c_int, [_VP, C.POINTER(SparseView)]),
     "mtam_profile_enable": (C.c_int, [_VP, _I32]),

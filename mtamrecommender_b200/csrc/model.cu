@@ -69,6 +69,7 @@ struct mtam_model {
   bool prof = false;
   cudaStream_t side = nullptr;       // index sorts run here, concurrently with forward/backward
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_ce_done = nullptr;  // caller-owned: recorded once the dense item-table gradient is complete
   bool sort_pending = false;
   const int32_t *sk[4] = {}, *sp[4] = {};   // sorted keys / permutations: item, category, position, user
   int bpr_neg = -1;                  // injected negative item id (mtam_set_bpr_negative); -1: draw one per step
@@ -420,6 +421,7 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   phase(h, MTAM_PH_CE_BWD, st);
   MTAM_TRY(ce_backward(c.gemm_mode, D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
                        w.ce_ws, G + l.item, w.dpred, st));
+  if (h->ev_ce_done) MTAM_CUDA_CHECK(cudaEventRecord(h->ev_ce_done, st));
   // hops
   phase(h, MTAM_PH_HOP_BWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.dX, 0, (size_t)T * D * sizeof(float), st));
@@ -506,6 +508,7 @@ static int sa_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float* 
   phase(h, MTAM_PH_CE_BWD, st);
   MTAM_TRY(ce_backward(c.gemm_mode, c.D, w.pred, h->params + h->lay.item, bt->target_item_id, w.lse, bt->B, c.item_rows,
                        1.0f / (float)global_batch, w.ce_ws, h->grads + h->lay.item, w.dpred, st));
+  if (h->ev_ce_done) MTAM_CUDA_CHECK(cudaEventRecord(h->ev_ce_done, st));
   phase(h, MTAM_PH_HOP_BWD, st);
   MTAM_TRY(sa_backward(sa_ctx(h, bt), st));
   phase(h, MTAM_PH_EMBED_BWD, st);
@@ -825,6 +828,35 @@ int mtam_finish_grads(mtam_handle h, float* norm_sq, int32_t scatter_local, void
   if (c.kind != MTAM_KIND_PISTREC)
     MTAM_TRY(seg_reduce_sorted(h->sk[3], h->sp[3], w.dEu, D, B, D, G + l.user, D, w.seg_ws, w.seg_ws_bytes, st));
   (void)bt;
+  return 0;
+}
+
+int mtam_set_item_grad_event(mtam_handle h, void* cuda_event) {
+  if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
+  h->ev_ce_done = (cudaEvent_t)cuda_event;
+  return 0;
+}
+
+int mtam_scatter_sparse_into(mtam_handle h, float* item_dst, float* category_dst, float* position_dst, float* user_dst,
+                             void* stream) {
+  if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
+  if (!h->grads_pending) return set_error(MTAM_ERR_INVALID, "mtam_scatter_sparse_into without a pending forward_backward");
+  if (h->cfg.kind == MTAM_KIND_BPRMF) return set_error(MTAM_ERR_UNSUPPORTED, "mtam_scatter_sparse_into: not for BPR-MF");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mtam_config& c = h->cfg;
+  Workspace& w = h->ws;
+  const int B = h->last_B, D = c.D;
+  const int64_t T = (int64_t)B * c.L;
+  if (h->sort_pending) {
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    h->sort_pending = false;
+  }
+  if (item_dst) MTAM_TRY(seg_reduce_sorted(h->sk[0], h->sp[0], w.dE2, 2 * D, T, D, item_dst, D, w.seg_ws, w.seg_ws_bytes, st));
+  if (category_dst)
+    MTAM_TRY(seg_reduce_sorted(h->sk[1], h->sp[1], w.dE2 + D, 2 * D, T, D, category_dst, D, w.seg_ws, w.seg_ws_bytes, st));
+  if (position_dst) MTAM_TRY(seg_reduce_sorted(h->sk[2], h->sp[2], w.dEp, D, T, D, position_dst, D, w.seg_ws, w.seg_ws_bytes, st));
+  if (user_dst && c.kind != MTAM_KIND_PISTREC)
+    MTAM_TRY(seg_reduce_sorted(h->sk[3], h->sp[3], w.dEu, D, B, D, user_dst, D, w.seg_ws, w.seg_ws_bytes, st));
   return 0;
 }
 

@@ -30,7 +30,16 @@ from .engine import (DeviceBatch, Engine, gather, merge_topk, scatter_add, scatt
 
 
 class DataParallel:
-    def __init__(self, engine: Engine, group=None):
+    """mode "dense"  (tables not much larger than the gathered rows, e.g. 100 K items): every rank scatter-adds its
+                     OWN sparse item / category / position pieces into a zeroed [rows, D] buffer (sorts already done
+                     beside the forward pass) and the buffer is all-reduced -- traffic independent of the world size;
+       mode "gather" (huge tables, e.g. 10 M items): the sparse pieces (ids + value rows) are all-gathered and every
+                     rank scatter-adds the identical global list.
+    The user table is always handled the "gather" way (B rows per rank).  In both modes the all-reduce of the dense
+    item-table gradient starts on a second stream as soon as the softmax backward has produced it and overlaps the
+    rest of the backward pass."""
+
+    def __init__(self, engine: Engine, group=None, mode: str = "auto"):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.eng = engine
@@ -41,17 +50,31 @@ class DataParallel:
         dev = engine.device
         B, L, D, W = cfg.max_batch, cfg.L, cfg.D, self.world
         T = B * L
-        self.g_item = torch.empty(W * T, dtype=torch.int32, device=dev)
-        self.g_cat = torch.empty(W * T, dtype=torch.int32, device=dev)
-        self.g_pos = torch.empty(W * T, dtype=torch.int32, device=dev)
-        self.g_user = torch.empty(W * B, dtype=torch.int32, device=dev)
-        self.g_dE2 = torch.empty((W * T, 2 * D), dtype=torch.float32, device=dev)
-        self.g_dEp = torch.empty((W * T, D), dtype=torch.float32, device=dev)
-        self.g_dEu = torch.empty((W * B, D), dtype=torch.float32, device=dev)
         c = engine.c_cfg
-        need = max(scatter_add_workspace(W * T, c.item_rows, D), scatter_add_workspace(W * T, c.category_rows, D),
-                   scatter_add_workspace(W * T, c.position_rows, D), scatter_add_workspace(W * B, c.user_rows, D))
+        if mode == "auto":
+            mode = "dense" if c.item_rows <= 8 * W * T else "gather"
+        if mode not in ("dense", "gather"):
+            raise ValueError(f"unknown data-parallel mode {mode!r}")
+        self.mode = mode
+        self.g_user = torch.empty(W * B, dtype=torch.int32, device=dev)
+        self.g_dEu = torch.empty((W * B, D), dtype=torch.float32, device=dev)
+        need = scatter_add_workspace(W * B, c.user_rows, D)
+        if mode == "gather":
+            self.g_item = torch.empty(W * T, dtype=torch.int32, device=dev)
+            self.g_cat = torch.empty(W * T, dtype=torch.int32, device=dev)
+            self.g_pos = torch.empty(W * T, dtype=torch.int32, device=dev)
+            self.g_dE2 = torch.empty((W * T, 2 * D), dtype=torch.float32, device=dev)
+            self.g_dEp = torch.empty((W * T, D), dtype=torch.float32, device=dev)
+            need = max(need, scatter_add_workspace(W * T, c.item_rows, D), scatter_add_workspace(W * T, c.category_rows, D),
+                       scatter_add_workspace(W * T, c.position_rows, D))
+        else:
+            rows = c.item_rows + c.category_rows + c.position_rows
+            self.sp = torch.zeros((rows, D), dtype=torch.float32, device=dev)   # [item | category | position]
         self.scatter_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self.comm = torch.cuda.Stream(dev)
+        self.ev_item = torch.cuda.Event()
+        self.ev_item.record(torch.cuda.current_stream(dev))   # materialises the cudaEvent_t
+        check(engine.lib.mtam_set_item_grad_event(engine.h, C.c_void_p(self.ev_item.cuda_event)), "mtam_set_item_grad_event")
 
     # -- views into the engine's arenas / workspace ---------------------------------------------
     def _ws_view(self, ptr: int, rows: int, cols: int) -> torch.Tensor:
@@ -72,22 +95,46 @@ class DataParallel:
         eng, W = self.eng, self.world
         B, L, D = batch.B, eng.cfg.L, eng.cfg.D
         T = B * L
+        c = eng.c_cfg
+        main = torch.cuda.current_stream(eng.device)
         eng.forward_backward_device(batch, global_batch=B * W)
         sv = _lib.SparseView()
         check(eng.lib.mtam_sparse_pieces(eng.h, C.byref(sv)), "mtam_sparse_pieces")
+        item_lo, item_hi = int(sv.item_offset), int(sv.item_offset) + c.item_rows * D
+        # 1. dense item-table gradient: all-reduce on the second stream, from the moment the softmax backward is done
+        self.comm.wait_event(self.ev_item)
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(eng.grads[item_lo:item_hi], group=self.group)
+        # 2. the rest of the dense pieces, the loss scalars, the squared norm of the un-deduplicated sparse pieces
         dist.all_reduce(eng.scalars[:3], group=self.group)
-        dist.all_reduce(eng.grads[int(sv.dense_begin):], group=self.group)
         dist.all_reduce(eng.norm_sq, group=self.group)
-        eng.finish_grads(scatter_local=False)
-        c = eng.c_cfg
-        g_item = self._gather(self.g_item, batch.t["item_list"].reshape(-1))
-        g_cat = self._gather(self.g_cat, batch.t["category_list"].reshape(-1))
-        g_pos = self._gather(self.g_pos, batch.t["position_list"].reshape(-1))
-        g_dE2 = self._gather(self.g_dE2, self._ws_view(sv.item_cat_rows, T, 2 * D))
-        g_dEp = self._gather(self.g_dEp, self._ws_view(sv.position_rows, T, D))
-        scatter_add(self._grad_region(int(sv.item_offset), c.item_rows), g_item, g_dE2[:, :D], self.scatter_ws)
-        scatter_add(self._grad_region(int(sv.category_offset), c.category_rows), g_cat, g_dE2[:, D:], self.scatter_ws)
-        scatter_add(self._grad_region(int(sv.position_offset), c.position_rows), g_pos, g_dEp, self.scatter_ws)
+        dense_begin = int(sv.dense_begin)
+        if item_lo > dense_begin:
+            dist.all_reduce(eng.grads[dense_begin:item_lo], group=self.group)
+        dist.all_reduce(eng.grads[item_hi:], group=self.group)
+        main.wait_stream(self.comm)
+        eng.finish_grads(scatter_local=False)          # adds the squared norm of the (global) dense pieces
+        # 3. sparse pieces
+        if self.mode == "dense":
+            sp_item = self.sp[:c.item_rows]
+            sp_cat = self.sp[c.item_rows: c.item_rows + c.category_rows]
+            sp_pos = self.sp[c.item_rows + c.category_rows:]
+            self.sp.zero_()
+            check(eng.lib.mtam_scatter_sparse_into(eng.h, sp_item.data_ptr(), sp_cat.data_ptr(), sp_pos.data_ptr(), None,
+                                                   main.cuda_stream), "mtam_scatter_sparse_into")
+            dist.all_reduce(self.sp, group=self.group)
+            self._grad_region(int(sv.item_offset), c.item_rows).add_(sp_item)
+            self._grad_region(int(sv.category_offset), c.category_rows).copy_(sp_cat)
+            self._grad_region(int(sv.position_offset), c.position_rows).copy_(sp_pos)
+        else:
+            g_item = self._gather(self.g_item, batch.t["item_list"].reshape(-1))
+            g_cat = self._gather(self.g_cat, batch.t["category_list"].reshape(-1))
+            g_pos = self._gather(self.g_pos, batch.t["position_list"].reshape(-1))
+            g_dE2 = self._gather(self.g_dE2, self._ws_view(sv.item_cat_rows, T, 2 * D))
+            g_dEp = self._gather(self.g_dEp, self._ws_view(sv.position_rows, T, D))
+            scatter_add(self._grad_region(int(sv.item_offset), c.item_rows), g_item, g_dE2[:, :D], self.scatter_ws)
+            scatter_add(self._grad_region(int(sv.category_offset), c.category_rows), g_cat, g_dE2[:, D:], self.scatter_ws)
+            scatter_add(self._grad_region(int(sv.position_offset), c.position_rows), g_pos, g_dEp, self.scatter_ws)
         g_user = None
         if sv.has_user:
             g_user = self._gather(self.g_user, batch.t["user_id"])

@@ -37,23 +37,27 @@ def _rank_main(rank, world, port, q):
     Bl = 48 // world
     local = {k: v[rank * Bl:(rank + 1) * Bl] for k, v in full.items()}
     mc = dict(kind="MTAM", L=12, D=64, H=1, N=2, user_count=60, item_count=900, category_count=13)
-    eng = E.Engine(E.ModelConfig(max_batch=Bl, **mc), device=dev)
-    eng.set_params(P)
-    dp = DataParallel(eng)
-    losses = [dp.train_step(local, 1e-3) for _ in range(3)]
-    got = eng.get_params()
-    # replicas must be bit-identical
-    flat = eng.params.clone()
-    other = [torch.empty_like(flat) for _ in range(world)]
-    dist.all_gather(other, flat)
-    out["replicas_identical"] = all(bool(torch.equal(o, flat)) for o in other)
+    want = rl = None
     if rank == 0:
         ref = E.Engine(E.ModelConfig(max_batch=48, **mc), device=dev)
         ref.set_params(P)
         rl = [ref.train_step(full, 1e-3) for _ in range(3)]
         want = ref.get_params()
-        out["loss_err"] = max(abs(a - b) / abs(b) for a, b in zip(losses, rl))
-        out["param_err"] = max(float(np.linalg.norm(got[k] - want[k]) / max(np.linalg.norm(want[k]), 1e-30)) for k in want)
+    for mode in ("dense", "gather"):
+        eng = E.Engine(E.ModelConfig(max_batch=Bl, **mc), device=dev)
+        eng.set_params(P)
+        dp = DataParallel(eng, mode=mode)
+        losses = [dp.train_step(local, 1e-3) for _ in range(3)]
+        got = eng.get_params()
+        flat = eng.params.clone()                      # replicas must be bit-identical
+        other = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(other, flat)
+        out[f"replicas_identical_{mode}"] = all(bool(torch.equal(o, flat)) for o in other)
+        if rank == 0:
+            out[f"loss_err_{mode}"] = max(abs(a - b) / abs(b) for a, b in zip(losses, rl))
+            out[f"param_err_{mode}"] = max(float(np.linalg.norm(got[k] - want[k]) / max(np.linalg.norm(want[k]), 1e-30))
+                                           for k in want)
+        del dp, eng
     # ---- row-sharded catalogue -----------------------------------------------------------------
     V, D, k = 20011, 64, 50
     g = torch.Generator().manual_seed(11)
@@ -92,8 +96,9 @@ def test_two_gpu_dp_and_sharded_catalogue():
         p.join(60)
         assert p.exitcode == 0
     for r in (0, 1):
-        assert res[r]["replicas_identical"], "replicas diverged"
+        assert res[r]["replicas_identical_dense"] and res[r]["replicas_identical_gather"], "replicas diverged"
         assert res[r]["lookup_exact"], "sharded lookup differs from the local gather"
         assert res[r]["topk_exact"], "sharded top-k differs from the unsharded one"
-    assert res[0]["loss_err"] < 2e-5, res[0]
-    assert res[0]["param_err"] < 1e-4, res[0]
+    for mode in ("dense", "gather"):
+        assert res[0][f"loss_err_{mode}"] < 2e-5, res[0]
+        assert res[0][f"param_err_{mode}"] < 1e-4, res[0]
