@@ -98,16 +98,30 @@ class Engine:
             pi = ParamInfo()
             check(self.lib.mtam_param_info_get(self.h, i, C.byref(pi)), "mtam_param_info_get")
             self.info[pi.name.decode()] = pi
-        # pinned staging for the per-step host->device feed copy
+        # Per-step host->device feed: the 11 arrays live back to back in ONE pinned host buffer and ONE device buffer
+        # (256-byte aligned regions), so a step's feed is a single cudaMemcpyAsync; `_pinned[k]` / `_dev[k]` are views.
         self._pinned: Dict[str, torch.Tensor] = {}
+        self._pinned_np: Dict[str, np.ndarray] = {}
         self._dev: Dict[str, torch.Tensor] = {}
         B, L = cfg.max_batch, cfg.L
+        offs, total = {}, 0
         for k in FEED_KEYS:
+            n = B * L if k.endswith("_list") else B
+            offs[k] = (total, n)
+            total += (n * 4 + 255) // 256 * 256
+        self._pinned_all = torch.empty(total, dtype=torch.uint8).pin_memory()
+        self._dev_all = torch.empty(total, dtype=torch.uint8, device=dev)
+        for k in FEED_KEYS:
+            o, n = offs[k]
             shape = (B, L) if k.endswith("_list") else (B,)
             dt = torch.int32 if k in FEED_INT else torch.float32
-            self._pinned[k] = torch.empty(shape, dtype=dt).pin_memory()
-            self._dev[k] = torch.empty(shape, dtype=dt, device=dev)
+            self._pinned[k] = self._pinned_all[o: o + n * 4].view(dt).view(shape)
+            self._pinned_np[k] = self._pinned[k].numpy()
+            self._dev[k] = self._dev_all[o: o + n * 4].view(dt).view(shape)
         self._scalars_host = torch.empty(_lib.S_COUNT, dtype=torch.float32).pin_memory()
+        self._graph = None
+        self._graph_B = -1
+        self._h2d_done = None
         if seed is not None:
             self.init_random(seed)
 
@@ -196,15 +210,15 @@ class Engine:
         B = int(len(feed["user_id"]))
         if B < 1 or B > self.cfg.max_batch:
             raise ValueError(f"batch size {B} outside [1, {self.cfg.max_batch}]")
-        out = {}
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()          # the previous feed's DMA must have left the pinned buffer
         for k in FEED_KEYS:
-            src = torch.from_numpy(np.ascontiguousarray(feed[k]))
-            pin = self._pinned[k][:B]
-            pin.copy_(src)
-            dv = self._dev[k][:B]
-            dv.copy_(pin, non_blocking=True)
-            out[k] = dv
-        return DeviceBatch(out, B)
+            np.copyto(self._pinned_np[k][:B], feed[k], casting="same_kind")
+        self._dev_all.copy_(self._pinned_all, non_blocking=True)          # one H2D copy for the whole feed
+        if self._h2d_done is None:
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.device))
+        return DeviceBatch({k: self._dev[k][:B] for k in FEED_KEYS}, B)
 
     def device_batch(self, tensors: Dict[str, torch.Tensor]) -> DeviceBatch:
         B = int(tensors["user_id"].shape[0])
@@ -229,7 +243,13 @@ class Engine:
         return self._scalars_host.numpy().copy()
 
     def train_step(self, feed: Dict[str, np.ndarray], lr: float) -> float:
-        self.train_step_device(self.upload(feed), lr)
+        """One `model.train` call from a host feed: pack -> one H2D copy -> the step (the captured CUDA graph when
+        `capture_train_graph` was called for this batch size, else eager launches) -> loss read back."""
+        batch = self.upload(feed)
+        if self._graph is not None and batch.B == self._graph_B:
+            self.train_step_graph(lr)
+        else:
+            self.train_step_device(batch, lr)
         return float(self.read_scalars()[_lib.S_LOSS])
 
     def forward_device(self, batch: DeviceBatch, want_pred=True):
