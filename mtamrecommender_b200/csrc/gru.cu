@@ -49,6 +49,19 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
   const float kw1 = vecs[0 * D + n2], kb1 = vecs[1 * D + n2], hw1 = vecs[2 * D + n2], tw1 = vecs[3 * D + n2],
               tb1 = vecs[4 * D + n2], kw2 = vecs[5 * D + n2], tw12 = vecs[6 * D + n2], tb12 = vecs[7 * D + n2];
 
+  // this thread's two weight columns never change over the L steps: keep them in registers (the shared-memory copy
+  // is only the staging area), so a step's inner loops read nothing but the broadcast state vectors
+  constexpr bool REGW = D <= 64;           // at num_units 128 the 256 values per thread would spill
+  constexpr int RW = REGW ? D : 1;
+  float w1r[RW], w2r[RW];
+  if (REGW) {
+#pragma unroll
+    for (int k = 0; k < RW; ++k) {
+      w1r[k] = Wh[k * 3 * D + n1];
+      w2r[k] = Wh[k * 3 * D + 2 * D + n2];
+    }
+  }
+
   for (int t = 0; t < tmax; ++t) {
     // ---- phase 1: r,u ----
     float g1[4];
@@ -58,9 +71,9 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
       g1[i] = ld_nc_pred(GX + ((int64_t)(b0 + row) * L + t) * (3 * D) + n1, t < steps[row]);
     }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
+#pragma unroll REGW ? D : 8
     for (int k = 0; k < D; ++k) {
-      float w = Wh[k * 3 * D + n1];
+      const float w = REGW ? w1r[REGW ? k : 0] : Wh[k * 3 * D + n1];
       float4 h4 = *reinterpret_cast<const float4*>(&hT[k * RB + rg1 * 4]);
       acc[0] = fmaf(h4.x, w, acc[0]); acc[1] = fmaf(h4.y, w, acc[1]);
       acc[2] = fmaf(h4.z, w, acc[2]); acc[3] = fmaf(h4.w, w, acc[3]);
@@ -94,9 +107,9 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
       dl[i] = ld_nc_pred(timelast + tok, live);
     }
     float acc2[2] = {0.f, 0.f};
-#pragma unroll 8
+#pragma unroll REGW ? D : 8
     for (int k = 0; k < D; ++k) {
-      float w = Wh[k * 3 * D + 2 * D + n2];
+      const float w = REGW ? w2r[REGW ? k : 0] : Wh[k * 3 * D + 2 * D + n2];
       float2 r2 = *reinterpret_cast<const float2*>(&rhT[k * RB + rg2 * 2]);
       acc2[0] = fmaf(r2.x, w, acc2[0]);
       acc2[1] = fmaf(r2.y, w, acc2[1]);
