@@ -173,8 +173,40 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
   float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // kw1,kb1,hw1,tw1,tb1,kw2,tw12,tb12
   float dh[2] = {0.f, 0.f};
 
+  // the step's saved activations are independent of the recurrence: the loads of step t-1 are issued at the top of
+  // step t and land while its two matrix-vector loops run
+  struct StepIn { float r, u, c, Tg, hold, x, dl; };
+  auto fetch = [&](int t, StepIn (&v)[2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = rg * 2 + i;
+      const bool live = t >= 0 && t < steps[row];
+      const int64_t tok = (int64_t)(b0 + row) * L + (live ? t : 0);
+      const float* s4 = RUCT + tok * (4 * D);
+      v[i].r = ld_nc_pred(s4 + n, live); v[i].u = ld_nc_pred(s4 + D + n, live);
+      v[i].c = ld_nc_pred(s4 + 2 * D + n, live); v[i].Tg = ld_nc_pred(s4 + 3 * D + n, live);
+      v[i].hold = ld_nc_pred(Hs + tok * D + n, live);      // h_{t-1}: Hs is shifted by one (leading zero row)
+      v[i].x = ld_nc_pred(X + tok * D + n, live);
+      v[i].dl = ld_nc_pred(timelast + tok, live);
+    }
+  };
+  // part of this thread's weight column lives in registers for all L steps (D <= 64): the candidate path
+  // (rows 2D..3D of WhT) and the first D rows of the gate path
+  constexpr bool REGW = D <= 64;
+  constexpr int RW = REGW ? D : 1;
+  float wc[RW], wg[RW];
+  if (REGW) {
+#pragma unroll
+    for (int m = 0; m < RW; ++m) {
+      wc[m] = WhT[(2 * D + m) * D + n];
+      wg[m] = WhT[m * D + n];
+    }
+  }
+  StepIn cur[2], nxt[2];
+  fetch(tmax - 1, cur);
   for (int t = tmax - 1; t >= 0; --t) {
     float dhacc[2], rr[2], hh[2];
+    fetch(t - 1, nxt);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       int row = rg * 2 + i;
@@ -183,10 +215,8 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
         int64_t b = b0 + row;
         int64_t tok = b * L + t;
         if (t == steps[row] - 1) dh[i] += __ldg(dq0 + b * D + n);
-        const float* s4 = RUCT + tok * (4 * D);
-        float r = __ldg(s4 + n), u = __ldg(s4 + D + n), c = __ldg(s4 + 2 * D + n), Tg = __ldg(s4 + 3 * D + n);
-        float hold = __ldg(Hs + tok * D + n);  // h_{t-1}: Hs is shifted by one (leading zero row)
-        float x = __ldg(X + tok * D + n), dl = __ldg(timelast + tok);
+        const float r = cur[i].r, u = cur[i].u, c = cur[i].c, Tg = cur[i].Tg, hold = cur[i].hold, x = cur[i].x,
+                    dl = cur[i].dl;
         float d = dh[i];
         float du = d * (hold - c * Tg), dc = d * (1.f - u) * Tg, dT = d * (1.f - u) * c;
         dhacc[i] = d * u;
@@ -215,9 +245,9 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
     __syncthreads();
     // d(r*h)[n] = sum_m dpc[m] * Wc_h[n][m]
     float acc[2] = {0.f, 0.f};
-#pragma unroll 8
+#pragma unroll REGW ? D : 8
     for (int m = 0; m < D; ++m) {
-      float w = WhT[(2 * D + m) * D + n];
+      const float w = REGW ? wc[REGW ? m : 0] : WhT[(2 * D + m) * D + n];
       float2 d2 = *reinterpret_cast<const float2*>(&dpcS[m * RB + rg * 2]);
       acc[0] = fmaf(d2.x, w, acc[0]);
       acc[1] = fmaf(d2.y, w, acc[1]);
@@ -237,16 +267,26 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
     __syncthreads();
     // dh_prev[n] += sum_m dpg[m] * Wg_h[n][m],  m over 2D
     float acc2[2] = {0.f, 0.f};
+    if (REGW) {
+#pragma unroll
+      for (int m = 0; m < RW; ++m) {
+        const float2 d2 = *reinterpret_cast<const float2*>(&dpgS[m * RB + rg * 2]);
+        acc2[0] = fmaf(d2.x, wg[m], acc2[0]);
+        acc2[1] = fmaf(d2.y, wg[m], acc2[1]);
+      }
+    }
 #pragma unroll 8
-    for (int m = 0; m < 2 * D; ++m) {
+    for (int m = REGW ? D : 0; m < 2 * D; ++m) {
       float w = WhT[m * D + n];
       float2 d2 = *reinterpret_cast<const float2*>(&dpgS[m * RB + rg * 2]);
       acc2[0] = fmaf(d2.x, w, acc2[0]);
       acc2[1] = fmaf(d2.y, w, acc2[1]);
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i) {
       if (t < steps[rg * 2 + i]) dh[i] = dhacc[i] + acc2[i];
+      cur[i] = nxt[i];
+    }
     __syncthreads();
   }
   // per-CTA reduction of the vector-parameter gradients over the 4 row groups (fixed order)
