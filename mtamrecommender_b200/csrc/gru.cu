@@ -62,14 +62,33 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
     }
   }
 
+  // x-side inputs of a step do not depend on the recurrence: those of step t+1 are loaded during step t
+  struct StepIn { float g1[4], g2[2], xv[2], dl[2]; };
+  auto fetch = [&](int t, StepIn& v) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = rg1 * 4 + i;
+      const bool live = t < steps[row];
+      v.g1[i] = ld_nc_pred(GX + ((int64_t)(b0 + row) * L + (live ? t : 0)) * (3 * D) + n1, live);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = rg2 * 2 + i;
+      const bool live = t < steps[row];
+      const int64_t tok = (int64_t)(b0 + row) * L + (live ? t : 0);
+      v.g2[i] = ld_nc_pred(GX + tok * (3 * D) + 2 * D + n2, live);
+      v.xv[i] = ld_nc_pred(X + tok * D + n2, live);
+      v.dl[i] = ld_nc_pred(timelast + tok, live);
+    }
+  };
+  StepIn cur, nxt;
+  fetch(0, cur);
   for (int t = 0; t < tmax; ++t) {
+    fetch(t + 1, nxt);          // rows whose sequence has ended (and t + 1 == tmax) load nothing
     // ---- phase 1: r,u ----
     float g1[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int row = rg1 * 4 + i;
-      g1[i] = ld_nc_pred(GX + ((int64_t)(b0 + row) * L + t) * (3 * D) + n1, t < steps[row]);
-    }
+    for (int i = 0; i < 4; ++i) g1[i] = cur.g1[i];
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll REGW ? D : 8
     for (int k = 0; k < D; ++k) {
@@ -98,14 +117,7 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
     // ---- phase 2: candidate, time gate, state update ----
     float g2[2], xv[2], dl[2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      int row = rg2 * 2 + i;
-      bool live = t < steps[row];
-      int64_t tok = (int64_t)(b0 + row) * L + t;
-      g2[i] = ld_nc_pred(GX + tok * (3 * D) + 2 * D + n2, live);
-      xv[i] = ld_nc_pred(X + tok * D + n2, live);
-      dl[i] = ld_nc_pred(timelast + tok, live);
-    }
+    for (int i = 0; i < 2; ++i) { g2[i] = cur.g2[i]; xv[i] = cur.xv[i]; dl[i] = cur.dl[i]; }
     float acc2[2] = {0.f, 0.f};
 #pragma unroll REGW ? D : 8
     for (int k = 0; k < D; ++k) {
@@ -132,6 +144,7 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
         hT[n2 * RB + row] = hn;       // only this thread touches this element in phase 2
       }
     }
+    cur = nxt;
     __syncthreads();
   }
 #pragma unroll
