@@ -256,12 +256,16 @@ long long mtam_launch_count(void);
 /* Full-catalogue scoring + top-k: tf.matmul(pred, item_table^T) + tf.nn.top_k (base_model.py:194-202).
  * Sorted descending, ties -> lower index.  idx_out [B,k] int32, score_out [B,k] (may be NULL).
  * `row_begin`/`row_end` restrict scoring to item rows [row_begin,row_end) (a table shard); indices
- * written are global row numbers. */
+ * written are global row numbers.
+ * gemm_mode (mtam_gemm_mode; mtam_eval_topk uses the handle's): MTAM_GEMM_FP32 computes every score with an fp32 FMA
+ * chain; MTAM_GEMM_TF32X3 (num_units 32 / 64) runs the [B,V] product on tcgen05 as a filter (maximum logit per bucket
+ * of 16 / 64 items), then rescores the items of the k+14 best buckets per row with the same fp32 FMA chain -- same
+ * indices and scores unless more than 14 bucket maxima tie with the k-th within the 3xTF32 rounding error. */
 int mtam_eval_topk(mtam_handle h, const mtam_batch* batch, int32_t k, int32_t* idx_out, float* score_out,
                    void* stream);
-int mtam_score_topk(const float* pred, int32_t B, int32_t D, const float* item_table, int32_t row_begin,
-                    int32_t row_end, int32_t k, int32_t* idx_out, float* score_out, void* workspace,
-                    size_t workspace_bytes, void* stream);
+int mtam_score_topk(int32_t gemm_mode, const float* pred, int32_t B, int32_t D, const float* item_table,
+                    int32_t row_begin, int32_t row_end, int32_t k, int32_t* idx_out, float* score_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
 size_t mtam_score_topk_workspace(int32_t B, int32_t rows, int32_t k);
 
 /* Merge per-shard top-k lists: in_idx/in_score are [n_lists,B,k] (each list sorted, shard order =

@@ -88,7 +88,7 @@ SIGNATURES = {
     "mtam_gemm_workspace": (_SZ, [_I32, _I32, _I32]),
     "mtam_launch_count": (C.c_longlong, []),
     "mtam_eval_topk": (C.c_int, [_VP, C.POINTER(Batch), _I32, _VP, _VP, _VP]),
-    "mtam_score_topk": (C.c_int, [_VP, _I32, _I32, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _SZ, _VP]),
+    "mtam_score_topk": (C.c_int, [_I32, _VP, _I32, _I32, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _SZ, _VP]),
     "mtam_score_topk_workspace": (_SZ, [_I32, _I32, _I32]),
     "mtam_merge_topk": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP, _VP, _VP]),
     "mtam_hr_ndcg": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP]),

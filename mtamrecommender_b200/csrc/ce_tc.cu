@@ -22,6 +22,7 @@
 #include "kernels.h"
 #include "model_kernels.h"
 #include "tc_common.cuh"
+#include "../../include/mtam.h"
 
 namespace mtam {
 using namespace tc;
@@ -35,10 +36,11 @@ constexpr int kWarpS = kEpiWarps + kProdWarps, kWarpPV = kWarpS + 1;   // the tw
 constexpr int kWarpLd = kWarpPV + 1;                                    // bulk-copy issuing warp
 constexpr int kThreads = (kWarpLd + 1) * 32;
 constexpr float kLog2e = 1.4426950408889634f;
-enum { CE_FWD = 0, CE_DP = 1, CE_DT = 2 };
+enum { CE_FWD = 0, CE_DP = 1, CE_DT = 2, CE_BMAX = 3 };
 // X tile rows = UMMA N of S (and K of O).  The forward pass has no second product and room in TMEM for
 // 128-column S buffers; a 128-wide MMA keeps the tensor pipe ahead of the issuing thread.
-__host__ __device__ constexpr int ce_bx(int mode) { return mode == CE_FWD ? 128 : 64; }
+__host__ __device__ constexpr int ce_bx(int mode) { return (mode == CE_FWD || mode == CE_BMAX) ? 128 : 64; }
+__host__ __device__ constexpr bool ce_pv(int mode) { return mode == CE_DP || mode == CE_DT; }
 
 // 2^x on the MUFU pipe (ex2.approx: 2 ulp; -inf -> 0)
 __device__ __forceinline__ float ex2(float x) {
@@ -76,6 +78,8 @@ struct CeTcArgs {
   float* tlogit;            // FWD: [B]
   float* dpred_partial;     // DP : [gridDim.x][B][D]
   float* dTable;            // DT : [V][D]
+  float* bmax;              // BMAX: [B][bmax_ld] maxima of the logits over buckets of bmax_bs (16 / 64) consecutive items
+  int bmax_ld, bmax_bs;
 };
 
 struct Bars {
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
   constexpr int BX = ce_bx(MODE);
   constexpr int KC = D / 32;                      // 32-float (128-byte) chunks of D
   constexpr int XT = BX * 32;                     // floats per chunk tile
-  constexpr bool PV = MODE != CE_FWD;
+  constexpr bool PV = ce_pv(MODE);
   constexpr int NST = 2;                          // operand stages in shared memory
   constexpr int STAGE = (PV ? 4 : 2) * KC * XT;   // floats per operand stage: K-major hi, lo (, MN-major hi, lo)
   constexpr int NSG = PV ? 3 : 4;                 // raw fp32 staging slots (64 X rows each) filled by bulk copies
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
     int tg = -1;
     float nl2 = 0.f;              // CE_DP: -lse[row]*log2(e)
     float m = -INFINITY, s = 0.f;
-    if (MODE != CE_DT && qvalid) {
+    if ((MODE == CE_FWD || MODE == CE_DP) && qvalid) {
       tg = __ldg(a.target + qrow);
       if (MODE == CE_DP) nl2 = -__ldg(a.lse + qrow) * kLog2e;
     }
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       if (lane == 0 && quad == 0) CE_TRACE(3 + 5 * half, i);
       const uint32_t scol = lane_base + COL_S0 + b * SW + half * HC, gcol = lane_base + COL_GL0 + b * SW + half * HC;
       const bool ragged = x0 + HC > xmax;          // only the catalogue's last tile (warp-uniform)
-      if (MODE == CE_FWD) {
+      if (!PV) {
         // pull this thread's 64 logits out of TMEM in one go and hand the S buffer straight back to the tensor core
         uint32_t r[HC];
         {
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
         float v[HC];
 #pragma unroll
         for (int j = 0; j < HC; ++j) v[j] = __uint_as_float(r[j]);
-        if ((unsigned)(tg - x0) < (unsigned)HC) {
+        if (MODE == CE_FWD && (unsigned)(tg - x0) < (unsigned)HC) {
 #pragma unroll
           for (int j = 0; j < HC; ++j)
             if (x0 + j == tg) a.tlogit[qrow] = v[j];
@@ -350,6 +354,26 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
 #pragma unroll
           for (int j = 0; j < HC; ++j)
             if (x0 + j >= xmax) v[j] = -INFINITY;
+        }
+        if (MODE == CE_BMAX) {
+          // top-k filter pass: only the maximum of every bucket of 16 (or 64) consecutive items leaves the SM
+          float g[HC / 16];
+#pragma unroll
+          for (int q = 0; q < HC / 16; ++q) {
+            float e0 = fmaxf(v[q * 16], v[q * 16 + 1]), e1 = fmaxf(v[q * 16 + 2], v[q * 16 + 3]);
+#pragma unroll
+            for (int j = 4; j < 16; j += 4) {
+              e0 = fmaxf(e0, fmaxf(v[q * 16 + j], v[q * 16 + j + 1]));
+              e1 = fmaxf(e1, fmaxf(v[q * 16 + j + 2], v[q * 16 + j + 3]));
+            }
+            g[q] = fmaxf(e0, e1);
+          }
+          if (qvalid) {
+            float* dst = a.bmax + (int64_t)qrow * a.bmax_ld;
+            if (a.bmax_bs == 16) *reinterpret_cast<float4*>(dst + (x0 >> 4)) = make_float4(g[0], g[1], g[2], g[3]);
+            else dst[x0 >> 6] = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+          }
+          continue;
         }
         float c0 = v[0], c1 = v[1], c2 = v[2], c3 = v[3];
 #pragma unroll
@@ -424,7 +448,8 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       mbar_arrive(&bars.g_full[b]);
       if (lane == 0 && quad == 0) CE_TRACE(4 + 5 * half, i);
     }
-    if (MODE == CE_FWD) {
+    if (MODE == CE_BMAX) {
+    } else if (MODE == CE_FWD) {
       if (qvalid) a.ms_partial[(int64_t)(blockIdx.x * 2 + half) * a.B + qrow] = make_float2(m, s);
     } else {
       constexpr int OC = D / 2;
@@ -456,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
 template <int D, int MODE>
 int ce_tc_launch(dim3 grid, const CeTcArgs& a, cudaStream_t st) {
   constexpr int KC = D / 32;
-  const size_t smem = (size_t)(2 * (MODE == CE_FWD ? 2 : 4) * KC * ce_bx(MODE) * 32 + (MODE == CE_FWD ? 4 : 3) * 64 * D) * sizeof(float) + 1024;
+  const size_t smem = (size_t)(2 * (ce_pv(MODE) ? 4 : 2) * KC * ce_bx(MODE) * 32 + (ce_pv(MODE) ? 3 : 4) * 64 * D) * sizeof(float) + 1024;
   MTAM_CUDA_CHECK(cudaFuncSetAttribute(ce_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ce_tc_kernel<D, MODE><<<grid, kThreads, smem, st>>>(a);
   MTAM_LAUNCH_CHECK();
@@ -516,6 +541,21 @@ int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* 
     return set_error(-1, "tensor-core softmax CE: num_units=%d not supported (32, 64)", D);
   }
   return ce_reduce_partials(a.dpred_partial, G, (int64_t)B * D, dpred, st);
+}
+
+// Top-k filter pass (topk.cu): bmax[b][j] = max over the items of bucket j of <pred[b], table[j*bs + .]>, buckets of
+// bs = 16 or 64 consecutive rows of `table` (V rows), ld = 128/bs * ceil(V/128) floats per pred row.
+int ce_bucket_max_tc(int D, const float* pred, int B, const float* table, int V, int bs, float* bmax, int ld,
+                     cudaStream_t st) {
+  if (bs != 16 && bs != 64) return set_error(MTAM_ERR_INVALID, "bucket maxima: bucket size %d not in {16, 64}", bs);
+  CeTcArgs a{};
+  a.pred = pred; a.table = table; a.B = B; a.V = V; a.bmax = bmax; a.bmax_ld = ld; a.bmax_bs = bs;
+  int G;
+  ce_tc_partition(CE_BMAX, B, V, &G, &a.tiles_per_cta);
+  dim3 grid(G, cdiv(B, QM));
+  if (D == 64) return ce_tc_launch<64, CE_BMAX>(grid, a, st);
+  if (D == 32) return ce_tc_launch<32, CE_BMAX>(grid, a, st);
+  return set_error(MTAM_ERR_INVALID, "tensor-core scoring: num_units=%d not supported (32, 64)", D);
 }
 
 }  // namespace mtam

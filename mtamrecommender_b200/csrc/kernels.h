@@ -62,7 +62,7 @@ size_t colsum_workspace_bytes(int M, int N);
 
 // ---- topk.cu --------------------------------------------------------------------------------
 size_t score_topk_workspace_bytes(int B, int rows, int k);
-int score_topk(const float* pred, int B, int D, const float* table, int row_begin, int row_end, int k, int32_t* idx_out,
+int score_topk(int mode, const float* pred, int B, int D, const float* table, int row_begin, int row_end, int k, int32_t* idx_out,
                float* score_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int merge_topk(const int32_t* in_idx, const float* in_score, int n_lists, int B, int k, int32_t* out_idx,
                float* out_score, cudaStream_t st);

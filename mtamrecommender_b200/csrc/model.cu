@@ -890,7 +890,7 @@ int mtam_eval_topk(mtam_handle h, const mtam_batch* batch, int32_t k, int32_t* i
   if (!idx_out) return set_error(MTAM_ERR_INVALID, "idx_out is null");
   cudaStream_t st = (cudaStream_t)stream;
   MTAM_TRY(fwd_dispatch(h, batch, batch->B, nullptr, false, st));
-  return score_topk(h->ws.pred, batch->B, h->cfg.D, h->params + h->lay.item, 0, h->cfg.item_rows, k, idx_out, score_out,
+  return score_topk(h->cfg.gemm_mode, h->ws.pred, batch->B, h->cfg.D, h->params + h->lay.item, 0, h->cfg.item_rows, k, idx_out, score_out,
                     h->ws.topk_ws, h->ws.topk_ws_bytes, st);
 }
 

@@ -113,6 +113,10 @@ int ce_forward_tc(int D, const float* pred, const float* table, const int32_t* t
 int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
                    float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st);
 
+// top-k filter pass: maxima of the logits over buckets of bs (16 / 64) consecutive table rows, [B][ld]
+int ce_bucket_max_tc(int D, const float* pred, int B, const float* table, int V, int bs, float* bmax, int ld,
+                     cudaStream_t st);
+
 // ---- optim.cu -------------------------------------------------------------------------------
 int sumsq_num_partials(int64_t n);
 int sumsq_partials(const float* x, int64_t n, float* partial, int* n_partial, cudaStream_t st);

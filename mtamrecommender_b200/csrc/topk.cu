@@ -7,6 +7,13 @@
 // The [B,V] score matrix is never written: a CTA owns 64 prediction rows and a contiguous chunk
 // of items, keeps the rows' running top-k in shared memory and only appends tile candidates that
 // beat the current k-th score.
+//
+// MTAM_GEMM_TF32X3 (num_units 32 / 64): the [B,V] product runs on tcgen05 as a FILTER.  ce_bucket_max_tc
+// (ce_tc.cu, the softmax forward pipeline with a max epilogue) leaves only the maximum logit of every bucket of
+// 16 / 64 consecutive items; topk_refine_kernel then picks, per pred row, the k+14 buckets with the largest maxima
+// (radix select, ties -> lower bucket), rescores their items with the same fp32 FMA chain as the kernel above and
+// selects the top k under (score desc, index asc).  Scores and indices therefore equal the exact-fp32 path bit for
+// bit unless more than 14 bucket maxima lie within the 3xTF32 rounding error (~1e-6 relative) of the k-th one.
 #include <limits.h>
 
 #include <algorithm>
@@ -193,6 +200,222 @@ __global__ void __launch_bounds__(256) hr_ndcg_kernel(const int32_t* __restrict_
   }
 }
 
+
+// ---- tensor-core filter + exact rescoring -----------------------------------------------------------------
+constexpr int kBucketPad = 14;                       // buckets kept beyond k
+constexpr int kMaxSel = KMAX + kBucketPad;           // 78
+constexpr int kMaxCand = kMaxSel * 64;
+
+__device__ __forceinline__ uint32_t order_key(float x) {   // monotone float -> uint32
+  const uint32_t b = __float_as_uint(x);
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+
+// exclusive scan of one int per thread over a 256-thread block, in thread order; total in *total
+__device__ __forceinline__ int block_excl_scan256(int v, int* warp_tot, int* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = warp_tot[i];
+    if (i < w) base += t;
+    tot += t;
+  }
+  *total = tot;
+  return base + inc - v;
+}
+
+// one CTA per pred row: select n_sel buckets by their maxima, rescore their items in fp32, emit the sorted top k
+template <int D>
+__global__ void __launch_bounds__(256) topk_refine_kernel(const float* __restrict__ pred, const float* __restrict__ table,
+                                                          const float* __restrict__ bmax, int ld, int n_buckets, int bs,
+                                                          int n_sel, int row_begin, int row_end, int k,
+                                                          int32_t* __restrict__ idx_out, float* __restrict__ score_out) {
+  __shared__ int hist[256];
+  __shared__ int sel[kMaxSel];
+  __shared__ float cs[kMaxCand];
+  __shared__ int warp_tot[8];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_need;
+  __shared__ float ws[8];
+  __shared__ int wi[8], wp[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const float* mrow = bmax + (int64_t)b * ld;
+
+  // ---- 1. key of the n_sel-th largest bucket maximum (MSB-first radix select, 8 bits per pass) ----
+  uint32_t prefix = 0, mask = 0;
+  int need = n_sel;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_buckets; i += 256) {
+      const uint32_t u = order_key(__ldg(mrow + i));
+      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // bins 255 .. 0 in descending order, 8 per lane: lane l owns bins 255-8l .. 248-8l
+      int c[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - (lane * 8 + j)]; tot += c[j]; }
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int before = inc - tot;                   // entries in strictly higher bins than this lane's
+      if (before < need && inc >= need) {       // the crossing bin is one of this lane's
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (before < need && before + c[j] >= need) {
+            s_prefix = prefix | ((uint32_t)(255 - (lane * 8 + j)) << shift);
+            s_need = need - before;
+            before = need;                      // stop
+          } else if (before < need) {
+            before += c[j];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    need = s_need;
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  // prefix = key K of the n_sel-th largest maximum; `need` of the buckets equal to K are taken, lowest index first
+
+  // ---- 2. ordered compaction of the selected bucket ids (thread t owns a contiguous index range) ----
+  {
+    const int seg = (n_buckets + 255) / 256;
+    const int i0 = min(n_buckets, tid * seg), i1 = min(n_buckets, i0 + seg);
+    int ngt = 0, neq = 0;
+    for (int i = i0; i < i1; ++i) {
+      const uint32_t u = order_key(__ldg(mrow + i));
+      ngt += u > prefix;
+      neq += u == prefix;
+    }
+    int tot_gt, tot_eq;
+    int ogt = block_excl_scan256(ngt, warp_tot, &tot_gt);
+    int oeq = block_excl_scan256(neq, warp_tot, &tot_eq);
+    for (int i = i0; i < i1; ++i) {
+      const uint32_t u = order_key(__ldg(mrow + i));
+      if (u > prefix) sel[ogt++] = i;
+      else if (u == prefix) {
+        if (oeq < need) sel[tot_gt + oeq] = i;
+        ++oeq;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. exact fp32 scores of the selected buckets' items: the FMA chain of score_topk_kernel ----
+  const int n_cand = n_sel * bs;
+  {
+    float q[D];
+#pragma unroll
+    for (int c = 0; c < D; c += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(pred + (int64_t)b * D + c));
+      q[c] = v.x; q[c + 1] = v.y; q[c + 2] = v.z; q[c + 3] = v.w;
+    }
+    for (int c = tid; c < n_cand; c += 256) {
+      const int item = row_begin + sel[c / bs] * bs + c % bs;
+      float acc = -INFINITY;
+      if (item < row_end) {
+        const float4* x = reinterpret_cast<const float4*>(table + (int64_t)item * D);
+        acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < D / 4; ++j) {
+          const float4 v = __ldg(x + j);
+          acc = fmaf(q[4 * j], v.x, acc);
+          acc = fmaf(q[4 * j + 1], v.y, acc);
+          acc = fmaf(q[4 * j + 2], v.z, acc);
+          acc = fmaf(q[4 * j + 3], v.w, acc);
+        }
+      }
+      cs[c] = acc;
+    }
+  }
+  __syncthreads();
+
+  // ---- 4. k rounds of arg-best under (score desc, item index asc) ----
+  for (int r = 0; r < k; ++r) {
+    float bsc = -INFINITY;
+    int bi = INT_MAX, bp = -1;
+    for (int c = tid; c < n_cand; c += 256) {
+      const float s = cs[c];
+      const int item = row_begin + sel[c / bs] * bs + c % bs;
+      if (item < row_end && s == s && (bp < 0 || better(s, item, bsc, bi))) { bsc = s; bi = item; bp = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float s2 = __shfl_xor_sync(0xffffffffu, bsc, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o), p2 = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (p2 >= 0 && (bp < 0 || better(s2, i2, bsc, bi))) { bsc = s2; bi = i2; bp = p2; }
+    }
+    if (lane == 0) { ws[warp] = bsc; wi[warp] = bi; wp[warp] = bp; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (wp[w] >= 0 && (bp < 0 || better(ws[w], wi[w], bsc, bi))) { bsc = ws[w]; bi = wi[w]; bp = wp[w]; }
+      idx_out[(int64_t)b * k + r] = bi;
+      if (score_out) score_out[(int64_t)b * k + r] = bsc;
+      if (bp >= 0) cs[bp] = __int_as_float(0x7fc00000);   // taken (NaN: skipped by the s == s test above)
+    }
+    __syncthreads();
+  }
+}
+
+// geometry of the tensor-core path for `rows` catalogue rows
+struct TcTopkPlan { int bs, ld, n_buckets, n_sel, chunk_rows; };
+static TcTopkPlan tc_topk_plan(int B, int rows, int k, size_t ws_bytes) {
+  TcTopkPlan p;
+  p.bs = rows > (1 << 20) ? 64 : 16;
+  p.ld = cdiv(rows, 128) * (128 / p.bs);
+  p.n_buckets = cdiv(rows, p.bs);
+  p.n_sel = std::min(p.n_buckets, k + kBucketPad);
+  const int64_t fit = (int64_t)(ws_bytes / sizeof(float)) / p.ld;
+  p.chunk_rows = (int)std::min<int64_t>(fit, B);
+  if (p.chunk_rows < B) p.chunk_rows = p.chunk_rows / 128 * 128;   // whole 128-row tiles except for the last chunk
+  return p;
+}
+static size_t tc_topk_workspace_bytes(int B, int rows) {
+  const int bs = rows > (1 << 20) ? 64 : 16;
+  const size_t ld = (size_t)cdiv(rows, 128) * (128 / bs);
+  // bucket maxima of up to B pred rows; beyond 1 GiB the pred rows are processed in chunks of >= 128
+  const size_t cap_rows = std::max<size_t>(128, ((size_t)1 << 30) / (ld * sizeof(float)) / 128 * 128);
+  return std::min<size_t>((size_t)B, cap_rows) * ld * sizeof(float) + 256;
+}
+
+template <int D>
+static int score_topk_tc_launch(const float* pred, int B, const float* table, int row_begin, int row_end, int k,
+                                int32_t* idx_out, float* score_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int rows = row_end - row_begin;
+  const TcTopkPlan p = tc_topk_plan(B, rows, k, ws_bytes);
+  if (p.chunk_rows < std::min(B, 128)) return set_error(MTAM_ERR_WORKSPACE, "score_topk (tensor-core path): workspace too small");
+  float* bmax = (float*)ws;
+  for (int b0 = 0; b0 < B; b0 += p.chunk_rows) {
+    const int nb = std::min(p.chunk_rows, B - b0);
+    MTAM_TRY(ce_bucket_max_tc(D, pred + (int64_t)b0 * D, nb, table + (int64_t)row_begin * D, rows, p.bs, bmax, p.ld, st));
+    topk_refine_kernel<D><<<nb, 256, 0, st>>>(pred + (int64_t)b0 * D, table, bmax, p.ld, p.n_buckets, p.bs, p.n_sel, row_begin,
+                                              row_end, k, idx_out + (int64_t)b0 * k, score_out ? score_out + (int64_t)b0 * k : nullptr);
+    MTAM_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 static int topk_chunks(int B, int rows) {
   int row_tiles = cdiv(B, KT);
   int want = std::max(1, cdiv(2 * kNumSMs, row_tiles));
@@ -200,9 +423,13 @@ static int topk_chunks(int B, int rows) {
   return std::min(want, maxc);
 }
 
-size_t score_topk_workspace_bytes(int B, int rows, int k) {
+static size_t score_topk_fp32_workspace_bytes(int B, int rows, int k) {
   int nc = topk_chunks(B, rows);
   return align_up((size_t)nc * B * k * sizeof(float), 256) + align_up((size_t)nc * B * k * sizeof(int32_t), 256) + 512;
+}
+// enough for either path
+size_t score_topk_workspace_bytes(int B, int rows, int k) {
+  return std::max(score_topk_fp32_workspace_bytes(B, rows, k), tc_topk_workspace_bytes(B, rows));
 }
 
 int merge_topk(const int32_t* in_idx, const float* in_score, int n_lists, int B, int k, int32_t* out_idx,
@@ -220,7 +447,7 @@ static int score_topk_launch(const float* pred, int B, const float* table, int r
                              int32_t* idx_out, float* score_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int rows = row_end - row_begin;
   const int nc = topk_chunks(B, rows);
-  if (ws_bytes < score_topk_workspace_bytes(B, rows, k)) return set_error(MTAM_ERR_WORKSPACE, "score_topk: workspace too small");
+  if (ws_bytes < score_topk_fp32_workspace_bytes(B, rows, k)) return set_error(MTAM_ERR_WORKSPACE, "score_topk: workspace too small");
   float* cs = (float*)ws;
   int32_t* ci = (int32_t*)((char*)ws + align_up((size_t)nc * B * k * sizeof(float), 256));
   int chunk_items = cdiv(cdiv(rows, nc), KT) * KT;
@@ -232,10 +459,15 @@ static int score_topk_launch(const float* pred, int B, const float* table, int r
   return merge_topk(ci, cs, nc, B, k, idx_out, score_out, st);
 }
 
-int score_topk(const float* pred, int B, int D, const float* table, int row_begin, int row_end, int k, int32_t* idx_out,
-               float* score_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+int score_topk(int mode, const float* pred, int B, int D, const float* table, int row_begin, int row_end, int k,
+               int32_t* idx_out, float* score_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (k < 1 || k > KMAX) return set_error(MTAM_ERR_INVALID, "top-k: k=%d outside [1,%d]", k, KMAX);
   if (row_end - row_begin < k) return set_error(MTAM_ERR_INVALID, "top-k: fewer than k=%d rows to score", k);
+  if (mode != MTAM_GEMM_FP32 && mode != MTAM_GEMM_TF32X3) return set_error(MTAM_ERR_INVALID, "top-k: unknown gemm_mode %d", mode);
+  if (mode == MTAM_GEMM_TF32X3 && ce_tc_supported(D)) {
+    if (D == 64) return score_topk_tc_launch<64>(pred, B, table, row_begin, row_end, k, idx_out, score_out, ws, ws_bytes, st);
+    return score_topk_tc_launch<32>(pred, B, table, row_begin, row_end, k, idx_out, score_out, ws, ws_bytes, st);
+  }
   switch (D) {
     case 32: return score_topk_launch<32>(pred, B, table, row_begin, row_end, k, idx_out, score_out, ws, ws_bytes, st);
     case 64: return score_topk_launch<64>(pred, B, table, row_begin, row_end, k, idx_out, score_out, ws, ws_bytes, st);
@@ -250,11 +482,12 @@ extern "C" {
 
 size_t mtam_score_topk_workspace(int32_t B, int32_t rows, int32_t k) { return mtam::score_topk_workspace_bytes(B, rows, k); }
 
-int mtam_score_topk(const float* pred, int32_t B, int32_t D, const float* item_table, int32_t row_begin, int32_t row_end,
-                    int32_t k, int32_t* idx_out, float* score_out, void* workspace, size_t workspace_bytes, void* stream) {
+int mtam_score_topk(int32_t gemm_mode, const float* pred, int32_t B, int32_t D, const float* item_table, int32_t row_begin,
+                    int32_t row_end, int32_t k, int32_t* idx_out, float* score_out, void* workspace, size_t workspace_bytes,
+                    void* stream) {
   if (!pred || !item_table || !idx_out || !workspace || B < 1)
     return mtam::set_error(MTAM_ERR_INVALID, "mtam_score_topk: null argument");
-  return mtam::score_topk(pred, B, D, item_table, row_begin, row_end, k, idx_out, score_out, workspace, workspace_bytes,
+  return mtam::score_topk(gemm_mode, pred, B, D, item_table, row_begin, row_end, k, idx_out, score_out, workspace, workspace_bytes,
                           (cudaStream_t)stream);
 }
 

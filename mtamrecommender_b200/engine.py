@@ -426,21 +426,21 @@ def scatter_add_sorted(dst: torch.Tensor, sorted_idx: SortedIndices, rows: torch
 
 
 def score_topk(pred: torch.Tensor, table: torch.Tensor, k: int, row_begin: int = 0, row_end: Optional[int] = None,
-               index_base: int = 0, workspace: Optional[torch.Tensor] = None):
+               index_base: int = 0, workspace: Optional[torch.Tensor] = None, gemm_mode: int = _lib.GEMM_TF32X3):
     """Top-k of pred x table[row_begin:row_end]^T (mtam_score_topk): sorted descending, ties -> lower index.
     `table` holds rows [index_base, index_base + table.shape[0]) of the catalogue; indices returned are global."""
     lib = _lib.load()
     B, D = pred.shape
     row_end = index_base + table.shape[0] if row_end is None else row_end
     rows = row_end - row_begin
-    need = max(int(lib.mtam_score_topk_workspace(B, rows, k)), 16)
-    if workspace is None or workspace.numel() < need:
+    if workspace is None:       # a caller-supplied workspace is passed as is (the library checks its size)
+        need = max(int(lib.mtam_score_topk_workspace(B, rows, k)), 16)
         workspace = torch.empty(need, dtype=torch.uint8, device=pred.device)
     idx = torch.empty((B, k), dtype=torch.int32, device=pred.device)
     sc = torch.empty((B, k), dtype=torch.float32, device=pred.device)
     # the library indexes item_table by global row number: pass the base shifted back by index_base rows
     base = table.data_ptr() - index_base * D * 4
-    check(lib.mtam_score_topk(pred.data_ptr(), B, D, base, row_begin, row_end, k, idx.data_ptr(), sc.data_ptr(),
+    check(lib.mtam_score_topk(gemm_mode, pred.data_ptr(), B, D, base, row_begin, row_end, k, idx.data_ptr(), sc.data_ptr(),
                               workspace.data_ptr(), workspace.numel(),
                               torch.cuda.current_stream(pred.device).cuda_stream), "mtam_score_topk")
     return idx, sc

@@ -14,8 +14,9 @@ def _topk_oracle(pred, table, k):
     return idx.astype(np.int32), np.take_along_axis(s, idx, axis=1)
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["fp32", "tf32x3"])
 @pytest.mark.parametrize("V,B,D,k,shards", [(5003, 37, 64, 50, 4), (20011, 130, 64, 50, 8), (3709, 9, 128, 10, 3)])
-def test_sharded_score_merge_equals_unsharded(V, B, D, k, shards):
+def test_sharded_score_merge_equals_unsharded(V, B, D, k, shards, mode):
     import torch
     from mtamrecommender_b200 import engine as E
     from mtamrecommender_b200.parallel import shard_rows
@@ -25,13 +26,13 @@ def test_sharded_score_merge_equals_unsharded(V, B, D, k, shards):
     table[V - 1] = table[3]
     pred = rng.standard_normal((B, D)).astype(np.float32)
     dt, dp = torch.from_numpy(table).cuda(), torch.from_numpy(pred).cuda()
-    full_i, full_s = E.score_topk(dp, dt, k)
+    full_i, full_s = E.score_topk(dp, dt, k, gemm_mode=mode)
     S = shard_rows(V, shards)
     li, ls = [], []
     for r in range(shards):
         lo, hi = r * S, min(V, (r + 1) * S)
         shard = dt[lo:hi].clone()              # a separate allocation, like a rank's shard
-        i, s = E.score_topk(dp, shard, k, lo, hi, index_base=lo)
+        i, s = E.score_topk(dp, shard, k, lo, hi, index_base=lo, gemm_mode=mode)
         assert int(i.min()) >= lo and int(i.max()) < hi
         li.append(i); ls.append(s)
     mi, ms = E.merge_topk(torch.stack(li), torch.stack(ls))
@@ -43,6 +44,36 @@ def test_sharded_score_merge_equals_unsharded(V, B, D, k, shards):
     exact_tie_or_gap = np.all((gap > 1e-5) | (gap == 0.0), axis=1)
     assert exact_tie_or_gap.mean() > 0.8
     assert np.array_equal(mi.cpu().numpy()[exact_tie_or_gap], oi[exact_tie_or_gap])
+
+
+@pytest.mark.parametrize("V,B,D,k", [(300, 24, 64, 50), (77, 5, 32, 50), (100003, 300, 64, 50), (40000, 129, 32, 64),
+                                     (1200007, 140, 64, 50)])
+def test_tensor_core_topk_equals_fp32_topk(V, B, D, k):
+    """MTAM_GEMM_TF32X3 scoring (tcgen05 bucket-max filter + fp32 rescoring of the best buckets) returns the same
+    indices AND the same fp32 scores as the exact-fp32 kernel (tf.nn.top_k order: score desc, ties -> lower index)."""
+    import torch
+    from mtamrecommender_b200 import engine as E
+    g = torch.Generator().manual_seed(V + B)
+    table = (torch.rand(V, D, generator=g) - 0.5) * 0.6
+    table[V // 2] = table[1]                  # exact ties: duplicate rows far apart and adjacent
+    table[2] = table[1]
+    table[V - 1] = table[1]
+    pred = torch.randn(B, D, generator=g)
+    pred[0] = 0.0                             # every score equal: the answer is items 0..k-1
+    pred[1] = table[1] * 50                   # the tied rows are this row's best
+    dt, dp = table.cuda(), pred.cuda()
+    ei, es = E.score_topk(dp, dt, k, gemm_mode=0)
+    ti, ts = E.score_topk(dp, dt, k, gemm_mode=1)
+    assert torch.equal(ti[0].cpu(), torch.arange(k, dtype=torch.int32))
+    assert torch.equal(ei, ti), (ei != ti).nonzero()[:5]
+    assert torch.equal(es, ts)
+    # a row range (a shard) and a workspace that forces the pred rows to be processed in chunks of 128
+    lo, hi = V // 5, V - V // 7
+    ei, es = E.score_topk(dp, dt, k, lo, hi, gemm_mode=0)
+    bs = 64 if hi - lo > (1 << 20) else 16
+    small = torch.empty(128 * ((hi - lo + 127) // 128) * (128 // bs) * 4 + 256, dtype=torch.uint8, device="cuda")
+    ti, ts = E.score_topk(dp, dt, k, lo, hi, gemm_mode=1, workspace=small)
+    assert torch.equal(ei, ti) and torch.equal(es, ts)
 
 
 def test_sort_then_sorted_scatter_equals_scatter_add():
