@@ -52,8 +52,42 @@ class ClockSampler:
         self.p = None
         self.path = f"/tmp/mtam_clocks_{os.getpid()}.csv"
         self.gpu_index = gpu_index
+        self.nvml = None
+
+    def _nvml_loop(self):
+        import pynvml as N
+        h = self.nvml
+        bits = {"hw_slowdown": N.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": N.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": N.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
+            try:
+                self._sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self._reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def start(self):
+        # NVML in a sampling thread (a sample every ~5 ms of the timed region); nvidia-smi -lms as the fallback
+        try:
+            import threading
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu_index]) if vis and vis.split(",")[0].isdigit() else self.gpu_index
+            self.nvml = N.nvmlDeviceGetHandleByIndex(idx)
+            self._max = float(N.nvmlDeviceGetMaxClockInfo(self.nvml, N.NVML_CLOCK_SM))
+            self._sm, self._reasons, self._stop = [], set(), threading.Event()
+            self._th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self._th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.f = open(self.path, "w")
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", "--query-gpu=" + self.Q,
@@ -64,6 +98,14 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.nvml is not None:
+            self._stop.set()
+            self._th.join(timeout=2)
+            if self._sm:
+                out.update(sm_mhz=float(np.median(self._sm)), sm_min_mhz=float(min(self._sm)), sm_max_mhz=self._max,
+                           samples=len(self._sm), source="nvml")
+            out["reasons"] = sorted(self._reasons)
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -293,6 +335,7 @@ def run_cuda(args, w):
             roof = roofs[0] if roofs else None
         # ---- the two graded bandwidth kernels at cfg-4 shapes (n = 8192*200 rows, D = 64) ----
         bw = bandwidth_kernels(eng, dev, pk)
+        ev = eval_topk_bench(eng, batches, w, pk) if dp is None else None
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32 (tcgen05 3xTF32 split, fp32 accumulate)" if args.gemm_mode == "tf32x3" else "f32", "data": "synthetic",
@@ -305,7 +348,7 @@ def run_cuda(args, w):
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
                        "ms_per_step": ms_e2e / args.steps},
                "gpu_launches": int(launches), "clocks": clk, "phases_ms": phases, "roofline": roof,
-               "rooflines_top_phases": roofs, "bandwidth_kernels": bw}
+               "rooflines_top_phases": roofs, "bandwidth_kernels": bw, "eval_topk": ev}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(w)
     if world > 1:
@@ -313,6 +356,41 @@ def run_cuda(args, w):
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out), flush=True)
+
+
+def eval_topk_bench(eng, batches, w, pk, k=50, reps=10):
+    """metrics_topK of one batch (base_model.py:188-213): forward + full-catalogue scoring + top-50 + HR/NDCG, and the
+    scoring/top-k part alone.  Tensor work of the scoring = 2*B*D*V useful FLOPs (3x that issued in tf32)."""
+    import torch
+    try:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def t(fn):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ev0.record()
+            for i in range(reps):
+                fn(i)
+            ev1.record()
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1) / reps
+
+        def full(i=0):
+            b = batches[i % len(batches)]
+            idx, _ = eng.eval_topk_device(b, k)
+            return eng.hr_ndcg_device(idx, b.t["target_item_id"])
+        ms_full = t(full)
+        from mtamrecommender_b200 import engine as E
+        pred = torch.randn(w["B"], w["D"], device=eng.params.device)
+        table = eng.param_view("embedding_layer/item")
+        ms_score = t(lambda i=0: E.score_topk(pred, table, k, gemm_mode=eng.cfg.gemm_mode))
+        flops = 2.0 * w["B"] * w["D"] * table.shape[0]
+        return {"k": k, "batch": w["B"], "items": int(table.shape[0]), "ms_forward_score_topk_metrics": ms_full,
+                "seq_per_s": w["B"] / ms_full * 1e3, "ms_score_topk": ms_score,
+                "score_topk_useful_TFLOPs": flops / ms_score / 1e9, "frac_of_bf16_sustained": flops / ms_score / 1e9 / pk["tf_sust"]}
+    except Exception as e:   # report, never hide
+        return {"error": repr(e)}
 
 
 def bandwidth_kernels(eng, dev, pk, n=8192 * 200, D=64, rows=10_000_003):

@@ -259,8 +259,9 @@ long long mtam_launch_count(void);
  * written are global row numbers.
  * gemm_mode (mtam_gemm_mode; mtam_eval_topk uses the handle's): MTAM_GEMM_FP32 computes every score with an fp32 FMA
  * chain; MTAM_GEMM_TF32X3 (num_units 32 / 64) runs the [B,V] product on tcgen05 as a filter (maximum logit per bucket
- * of 16 / 64 items), then rescores the items of the k+14 best buckets per row with the same fp32 FMA chain -- same
- * indices and scores unless more than 14 bucket maxima tie with the k-th within the 3xTF32 rounding error. */
+ * of 16 / 64 items), then rescores the items of the k+14 best buckets per row in fp32 (fixed summation order, so
+ * sharded == unsharded bit for bit) -- exact top-k of those fp32 scores unless more than 14 bucket maxima tie with
+ * the k-th within the 3xTF32 rounding error. */
 int mtam_eval_topk(mtam_handle h, const mtam_batch* batch, int32_t k, int32_t* idx_out, float* score_out,
                    void* stream);
 int mtam_score_topk(int32_t gemm_mode, const float* pred, int32_t B, int32_t D, const float* item_table,

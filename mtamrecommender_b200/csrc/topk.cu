@@ -12,8 +12,10 @@
 // (ce_tc.cu, the softmax forward pipeline with a max epilogue) leaves only the maximum logit of every bucket of
 // 16 / 64 consecutive items; topk_refine_kernel then picks, per pred row, the k+14 buckets with the largest maxima
 // (radix select, ties -> lower bucket), rescores their items with the same fp32 FMA chain as the kernel above and
-// selects the top k under (score desc, index asc).  Scores and indices therefore equal the exact-fp32 path bit for
-// bit unless more than 14 bucket maxima lie within the 3xTF32 rounding error (~1e-6 relative) of the k-th one.
+// selects the top k under (score desc, index asc).  The returned scores are fp32 dot products (not tf32 values), and
+// the selection is exact with respect to them unless more than 14 bucket maxima lie within the 3xTF32 rounding
+// error (~1e-6 relative) of the k-th one.  An item's score is computed in one fixed order, so sharded and unsharded
+// runs agree bit for bit; it can differ from the MTAM_GEMM_FP32 kernel's in the last bit (another summation order).
 #include <limits.h>
 
 #include <algorithm>
@@ -204,11 +206,16 @@ __global__ void __launch_bounds__(256) hr_ndcg_kernel(const int32_t* __restrict_
 // ---- tensor-core filter + exact rescoring -----------------------------------------------------------------
 constexpr int kBucketPad = 14;                       // buckets kept beyond k
 constexpr int kMaxSel = KMAX + kBucketPad;           // 78
-constexpr int kMaxCand = kMaxSel * 64;
+// bucket size: per pred row the maxima cost rows/bs*8 B of traffic and the rescoring (k+14)*bs*4D B, equal near 2 M rows
+constexpr int kSmallBucketMaxRows = 1 << 21;
+constexpr int kMaxGroups = 16384 - 1;                    // groups of 32 buckets per pred row that fit in shared memory
 
-__device__ __forceinline__ uint32_t order_key(float x) {   // monotone float -> uint32
+__device__ __forceinline__ uint32_t order_key(float x) {   // monotone float -> uint32 (every real key > 0)
   const uint32_t b = __float_as_uint(x);
   return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t u) {
+  return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xFFFFFFFFu));
 }
 
 // exclusive scan of one int per thread over a 256-thread block, in thread order; total in *total
@@ -234,156 +241,212 @@ __device__ __forceinline__ int block_excl_scan256(int v, int* warp_tot, int* tot
   return base + inc - v;
 }
 
-// one CTA per pred row: select n_sel buckets by their maxima, rescore their items in fp32, emit the sorted top k
-template <int D>
-__global__ void __launch_bounds__(256) topk_refine_kernel(const float* __restrict__ pred, const float* __restrict__ table,
-                                                          const float* __restrict__ bmax, int ld, int n_buckets, int bs,
-                                                          int n_sel, int row_begin, int row_end, int k,
-                                                          int32_t* __restrict__ idx_out, float* __restrict__ score_out) {
-  __shared__ int hist[256];
-  __shared__ int sel[kMaxSel];
-  __shared__ float cs[kMaxCand];
-  __shared__ int warp_tot[8];
-  __shared__ uint32_t s_prefix;
-  __shared__ int s_need;
-  __shared__ float ws[8];
-  __shared__ int wi[8], wp[8];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x;
-  const float* mrow = bmax + (int64_t)b * ld;
+struct SelectScratch { int hist[256]; uint32_t mn[8], mx[8]; int warp_tot[8]; uint32_t prefix; int need; };
 
-  // ---- 1. key of the n_sel-th largest bucket maximum (MSB-first radix select, 8 bits per pass) ----
-  uint32_t prefix = 0, mask = 0;
-  int need = n_sel;
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    hist[tid] = 0;
-    __syncthreads();
-    for (int i = tid; i < n_buckets; i += 256) {
-      const uint32_t u = order_key(__ldg(mrow + i));
-      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255], 1);
-    }
-    __syncthreads();
-    if (warp == 0) {
-      // bins 255 .. 0 in descending order, 8 per lane: lane l owns bins 255-8l .. 248-8l
-      int c[8], tot = 0;
+// keys[0..n) in shared memory, 256 threads.  Writes to out[0..take) the positions of the `take` largest keys
+// (equal keys: lower position first) in ascending position order.  take <= n.
+// MSB-first radix select, 8 bits per pass, that starts at the highest bit on which two keys differ: the scores
+// of one row share their leading bits, which would otherwise pile every key onto one histogram bin.
+__device__ void select_largest(const uint32_t* __restrict__ keys, int n, int take, int* __restrict__ out, SelectScratch* sc) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t mn = 0xFFFFFFFFu, mx = 0;
+  for (int i = tid; i < n; i += 256) { const uint32_t u = keys[i]; mn = min(mn, u); mx = max(mx, u); }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0) { sc->mn[warp] = mn; sc->mx[warp] = mx; }
+  sc->hist[tid] = 0;
+  __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - (lane * 8 + j)]; tot += c[j]; }
-      int inc = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
+  for (int w = 0; w < 8; ++w) { mn = min(mn, sc->mn[w]); mx = max(mx, sc->mx[w]); }
+  uint32_t T = mx;
+  int need = take;
+  if (mn != mx) {
+    int top = 32 - __clz(mn ^ mx);                         // bits [0, top) are the ones that vary
+    T = top == 32 ? 0u : (mx >> top) << top;               // the shared leading bits
+    bool first = true;
+    while (top > 0) {
+      const int nb = min(8, top), shift = top - nb;
+      const uint32_t dmask = (1u << nb) - 1u;
+      for (int i = tid; i < n; i += 256) {
+        const uint32_t u = keys[i];
+        if (first || (u >> top) == (T >> top)) atomicAdd(&sc->hist[(u >> shift) & dmask], 1);
       }
-      int before = inc - tot;                   // entries in strictly higher bins than this lane's
-      if (before < need && inc >= need) {       // the crossing bin is one of this lane's
+      __syncthreads();
+      if (warp == 0) {
+        // bins 255 .. 0 in descending order, 8 per lane: lane l owns bins 255-8l .. 248-8l
+        int c[8], tot = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (before < need && before + c[j] >= need) {
-            s_prefix = prefix | ((uint32_t)(255 - (lane * 8 + j)) << shift);
-            s_need = need - before;
-            before = need;                      // stop
-          } else if (before < need) {
-            before += c[j];
+        for (int q = 0; q < 8; ++q) { c[q] = sc->hist[255 - (lane * 8 + q)]; tot += c[q]; }
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        int before = inc - tot;                   // keys in strictly higher bins than this lane's
+        if (before < need && inc >= need) {       // the bin holding the need-th largest is one of this lane's
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (before < need && before + c[q] >= need) {
+              sc->prefix = T | ((uint32_t)(255 - (lane * 8 + q)) << shift);
+              sc->need = need - before;
+              before = need;                      // stop
+            } else if (before < need) {
+              before += c[q];
+            }
           }
         }
       }
+      __syncthreads();
+      T = sc->prefix;
+      need = sc->need;
+      sc->hist[tid] = 0;
+      __syncthreads();
+      top = shift;
+      first = false;
     }
-    __syncthreads();
-    prefix = s_prefix;
-    need = s_need;
-    mask |= 255u << shift;
-    __syncthreads();
   }
-  // prefix = key K of the n_sel-th largest maximum; `need` of the buckets equal to K are taken, lowest index first
-
-  // ---- 2. ordered compaction of the selected bucket ids (thread t owns a contiguous index range) ----
-  {
-    const int seg = (n_buckets + 255) / 256;
-    const int i0 = min(n_buckets, tid * seg), i1 = min(n_buckets, i0 + seg);
-    int ngt = 0, neq = 0;
-    for (int i = i0; i < i1; ++i) {
-      const uint32_t u = order_key(__ldg(mrow + i));
-      ngt += u > prefix;
-      neq += u == prefix;
-    }
-    int tot_gt, tot_eq;
-    int ogt = block_excl_scan256(ngt, warp_tot, &tot_gt);
-    int oeq = block_excl_scan256(neq, warp_tot, &tot_eq);
-    for (int i = i0; i < i1; ++i) {
-      const uint32_t u = order_key(__ldg(mrow + i));
-      if (u > prefix) sel[ogt++] = i;
-      else if (u == prefix) {
-        if (oeq < need) sel[tot_gt + oeq] = i;
-        ++oeq;
-      }
+  // T = the take-th largest key; every key above it is taken, and the first `need` equal to it
+  const int seg = (n + 255) / 256;
+  const int i0 = min(n, tid * seg), i1 = min(n, i0 + seg);
+  int ngt = 0, neq = 0;
+  for (int i = i0; i < i1; ++i) { const uint32_t u = keys[i]; ngt += u > T; neq += u == T; }
+  int tot_gt, tot_eq;
+  const int ogt = block_excl_scan256(ngt, sc->warp_tot, &tot_gt);
+  int oeq = block_excl_scan256(neq, sc->warp_tot, &tot_eq);
+  // ascending position order: an element's slot = number of taken elements before it
+  int slot = ogt + min(oeq, need);
+  for (int i = i0; i < i1; ++i) {
+    const uint32_t u = keys[i];
+    if (u > T) out[slot++] = i;
+    else if (u == T) {
+      if (oeq < need) out[slot++] = i;
+      ++oeq;
     }
   }
   __syncthreads();
+}
 
-  // ---- 3. exact fp32 scores of the selected buckets' items: the FMA chain of score_topk_kernel ----
-  const int n_cand = n_sel * bs;
-  {
-    float q[D];
-#pragma unroll
-    for (int c = 0; c < D; c += 4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(pred + (int64_t)b * D + c));
-      q[c] = v.x; q[c + 1] = v.y; q[c + 2] = v.z; q[c + 3] = v.w;
+// one CTA per pred row: pick n_sel buckets by their maxima (two levels: groups of 32 buckets first), rescore their
+// items in fp32, emit the sorted top k
+template <int D>
+__global__ void __launch_bounds__(256, 8) topk_refine_kernel(const float* __restrict__ pred, const float* __restrict__ table,
+                                                          const float* __restrict__ bmax, int ld, int n_buckets, int log2bs,
+                                                          int n_sel, int row_begin, int row_end, int k,
+                                                          int32_t* __restrict__ idx_out, float* __restrict__ score_out) {
+  extern __shared__ __align__(16) uint32_t dsm[];
+  __shared__ SelectScratch sc;
+  static_assert(D == 32 || D == 64, "8 lanes x 1 or 2 float4 per item");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const int bs = 1 << log2bs;
+  const int G = (n_buckets + 31) >> 5;             // groups of 32 buckets
+  const int n_grp = min(G, n_sel);                 // groups kept
+  const int n_cand = n_sel << log2bs;
+  float* qs = reinterpret_cast<float*>(dsm);       // [D] pred row
+  uint32_t* sup = dsm + D;                         // [G] group maxima (keys)
+  uint32_t* bk = sup + G;                          // [n_grp*32] bucket maxima of the kept groups (keys)
+  uint32_t* ck = bk + n_grp * 32;                  // [n_cand] candidate scores (keys)
+  int* gsel = reinterpret_cast<int*>(ck + n_cand); // [n_grp] kept groups, ascending
+  int* sel = gsel + n_grp;                         // [n_sel] kept buckets, ascending
+  int* win = sel + n_sel;                          // [k] winning candidates, ascending item index
+  const float* mrow = bmax + (int64_t)b * ld;
+
+  if (tid < D / 4)
+    reinterpret_cast<float4*>(qs)[tid] = __ldg(reinterpret_cast<const float4*>(pred + (int64_t)b * D) + tid);
+  // ---- 1. group maxima: a lane reads 4 consecutive bucket maxima, 8 lanes make a group of 32 ----
+  for (int g0 = warp * 4; g0 < G; g0 += 32) {
+    const int g = g0 + (lane >> 3), i = g * 32 + (lane & 7) * 4;
+    float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (i + 3 < n_buckets) {
+      v = __ldg(reinterpret_cast<const float4*>(mrow + i));
+    } else if (i < n_buckets) {                      // the row's last, partial quad
+      v.x = __ldg(mrow + i);
+      if (i + 1 < n_buckets) v.y = __ldg(mrow + i + 1);
+      if (i + 2 < n_buckets) v.z = __ldg(mrow + i + 2);
     }
-    for (int c = tid; c < n_cand; c += 256) {
-      const int item = row_begin + sel[c / bs] * bs + c % bs;
-      float acc = -INFINITY;
-      if (item < row_end) {
-        const float4* x = reinterpret_cast<const float4*>(table + (int64_t)item * D);
-        acc = 0.f;
+    float m = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+    if ((lane & 7) == 0 && g < G) sup[g] = order_key(m);
+  }
+  __syncthreads();
+  // ---- 2. the n_grp best groups contain the n_sel best buckets (a group's key >= each of its buckets') ----
+  select_largest(sup, G, n_grp, gsel, &sc);
+  for (int j = warp; j < n_grp; j += 8) {
+    const int i = gsel[j] * 32 + lane;
+    bk[j * 32 + lane] = i < n_buckets ? order_key(__ldg(mrow + i)) : 0u;
+  }
+  __syncthreads();
+  // ---- 3. the n_sel best buckets (ties -> lower bucket: positions in bk ascend with the bucket id) ----
+  select_largest(bk, n_grp * 32, n_sel, sel, &sc);
+  if (tid < n_sel) {
+    const int p = sel[tid];
+    sel[tid] = gsel[p >> 5] * 32 + (p & 31);
+  }
+  __syncthreads();
+  // ---- 4. fp32 scores of those buckets' items: 8 lanes per item (each a coalesced float4 of either half of the row:
+  //         two 4-term FMA chains, their sum, then a butterfly over the 8 lanes; D = 32: one chain) -- a fixed order,
+  //         so an item's score does not depend on the batch or on the row range ----
+  {
+    constexpr int NQ = D / 32;                     // float4 per lane
+    const int sub = lane & 7;
+    const int* __restrict__ selr = sel;
+    uint32_t* __restrict__ ckr = ck;
+    float4 q[NQ];
 #pragma unroll
-        for (int j = 0; j < D / 4; ++j) {
-          const float4 v = __ldg(x + j);
-          acc = fmaf(q[4 * j], v.x, acc);
-          acc = fmaf(q[4 * j + 1], v.y, acc);
-          acc = fmaf(q[4 * j + 2], v.z, acc);
-          acc = fmaf(q[4 * j + 3], v.w, acc);
-        }
+    for (int h = 0; h < NQ; ++h) q[h] = reinterpret_cast<const float4*>(qs)[sub + 8 * h];
+#pragma unroll 2
+    for (int c0 = warp * 4; c0 < n_cand; c0 += 32) {
+      const int c = c0 + (lane >> 3);
+      const int item = row_begin + (selr[c >> log2bs] << log2bs) + (c & (bs - 1));
+      const bool valid = item < row_end;
+      const float4* x = reinterpret_cast<const float4*>(table + (int64_t)item * D) + sub;
+      float acc = 0.f;
+#pragma unroll
+      for (int h = 0; h < NQ; ++h) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) v = __ldg(x + 8 * h);
+        float a = q[h].x * v.x;
+        a = fmaf(q[h].y, v.y, a);
+        a = fmaf(q[h].z, v.z, a);
+        a = fmaf(q[h].w, v.w, a);
+        acc = h == 0 ? a : acc + a;
       }
-      cs[c] = acc;
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (sub == 0) ckr[c] = valid ? order_key(acc) : 0u;    // past the row range: below every real score
     }
   }
   __syncthreads();
-
-  // ---- 4. k rounds of arg-best under (score desc, item index asc) ----
-  for (int r = 0; r < k; ++r) {
-    float bsc = -INFINITY;
-    int bi = INT_MAX, bp = -1;
-    for (int c = tid; c < n_cand; c += 256) {
-      const float s = cs[c];
-      const int item = row_begin + sel[c / bs] * bs + c % bs;
-      if (item < row_end && s == s && (bp < 0 || better(s, item, bsc, bi))) { bsc = s; bi = item; bp = c; }
+  // ---- 5. the k best candidates (ties -> lower item index), then their order by rank counting ----
+  select_largest(ck, n_cand, k, win, &sc);
+  if (tid < k) {
+    const int p = win[tid];
+    const uint32_t u = ck[p];
+    int rank = 0;
+    for (int j = 0; j < k; ++j) {
+      const uint32_t o = ck[win[j]];
+      rank += (o > u) || (o == u && j < tid);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float s2 = __shfl_xor_sync(0xffffffffu, bsc, o);
-      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o), p2 = __shfl_xor_sync(0xffffffffu, bp, o);
-      if (p2 >= 0 && (bp < 0 || better(s2, i2, bsc, bi))) { bsc = s2; bi = i2; bp = p2; }
-    }
-    if (lane == 0) { ws[warp] = bsc; wi[warp] = bi; wp[warp] = bp; }
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < 8; ++w)
-        if (wp[w] >= 0 && (bp < 0 || better(ws[w], wi[w], bsc, bi))) { bsc = ws[w]; bi = wi[w]; bp = wp[w]; }
-      idx_out[(int64_t)b * k + r] = bi;
-      if (score_out) score_out[(int64_t)b * k + r] = bsc;
-      if (bp >= 0) cs[bp] = __int_as_float(0x7fc00000);   // taken (NaN: skipped by the s == s test above)
-    }
-    __syncthreads();
+    idx_out[(int64_t)b * k + rank] = row_begin + (sel[p >> log2bs] << log2bs) + (p & (bs - 1));
+    if (score_out) score_out[(int64_t)b * k + rank] = key_value(u);
   }
+}
+
+static size_t refine_smem_bytes(int D, int n_buckets, int bs, int n_sel, int k) {
+  const int G = cdiv(n_buckets, 32), n_grp = std::min(G, n_sel);
+  return (size_t)(D + G + n_grp * 32 + n_sel * bs + n_grp + n_sel + k) * sizeof(uint32_t);
 }
 
 // geometry of the tensor-core path for `rows` catalogue rows
 struct TcTopkPlan { int bs, ld, n_buckets, n_sel, chunk_rows; };
 static TcTopkPlan tc_topk_plan(int B, int rows, int k, size_t ws_bytes) {
   TcTopkPlan p;
-  p.bs = rows > (1 << 20) ? 64 : 16;
-  p.ld = cdiv(rows, 128) * (128 / p.bs);
+  p.bs = rows > kSmallBucketMaxRows ? 64 : 16;
+  p.ld = cdiv(cdiv(rows, 128) * (128 / p.bs), 8) * 8;
   p.n_buckets = cdiv(rows, p.bs);
   p.n_sel = std::min(p.n_buckets, k + kBucketPad);
   const int64_t fit = (int64_t)(ws_bytes / sizeof(float)) / p.ld;
@@ -392,8 +455,8 @@ static TcTopkPlan tc_topk_plan(int B, int rows, int k, size_t ws_bytes) {
   return p;
 }
 static size_t tc_topk_workspace_bytes(int B, int rows) {
-  const int bs = rows > (1 << 20) ? 64 : 16;
-  const size_t ld = (size_t)cdiv(rows, 128) * (128 / bs);
+  const int bs = rows > kSmallBucketMaxRows ? 64 : 16;
+  const size_t ld = (size_t)cdiv(cdiv(rows, 128) * (128 / bs), 8) * 8;
   // bucket maxima of up to B pred rows; beyond 1 GiB the pred rows are processed in chunks of >= 128
   const size_t cap_rows = std::max<size_t>(128, ((size_t)1 << 30) / (ld * sizeof(float)) / 128 * 128);
   return std::min<size_t>((size_t)B, cap_rows) * ld * sizeof(float) + 256;
@@ -405,12 +468,17 @@ static int score_topk_tc_launch(const float* pred, int B, const float* table, in
   const int rows = row_end - row_begin;
   const TcTopkPlan p = tc_topk_plan(B, rows, k, ws_bytes);
   if (p.chunk_rows < std::min(B, 128)) return set_error(MTAM_ERR_WORKSPACE, "score_topk (tensor-core path): workspace too small");
+  if (cdiv(p.n_buckets, 32) > kMaxGroups)
+    return set_error(MTAM_ERR_INVALID, "score_topk (tensor-core path): %d rows exceed the supported range", rows);
+  const size_t smem = refine_smem_bytes(D, p.n_buckets, p.bs, p.n_sel, k);
+  MTAM_CUDA_CHECK(cudaFuncSetAttribute(topk_refine_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
   float* bmax = (float*)ws;
   for (int b0 = 0; b0 < B; b0 += p.chunk_rows) {
     const int nb = std::min(p.chunk_rows, B - b0);
     MTAM_TRY(ce_bucket_max_tc(D, pred + (int64_t)b0 * D, nb, table + (int64_t)row_begin * D, rows, p.bs, bmax, p.ld, st));
-    topk_refine_kernel<D><<<nb, 256, 0, st>>>(pred + (int64_t)b0 * D, table, bmax, p.ld, p.n_buckets, p.bs, p.n_sel, row_begin,
-                                              row_end, k, idx_out + (int64_t)b0 * k, score_out ? score_out + (int64_t)b0 * k : nullptr);
+    topk_refine_kernel<D><<<nb, 256, smem, st>>>(pred + (int64_t)b0 * D, table, bmax, p.ld, p.n_buckets, p.bs == 64 ? 6 : 4, p.n_sel,
+                                                 row_begin, row_end, k, idx_out + (int64_t)b0 * k,
+                                                 score_out ? score_out + (int64_t)b0 * k : nullptr);
     MTAM_LAUNCH_CHECK();
   }
   return 0;
