@@ -41,6 +41,9 @@ enum { CE_FWD = 0, CE_DP = 1, CE_DT = 2, CE_BMAX = 3 };
 // 128-column S buffers; a 128-wide MMA keeps the tensor pipe ahead of the issuing thread.
 __host__ __device__ constexpr int ce_bx(int mode) { return (mode == CE_FWD || mode == CE_BMAX) ? 128 : 64; }
 __host__ __device__ constexpr bool ce_pv(int mode) { return mode == CE_DP || mode == CE_DT; }
+// raw fp32 staging slots (64 X rows each) filled by bulk copies.  CE_DT keeps to 2 (161 KB of shared memory in all) so
+// that one of its CTAs fits on an SM beside a T-GRU / hop CTA of the backward chain it overlaps with (model.cu)
+__host__ __device__ constexpr int ce_nsg(int mode) { return mode == CE_DT ? 2 : (mode == CE_DP ? 3 : 4); }
 
 // 2^x on the MUFU pipe (ex2.approx: 2 ulp; -inf -> 0)
 __device__ __forceinline__ float ex2(float x) {
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
   constexpr bool PV = ce_pv(MODE);
   constexpr int NST = 2;                          // operand stages in shared memory
   constexpr int STAGE = (PV ? 4 : 2) * KC * XT;   // floats per operand stage: K-major hi, lo (, MN-major hi, lo)
-  constexpr int NSG = PV ? 3 : 4;                 // raw fp32 staging slots (64 X rows each) filled by bulk copies
+  constexpr int NSG = ce_nsg(MODE);
   constexpr int SLOT = 64 * D;                    // floats per staging slot
   constexpr uint32_t SW = BX;                     // S buffer width in TMEM columns
   extern __shared__ uint8_t smem_raw[];
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
 template <int D, int MODE>
 int ce_tc_launch(dim3 grid, const CeTcArgs& a, cudaStream_t st) {
   constexpr int KC = D / 32;
-  const size_t smem = (size_t)(2 * (ce_pv(MODE) ? 4 : 2) * KC * ce_bx(MODE) * 32 + (ce_pv(MODE) ? 3 : 4) * 64 * D) * sizeof(float) + 1024;
+  const size_t smem = (size_t)(2 * (ce_pv(MODE) ? 4 : 2) * KC * ce_bx(MODE) * 32 + ce_nsg(MODE) * 64 * D) * sizeof(float) + 1024;
   MTAM_CUDA_CHECK(cudaFuncSetAttribute(ce_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ce_tc_kernel<D, MODE><<<grid, kThreads, smem, st>>>(a);
   MTAM_LAUNCH_CHECK();
@@ -522,8 +525,9 @@ int ce_forward_tc(int D, const float* pred, const float* table, const int32_t* t
   return ce_finalize(a.ms_partial, 2 * G, B, tlogit, lse, loss_origin, block_partial, n_partial, st);
 }
 
+// parts: 1 = dpred only, 2 = the dense item-table gradient only (independent of part 1; may run on another stream), 3 = both
 int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
-                   float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st) {
+                   float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st, int parts) {
   CeTcArgs a{};
   a.pred = pred; a.table = table; a.target = target; a.lse = lse; a.B = B; a.V = V; a.inv_batch = inv_batch;
   int G;
@@ -532,15 +536,16 @@ int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* 
   a.dTable = dTable;
   dim3 grid_dp(G, cdiv(B, QM)), grid_dt(cdiv(V, QM));
   if (D == 64) {
-    MTAM_TRY((ce_tc_launch<64, CE_DP>(grid_dp, a, st)));
-    MTAM_TRY((ce_tc_launch<64, CE_DT>(grid_dt, a, st)));
+    if (parts & 1) MTAM_TRY((ce_tc_launch<64, CE_DP>(grid_dp, a, st)));
+    if (parts & 2) MTAM_TRY((ce_tc_launch<64, CE_DT>(grid_dt, a, st)));
   } else if (D == 32) {
-    MTAM_TRY((ce_tc_launch<32, CE_DP>(grid_dp, a, st)));
-    MTAM_TRY((ce_tc_launch<32, CE_DT>(grid_dt, a, st)));
+    if (parts & 1) MTAM_TRY((ce_tc_launch<32, CE_DP>(grid_dp, a, st)));
+    if (parts & 2) MTAM_TRY((ce_tc_launch<32, CE_DT>(grid_dt, a, st)));
   } else {
     return set_error(-1, "tensor-core softmax CE: num_units=%d not supported (32, 64)", D);
   }
-  return ce_reduce_partials(a.dpred_partial, G, (int64_t)B * D, dpred, st);
+  if (parts & 1) return ce_reduce_partials(a.dpred_partial, G, (int64_t)B * D, dpred, st);
+  return 0;
 }
 
 // Top-k filter pass (topk.cu): bmax[b][j] = max over the items of bucket j of <pred[b], table[j*bs + .]>, buckets of

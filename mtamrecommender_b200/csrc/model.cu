@@ -69,6 +69,8 @@ struct mtam_model {
   bool prof = false;
   cudaStream_t side = nullptr;       // index sorts run here, concurrently with forward/backward
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side2 = nullptr;      // tensor-core CE: the dense item-table gradient runs here, beside the backward chain
+  cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaEvent_t ev_ce_done = nullptr;  // caller-owned: recorded once the dense item-table gradient is complete
   bool sort_pending = false;
   const int32_t *sk[4] = {}, *sp[4] = {};   // sorted keys / permutations: item, category, position, user
@@ -419,9 +421,24 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   eacc.accumulate = 1;
   // softmax CE: dense item-table gradient straight into the arena, dpred
   phase(h, MTAM_PH_CE_BWD, st);
-  MTAM_TRY(ce_backward(c.gemm_mode, D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
-                       w.ce_ws, G + l.item, w.dpred, st));
-  if (h->ev_ce_done) MTAM_CUDA_CHECK(cudaEventRecord(h->ev_ce_done, st));
+  // The dense item-table gradient (dT = G^T pred, a full-machine tensor-core pass) feeds only the norm and Adam; the
+  // chain behind dpred (hops, T-GRU, embedding) is latency-bound kernels on a fraction of the SMs.  Run dT beside it.
+  // (Not while profiling: the per-phase times would no longer add up.)
+  const bool dt_aside = c.gemm_mode == MTAM_GEMM_TF32X3 && ce_tc_supported(D) && !h->prof;
+  if (dt_aside) {
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_fork2, st));
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(h->side2, h->ev_fork2, 0));
+    MTAM_TRY(ce_backward_tc(D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
+                            w.ce_ws, G + l.item, w.dpred, h->side2, 2));
+    if (h->ev_ce_done) MTAM_CUDA_CHECK(cudaEventRecord(h->ev_ce_done, h->side2));
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_join2, h->side2));
+    MTAM_TRY(ce_backward_tc(D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
+                            w.ce_ws, G + l.item, w.dpred, st, 1));
+  } else {
+    MTAM_TRY(ce_backward(c.gemm_mode, D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
+                         w.ce_ws, G + l.item, w.dpred, st));
+    if (h->ev_ce_done) MTAM_CUDA_CHECK(cudaEventRecord(h->ev_ce_done, st));
+  }
   // hops
   phase(h, MTAM_PH_HOP_BWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.dX, 0, (size_t)T * D * sizeof(float), st));
@@ -466,6 +483,7 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   MTAM_TRY(gemm(h, 0, 1, (int)T, D, 3 * D, w.dGX, 3 * D, P + l.Wgru, 3 * D, w.dX, D, eacc, st));
   phase(h, MTAM_PH_EMBED_BWD, st);
   MTAM_TRY(embed_backward(h, bt, 1, norm_sq_sparse, st));
+  if (dt_aside) MTAM_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join2, 0));
   phase(h, MTAM_PH_DENSE_NORM, st);
   return 0;
 }
@@ -655,7 +673,10 @@ int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam
   memset(&h->last_batch, 0, sizeof(h->last_batch));
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, 0) != cudaSuccess ||   /* lowest priority */
+      cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
     int e = set_error(MTAM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     mtam_destroy(h);
     return e;
@@ -670,6 +691,9 @@ int mtam_destroy(mtam_handle h) {
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side2) cudaStreamDestroy(h->side2);
+    if (h->ev_fork2) cudaEventDestroy(h->ev_fork2);
+    if (h->ev_join2) cudaEventDestroy(h->ev_join2);
     for (int i = 0; i <= MTAM_PHASE_COUNT; ++i)
       if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   }

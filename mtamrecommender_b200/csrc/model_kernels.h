@@ -111,7 +111,7 @@ size_t ce_ms_region_bytes(int B, int V);
 int ce_forward_tc(int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
                   float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st);
 int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
-                   float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st);
+                   float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st, int parts = 3);
 
 // top-k filter pass: maxima of the logits over buckets of bs (16 / 64) consecutive table rows, [B][ld]
 int ce_bucket_max_tc(int D, const float* pred, int B, const float* table, int V, int bs, float* bmax, int ld,

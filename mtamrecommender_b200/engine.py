@@ -315,7 +315,9 @@ class Engine:
         `train_step_graph` then only advances the host-side Adam state and replays it."""
         batch = DeviceBatch({k: v[:B] for k, v in self._dev.items()}, B)
         t0 = self.adam_step()
-        s = torch.cuda.Stream(self.device)
+        # high priority: the captured main chain is scheduled ahead of the library's side streams (the softmax
+        # dTable pass running beside the backward chain fills whatever the chain leaves free)
+        s = torch.cuda.Stream(self.device, priority=-1)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             self.train_step_device(batch, 0.0)       # warm-up outside capture: sets func attributes
