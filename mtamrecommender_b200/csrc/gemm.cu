@@ -146,21 +146,42 @@ __global__ void __launch_bounds__(GT) gemm_f32_kernel(int M, int N, int K, const
   }
 }
 
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, int M, int N, float* __restrict__ C,
-                                     int ldc, EpiDev epi, int64_t sC) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)M * N) return;
-  partial += (int64_t)blockIdx.y * S * M * N;   // batched: one problem per blockIdx.y
+// A block owns kRedCols consecutive outputs; its 8 warps take the partials z = w, w+8, ... (4 loads in flight each) and
+// warp 0 adds the 8 slice sums in slice order: S/8 dependent steps instead of S, and still one fixed order.
+constexpr int kRedCols = 32;
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int S, int M, int N,
+                                                            float* __restrict__ C, int ldc, EpiDev epi, int64_t sC) {
+  __shared__ float red[8][kRedCols];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t MN = (int64_t)M * N;
+  const int64_t i = (int64_t)blockIdx.x * kRedCols + tx;
+  partial += (int64_t)blockIdx.y * S * MN;      // batched: one problem per blockIdx.y
   C += (int64_t)blockIdx.y * sC;
-  int m = (int)(i / N), n = (int)(i % N);
-  float s = 0.f;
-  for (int z = 0; z < S; ++z) s += partial[(int64_t)z * M * N + i];  // fixed order: deterministic
-  C[(int64_t)m * ldc + n] = apply_epi(s, m, n, epi, C, ldc);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < MN) {
+    int z = ty;
+    for (; z + 24 < S; z += 32) {
+      s0 += partial[(int64_t)z * MN + i];
+      s1 += partial[(int64_t)(z + 8) * MN + i];
+      s2 += partial[(int64_t)(z + 16) * MN + i];
+      s3 += partial[(int64_t)(z + 24) * MN + i];
+    }
+    for (; z < S; z += 8) s0 += partial[(int64_t)z * MN + i];
+  }
+  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && i < MN) {
+    float s = red[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += red[w][tx];
+    const int m = (int)(i / N), n = (int)(i % N);
+    C[(int64_t)m * ldc + n] = apply_epi(s, m, n, epi, C, ldc);
+  }
 }
 
 int splitk_reduce(const float* partial, int S, int M, int N, float* C, int ldc, const EpiDev& epi, cudaStream_t st) {
   int64_t tot = (int64_t)M * N;
-  splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, st>>>(partial, S, M, N, C, ldc, epi, 0);
+  splitk_reduce_kernel<<<cdiv(tot, kRedCols), 256, 0, st>>>(partial, S, M, N, C, ldc, epi, 0);
   MTAM_LAUNCH_CHECK();
   return 0;
 }
@@ -216,7 +237,7 @@ int gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int ld
   MTAM_LAUNCH_CHECK();
   if (S > 1) {
     int64_t tot = (int64_t)M * N;
-    splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, st>>>(partial, S, M, N, C, ldc, epi, 0);
+    splitk_reduce_kernel<<<cdiv(tot, kRedCols), 256, 0, st>>>(partial, S, M, N, C, ldc, epi, 0);
     MTAM_LAUNCH_CHECK();
   }
   return 0;
@@ -249,7 +270,7 @@ int gemm_atb_batched_f32(int P, int M, int N, int K, const float* A, int lda, in
   dim3 grid(cdiv(N, GN), cdiv(M, GM), P * S);
   DISPATCH_V(1, 0);
   MTAM_LAUNCH_CHECK();
-  dim3 rgrid(cdiv((int64_t)M * N, 256), P);
+  dim3 rgrid(cdiv((int64_t)M * N, kRedCols), P);
   splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(partial, S, M, N, C, ldc, epi, sC);
   MTAM_LAUNCH_CHECK();
   return 0;
@@ -290,13 +311,31 @@ __global__ void __launch_bounds__(128) colsum_partial_kernel(const float* __rest
   }
   partial[(int64_t)blockIdx.y * N + n] = (s0 + s1) + (s2 + s3);
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int P, int N, float* __restrict__ out,
-                                    int accumulate) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float s = 0.f;
-  for (int p = 0; p < P; ++p) s += partial[(int64_t)p * N + n];
-  out[n] = accumulate ? out[n] + s : s;
+// 32 columns per block, the 8 warps take the row blocks p = w, w+8, ...; warp 0 adds the slice sums in slice order
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int P, int N,
+                                                           float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (n < N) {
+    int p = ty;
+    for (; p + 24 < P; p += 32) {
+      s0 += partial[(int64_t)p * N + n];
+      s1 += partial[(int64_t)(p + 8) * N + n];
+      s2 += partial[(int64_t)(p + 16) * N + n];
+      s3 += partial[(int64_t)(p + 24) * N + n];
+    }
+    for (; p < P; p += 8) s0 += partial[(int64_t)p * N + n];
+  }
+  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float s = red[0][tx];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += red[w][tx];
+    out[n] = accumulate ? out[n] + s : s;
+  }
 }
 size_t colsum_workspace_bytes(int M, int N) {
   return (size_t)cdiv(std::max(M, 1), colsum_rows_per_block(M, N)) * N * sizeof(float) + 256;
@@ -310,7 +349,7 @@ int colsum_f32(const float* A, int lda, const float* Bmul, int ldb, int M, int N
   if (ws_bytes < (size_t)P * N * sizeof(float)) return set_error(MTAM_ERR_WORKSPACE, "colsum workspace too small");
   dim3 grid(cdiv(N, 128), P);
   colsum_partial_kernel<<<grid, 128, 0, st>>>(A, lda, Bmul, ldb, M, N, rpb, (float*)ws);
-  colsum_final_kernel<<<cdiv(N, 128), 128, 0, st>>>((const float*)ws, P, N, out, accumulate);
+  colsum_final_kernel<<<cdiv(N, 32), 256, 0, st>>>((const float*)ws, P, N, out, accumulate);
   MTAM_LAUNCHES(1);
   MTAM_LAUNCH_CHECK();
   return 0;
