@@ -355,4 +355,63 @@ int colsum_f32(const float* A, int lda, const float* Bmul, int ldb, int M, int N
   return 0;
 }
 
+// ---- several column sums over the same M rows in ONE launch (the per-sequence bias / gain / gate gradients: M = batch,
+// a few hundred columns each -- as separate partial+final launch pairs they cost more in launches than in work) ----
+// A 1024-thread block owns 32 columns of one job; its 32 warps take the rows m = w, w+32, ... (4 loads in flight), and
+// warp 0 adds the 32 slice sums in slice order.
+__global__ void __launch_bounds__(1024) colsum_multi_kernel(const ColsumBatch jb, int M) {
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int j = 0;
+#pragma unroll
+  for (int q = 1; q < kColsumMaxJobs; ++q)
+    if (q < jb.n_jobs && (int)blockIdx.x >= jb.first_block[q]) j = q;
+  const ColsumJob job = jb.job[j];
+  const int n = ((int)blockIdx.x - jb.first_block[j]) * 32 + tx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (n < job.N) {
+    const float* A = job.A + n;
+    int m = ty;
+    if (job.Bmul) {
+      const float* Bm = job.Bmul + n;
+      for (; m + 96 < M; m += 128) {
+        s0 = fmaf(A[(int64_t)m * job.lda], Bm[(int64_t)m * job.ldb], s0);
+        s1 = fmaf(A[(int64_t)(m + 32) * job.lda], Bm[(int64_t)(m + 32) * job.ldb], s1);
+        s2 = fmaf(A[(int64_t)(m + 64) * job.lda], Bm[(int64_t)(m + 64) * job.ldb], s2);
+        s3 = fmaf(A[(int64_t)(m + 96) * job.lda], Bm[(int64_t)(m + 96) * job.ldb], s3);
+      }
+      for (; m < M; m += 32) s0 = fmaf(A[(int64_t)m * job.lda], Bm[(int64_t)m * job.ldb], s0);
+    } else {
+      for (; m + 96 < M; m += 128) {
+        s0 += A[(int64_t)m * job.lda];
+        s1 += A[(int64_t)(m + 32) * job.lda];
+        s2 += A[(int64_t)(m + 64) * job.lda];
+        s3 += A[(int64_t)(m + 96) * job.lda];
+      }
+      for (; m < M; m += 32) s0 += A[(int64_t)m * job.lda];
+    }
+  }
+  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && n < job.N) {
+    float s = red[0][tx];
+#pragma unroll
+    for (int w = 1; w < 32; ++w) s += red[w][tx];
+    job.out[n] = s;
+  }
+}
+int colsum_multi_f32(ColsumBatch jb, int M, cudaStream_t st) {
+  if (jb.n_jobs <= 0) return 0;
+  if (jb.n_jobs > kColsumMaxJobs) return set_error(MTAM_ERR_INVALID, "colsum_multi: %d jobs > %d", jb.n_jobs, kColsumMaxJobs);
+  int blocks = 0;
+  for (int j = 0; j < jb.n_jobs; ++j) {
+    jb.first_block[j] = blocks;
+    blocks += cdiv(std::max(jb.job[j].N, 0), 32);
+  }
+  if (blocks == 0) return 0;
+  colsum_multi_kernel<<<blocks, 1024, 0, st>>>(jb, M);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace mtam

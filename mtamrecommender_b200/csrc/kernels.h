@@ -60,6 +60,17 @@ int colsum_f32(const float* A, int lda, const float* Bmul, int ldb, int M, int N
                void* ws, size_t ws_bytes, cudaStream_t st);
 size_t colsum_workspace_bytes(int M, int N);
 
+// up to kColsumMaxJobs column sums (optionally of A*Bmul) over the same M rows in one launch
+constexpr int kColsumMaxJobs = 8;
+struct ColsumJob {
+  const float* A; int lda;
+  const float* Bmul; int ldb;
+  int N;
+  float* out;
+};
+struct ColsumBatch { ColsumJob job[kColsumMaxJobs]; int first_block[kColsumMaxJobs]; int n_jobs; };
+int colsum_multi_f32(ColsumBatch jobs, int M, cudaStream_t st);
+
 // ---- topk.cu --------------------------------------------------------------------------------
 size_t score_topk_workspace_bytes(int B, int rows, int k);
 int score_topk(int mode, const float* pred, int B, int D, const float* table, int row_begin, int row_end, int k, int32_t* idx_out,

@@ -454,12 +454,17 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   MTAM_TRY(hop_backward(a, g, st));
   // hop parameter gradients
   phase(h, MTAM_PH_HOP_PARAM_GRADS, st);
-  MTAM_TRY(colsum(h, w.dpred, D, nullptr, 0, B, D, G + l.lnfb, st));
-  MTAM_TRY(colsum(h, w.dpred, D, w.XHF, D, B, D, G + l.lnfg, st));
-  MTAM_TRY(colsum(h, w.DOUT, N * D, nullptr, 0, B, N * D, G + l.lnb, st));
-  MTAM_TRY(colsum(h, w.DOUT, N * D, w.XH, N * D, B, N * D, G + l.lng, st));
-  MTAM_TRY(colsum(h, w.DQP, N * D, nullptr, 0, B, N * D, G + l.bq, st));
-  MTAM_TRY(colsum(h, w.GB, 5 * N * L, nullptr, 0, B, 5 * N * L, G + l.gate, st));
+  {  // the six per-sequence column sums (LN gains / biases, query bias, gate vectors) in one launch
+    ColsumBatch cb{};
+    cb.job[0] = ColsumJob{w.dpred, D, nullptr, 0, D, G + l.lnfb};
+    cb.job[1] = ColsumJob{w.dpred, D, w.XHF, D, D, G + l.lnfg};
+    cb.job[2] = ColsumJob{w.DOUT, N * D, nullptr, 0, N * D, G + l.lnb};
+    cb.job[3] = ColsumJob{w.DOUT, N * D, w.XH, N * D, N * D, G + l.lng};
+    cb.job[4] = ColsumJob{w.DQP, N * D, nullptr, 0, N * D, G + l.bq};
+    cb.job[5] = ColsumJob{w.GB, 5 * N * L, nullptr, 0, 5 * N * L, G + l.gate};
+    cb.n_jobs = 6;
+    MTAM_TRY(colsum_multi_f32(cb, B, st));
+  }
   // dWq_i = Qin_i^T dQpre_i, dWt_i = Qin_i^T dQt_i: the N hops of each in one batched split-K launch
   MTAM_TRY(gemm_atb_batched_f32(N, D, D, B, w.Qin, D, (int64_t)B * D, w.DQP, N * D, D, G + l.Wq, D, (int64_t)D * D,
                                 w.gemm_ws, w.gemm_ws_bytes, st));
