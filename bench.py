@@ -287,6 +287,17 @@ def run_cuda(args, w):
     for i in range(2):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
+    # the same end-to-end step fed from the columnar record store (DataHandle/record_store.py): mtam_pack_records pads
+    # the batch straight into the pinned feed buffers (make_feed_dic_new of the reference, Behavior_...py:146-192)
+    ms_rec = None
+    if dp is None:
+        from mtamrecommender_b200.DataHandle.record_store import PackedRecords
+        from mtamrecommender_b200.synth import feed_to_records
+        store = PackedRecords.from_records([r for f in feeds for r in feed_to_records(f)])
+        views = [store[i * w["B"]:(i + 1) * w["B"]] for i in range(nb)]
+        for i in range(2):
+            eng.train_step_records(views[i % nb], LR)
+        ms_rec = timed(lambda i: eng.train_step_records(views[i % nb], LR), args.steps)
     clk = clocks.stop() if rank == 0 else {}
     seqs = w["B"] * world * args.steps
     value = seqs / (ms_dev / 1e3)
@@ -346,7 +357,10 @@ def run_cuda(args, w):
                           "l2": "4 rotating batches; every step streams the 4 parameter/Adam arenas "
                                 f"({4 * 4 * eng.n_floats / 1e6:.0f} MB) through HBM, > 126 MB L2"},
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
-                       "ms_per_step": ms_e2e / args.steps},
+                       "ms_per_step": ms_e2e / args.steps,
+                       "from_record_store": None if ms_rec is None else
+                       {"value": seqs / (ms_rec / 1e3), "unit": UNIT, "ms_per_step": ms_rec / args.steps,
+                        "what": "DataInput view of a PackedRecords store -> mtam_pack_records into pinned memory -> H2D -> step -> loss"}},
                "gpu_launches": int(launches), "clocks": clk, "phases_ms": phases, "roofline": roof,
                "rooflines_top_phases": roofs, "bandwidth_kernels": bw, "eval_topk": ev}
         if world == 1 and not args.no_cpu:

@@ -94,6 +94,26 @@ typedef struct {
   const int32_t* seq_length;         /* [B]   */
 } mtam_batch;
 
+/* A data set of examples in columnar form (host memory): replaces the reference's Python list of 9-tuples
+ * (user, items, cats, times, timelast, timenow, positions, [target id, cat, time], length) that
+ * Prepare/prepare_data_base.py:79-92 reads back with eval() and make_feed_dic_new pads list by list
+ * (Behavior_...py:146-192).  Record r owns steps [offsets[r], offsets[r+1]) of the six per-step columns. */
+typedef struct {
+  int64_t n_records;
+  const int64_t* offsets;            /* [n_records + 1] */
+  const int32_t* user_id;            /* [n_records] */
+  const int32_t* target_item_id;     /* [n_records] */
+  const int32_t* target_item_category;
+  const float* target_item_time;
+  const int32_t* seq_length;         /* [n_records]: the tuple's `length` field, fed verbatim */
+  const int32_t* item;               /* [offsets[n_records]] */
+  const int32_t* category;
+  const int32_t* position;
+  const float* time;
+  const float* timelast;
+  const float* timenow;
+} mtam_record_store;
+
 #define MTAM_NAME_MAX 160
 #define MTAM_PARAM_DEAD 1    /* created by the reference but never reached by tf.gradients */
 #define MTAM_PARAM_TABLE 2   /* embedding table (sparse + dense gradient pieces) */
@@ -249,6 +269,13 @@ int mtam_gemm(int32_t mode, int32_t transA, int32_t transB, int32_t M, int32_t N
               int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, const float* bias, int32_t relu,
               int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
 size_t mtam_gemm_workspace(int32_t M, int32_t N, int32_t K);
+
+/* make_feed_dic_new (Behavior_...py:146-192) for B records of a columnar store: records index[0..B) (or
+ * first..first+B when index is NULL) are right-padded with 0 to L steps and written into the 11 HOST arrays `out`
+ * points to (typically the pinned staging buffers of the step's single H2D copy).  Host code only; a record
+ * longer than L is an error, as np.pad's negative width is in the reference. */
+int mtam_pack_records(const mtam_record_store* rs, const int64_t* index, int64_t first, int32_t B, int32_t L,
+                      const mtam_batch* out);
 
 /* Kernels launched by the library since it was loaded (diagnostic). */
 long long mtam_launch_count(void);

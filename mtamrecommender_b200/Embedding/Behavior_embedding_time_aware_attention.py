@@ -47,8 +47,12 @@ class Behavior_embedding_time_aware_attention(Base_embedding):
             getattr(self, t + "_emb_lookup_table").bind(engine)
 
     def make_feed_dic_new(self, batch_data):
-        """Right-pads each example's six lists with 0 to position_count (:166-178)."""
+        """Right-pads each example's six lists with 0 to position_count (:166-178).  `batch_data` is the
+        reference's list of 9-tuples or a `PackedRecords` view (DataHandle/record_store.py), which is padded by
+        the library's mtam_pack_records in one pass."""
         B, L = len(batch_data), int(self.position_count)
+        if hasattr(batch_data, "pack_into"):
+            return {getattr(self, k): v for k, v in batch_data.feed(L).items()}
         a = {"user_id": np.zeros(B, np.int32), "item_list": np.zeros((B, L), np.int32),
              "category_list": np.zeros((B, L), np.int32), "time_list": np.zeros((B, L), np.float32),
              "timelast_list": np.zeros((B, L), np.float32), "timenow_list": np.zeros((B, L), np.float32),

@@ -10,6 +10,7 @@ import os
 
 import numpy as np
 
+from .._lib import GEMM_FP32, GEMM_TF32X3
 from ..engine import Engine, ModelConfig
 from ..util.model_log import create_log
 
@@ -55,7 +56,8 @@ class base_model(object):
         cfg = ModelConfig(kind=self.KIND, max_batch=max(F.train_batch_size, F.test_batch_size), L=self.max_len,
                           D=self.num_units, H=self.num_heads, N=self.num_blocks, user_count=emb.user_count,
                           item_count=emb.item_count, category_count=emb.category_count, reg=F.regulation_rate,
-                          clip=F.max_gradient_norm)
+                          clip=F.max_gradient_norm,
+                          gemm_mode=GEMM_FP32 if getattr(F, "gemm_mode", "tf32x3") == "fp32" else GEMM_TF32X3)
         device = getattr(sess, "device", "cuda:0") if sess is not None else "cuda:0"
         self.engine = Engine(cfg, device=device, seed=1234)
         emb.bind(self.engine)
@@ -116,12 +118,17 @@ class base_model(object):
         return {p.key: v for p, v in d.items()}
 
     def train(self, sess, batch_data, learning_rate, add_summary=False, global_step=0, epoch=0):
-        loss = self.engine.train_step(self._feed(batch_data), learning_rate)
+        if hasattr(batch_data, "pack_into"):      # PackedRecords: padded straight into the pinned feed buffers
+            loss = self.engine.train_step_records(batch_data, learning_rate)
+        else:
+            loss = self.engine.train_step(self._feed(batch_data), learning_rate)
         return np.float32(loss), self.merged
 
     def metrics_topK(self, sess, batch_data, global_step, topk):
-        feed = self._feed(batch_data)
-        b = self.engine.upload(feed)
+        if hasattr(batch_data, "pack_into"):
+            b = self.engine.upload_records(batch_data)
+        else:
+            b = self.engine.upload(self._feed(batch_data))
         idx, _ = self.engine.eval_topk_device(b, 50)
         m = self.engine.hr_ndcg_device(idx, b.t["target_item_id"]).cpu().numpy()
         return tuple(float(x) for x in m)

@@ -39,6 +39,13 @@ class Batch(C.Structure):
                 ("seq_length", C.c_void_p)]
 
 
+class RecordStore(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("offsets", C.c_void_p), ("user_id", C.c_void_p),
+                ("target_item_id", C.c_void_p), ("target_item_category", C.c_void_p), ("target_item_time", C.c_void_p),
+                ("seq_length", C.c_void_p), ("item", C.c_void_p), ("category", C.c_void_p), ("position", C.c_void_p),
+                ("time", C.c_void_p), ("timelast", C.c_void_p), ("timenow", C.c_void_p)]
+
+
 class ParamInfo(C.Structure):
     _fields_ = [("name", C.c_char * NAME_MAX), ("rows", C.c_int32), ("cols", C.c_int32), ("ndim", C.c_int32),
                 ("ld", C.c_int32), ("offset", C.c_uint64), ("flags", C.c_int32)]
@@ -57,6 +64,7 @@ PHASES = ("embed_fwd", "gru_x_gemm", "gru_fwd", "kv_gemm", "hop_fwd", "ce_fwd", 
 # every symbol include/mtam.h declares: (restype, argtypes)
 _VP, _I32, _I64, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
 SIGNATURES = {
+    "mtam_pack_records": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _VP]),
     "mtam_gather": (C.c_int, [_VP, _I32, _I32, _VP, _I64, _VP, _VP]),
     "mtam_scatter_add_workspace": (_SZ, [_I64, _I32, _I32]),
     "mtam_scatter_add": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _I32, _I64, _VP, _SZ, _VP, _VP, _VP]),

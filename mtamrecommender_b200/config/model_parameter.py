@@ -22,6 +22,9 @@ _DEFS = [
     ("neg_sample_ratio", float, 20), ("remove_duplicate", bool, True), ("experiment_data_type", str, "item_based"),
     ("fine_tune_load_path", str, None), ("load_type", str, "from_scratch"), ("draw_pic", bool, False),
     ("top_k", int, 20), ("experiment_name", str, "data_init"),
+    # not a reference flag: dense contractions on tcgen05 with the 3-term TF32 split ("tf32x3", fp32-class accuracy)
+    # or on exact-fp32 FFMA tiles ("fp32")
+    ("gemm_mode", str, "tf32x3"),
 ]
 
 # name -> (type, num_blocks, experiment_type, version, test_batch_size)

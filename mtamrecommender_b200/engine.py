@@ -220,6 +220,26 @@ class Engine:
         self._h2d_done.record(torch.cuda.current_stream(self.device))
         return DeviceBatch({k: self._dev[k][:B] for k in FEED_KEYS}, B)
 
+    def upload_records(self, records) -> DeviceBatch:
+        """A `PackedRecords` view (DataHandle/record_store.py) -> padded by mtam_pack_records straight into the
+        pinned staging arrays -> one H2D copy.  The columnar counterpart of make_feed_dic_new + upload."""
+        B = len(records)
+        if B < 1 or B > self.cfg.max_batch:
+            raise ValueError(f"batch size {B} outside [1, {self.cfg.max_batch}]")
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()
+        records.pack_into(self._pinned_np, self.cfg.L)
+        self._dev_all.copy_(self._pinned_all, non_blocking=True)
+        if self._h2d_done is None:
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.device))
+        return DeviceBatch({k: self._dev[k][:B] for k in FEED_KEYS}, B)
+
+    def train_step_records(self, records, lr: float) -> float:
+        """`train_step` for a `PackedRecords` view."""
+        batch = self.upload_records(records)
+        return self._step_uploaded(batch, lr)
+
     def device_batch(self, tensors: Dict[str, torch.Tensor]) -> DeviceBatch:
         B = int(tensors["user_id"].shape[0])
         for k in FEED_KEYS:
@@ -245,7 +265,9 @@ class Engine:
     def train_step(self, feed: Dict[str, np.ndarray], lr: float) -> float:
         """One `model.train` call from a host feed: pack -> one H2D copy -> the step (the captured CUDA graph when
         `capture_train_graph` was called for this batch size, else eager launches) -> loss read back."""
-        batch = self.upload(feed)
+        return self._step_uploaded(self.upload(feed), lr)
+
+    def _step_uploaded(self, batch: DeviceBatch, lr: float) -> float:
         if self._graph is not None and batch.B == self._graph_B:
             self.train_step_graph(lr)
         else:

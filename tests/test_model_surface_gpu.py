@@ -1,0 +1,57 @@
+"""The reference-facing surface (train_process.py:99-104, 326-344): Model(FLAGS, emb, sess), model.train, model.metrics_topK,
+fed by DataInput over the reference's list of 9-tuples and over the columnar record store -- same losses, same
+parameters, same metrics; and the first losses equal the CPU oracle's."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _flags(**kw):
+    from mtamrecommender_b200.config.model_parameter import model_parameter
+    F = model_parameter([]).flags.FLAGS
+    F.type, F.experiment_type, F.version = "synthetic", "MTAM", "t"
+    F.num_units, F.num_blocks, F.num_heads, F.length_of_user_history = 64, 2, 1, 12
+    F.train_batch_size, F.test_batch_size, F.dropout = 16, 16, 0.0
+    for k, v in kw.items():
+        setattr(F, k, v)
+    return F
+
+
+def _model(F, users, items, cats):
+    from mtamrecommender_b200.Embedding.Behavior_embedding_time_aware_attention import Behavior_embedding_time_aware_attention
+    from mtamrecommender_b200.Model.MTAMRec_model import MTAM
+    from mtamrecommender_b200.session import Session
+    emb = Behavior_embedding_time_aware_attention(True, users, items, cats, F.length_of_user_history)
+    sess = Session("cuda:0")
+    return MTAM(F, emb, sess), sess
+
+
+@pytest.mark.parametrize("gemm_mode", ["fp32", "tf32x3"])
+def test_train_and_eval_from_tuples_and_from_record_store(gemm_mode):
+    from oracle import mtam_oracle as O
+    from mtamrecommender_b200.DataHandle.get_input_data import DataInput
+    from mtamrecommender_b200.DataHandle.record_store import PackedRecords
+    users, items, cats = 30, 400, 7
+    F = _flags(gemm_mode=gemm_mode)
+    cfg = O.OracleConfig(kind=O.MTAM, L=12, D=64, H=1, N=2, user_count=users, item_count=items, category_count=cats)
+    recs = O.synth_records(cfg, 40, 9)                       # 2 full batches and a short one
+    rs = PackedRecords.from_records(recs)
+    m1, s1 = _model(F, users, items, cats)
+    m2, s2 = _model(F, users, items, cats)
+    P = m1.engine.get_params()
+    m2.engine.set_params(P)
+    tr = O.OracleTrainer(cfg, {k: v.copy() for k, v in P.items()})
+    lr = 1e-3
+    for (i, b1), (_, b2) in zip(DataInput(recs, 16), DataInput(rs, 16)):
+        l1, _ = m1.train(s1, b1, lr)
+        l2, _ = m2.train(s2, b2, lr)
+        lo = tr.train_step(O.make_feed(cfg, b1), lr)
+        assert l1 == l2, (i, l1, l2)
+        assert abs(float(l1) - lo) <= 2e-5 * abs(lo), (i, l1, lo)
+    assert bool((m1.engine.params == m2.engine.params).all())
+    a = m1.metrics_topK(s1, recs[:16], 0, 50)
+    b = m2.metrics_topK(s2, rs[:16], 0, 50)
+    assert a == b and len(a) == 10
+    ref, _, _ = O.metrics_topk(cfg, tr.params, O.make_feed(cfg, recs[:16]))
+    assert np.allclose(np.array(a), np.array(ref), atol=1e-6)
