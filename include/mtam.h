@@ -296,6 +296,22 @@ int mtam_score_topk(int32_t gemm_mode, const float* pred, int32_t B, int32_t D, 
                     void* workspace, size_t workspace_bytes, void* stream);
 size_t mtam_score_topk_workspace(int32_t B, int32_t rows, int32_t k);
 
+/* Softmax cross-entropy of base_model.output (base_model.py:316-321) against item rows [table, table + rows*D) -- the
+ * whole catalogue or one shard of a row-sharded table (sharded log-sum-exp).  `target` is relative to the
+ * range; a target outside [0, rows) has no logit here.
+ *   forward : lse_out[b] = log sum_v exp(<pred_b, row_v>) over the range; target_logit_out[b] = <pred_b, row_target>
+ *             where the target lies in the range, else 0.  Over shards: lse = logsumexp_r(lse_r), target logit = sum_r.
+ *   backward: with the GLOBAL lse, G = (exp(logit - lse) - onehot) * inv_batch; dtable[rows,D] = G^T pred (every row of
+ *             the range, written once), dpred[B,D] = G table (this range's share: sum over shards).
+ * The [B,rows] logits are never materialised; gemm_mode as in mtam_score_topk. */
+size_t mtam_softmax_ce_workspace(int32_t B, int32_t D, int32_t rows);
+int mtam_softmax_ce_forward(int32_t gemm_mode, const float* pred, int32_t B, int32_t D, const float* table, int32_t rows,
+                            const int32_t* target, float* lse_out, float* target_logit_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int mtam_softmax_ce_backward(int32_t gemm_mode, const float* pred, int32_t B, int32_t D, const float* table, int32_t rows,
+                             const int32_t* target, const float* lse, float inv_batch, float* dtable, float* dpred,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Merge per-shard top-k lists: in_idx/in_score are [n_lists,B,k] (each list sorted, shard order =
  * index order) -> out [B,k].  Used after the all-gather of the row-sharded eval. */
 int mtam_merge_topk(const int32_t* in_idx, const float* in_score, int32_t n_lists, int32_t B, int32_t k,

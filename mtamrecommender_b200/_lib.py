@@ -99,6 +99,9 @@ SIGNATURES = {
     "mtam_score_topk": (C.c_int, [_I32, _VP, _I32, _I32, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _SZ, _VP]),
     "mtam_score_topk_workspace": (_SZ, [_I32, _I32, _I32]),
     "mtam_merge_topk": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP, _VP, _VP]),
+    "mtam_softmax_ce_workspace": (_SZ, [_I32, _I32, _I32]),
+    "mtam_softmax_ce_forward": (C.c_int, [_I32, _VP, _I32, _I32, _VP, _I32, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "mtam_softmax_ce_backward": (C.c_int, [_I32, _VP, _I32, _I32, _VP, _I32, _VP, _VP, C.c_float, _VP, _VP, _VP, _SZ, _VP]),
     "mtam_hr_ndcg": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP]),
 }
 

@@ -369,3 +369,43 @@ int ce_backward(int mode, int D, const float* pred, const float* table, const in
 }
 
 }  // namespace mtam
+
+// ---- stand-alone softmax cross-entropy over a row range of the catalogue (the sharded log-sum-exp of SURVEY 8e) ----
+extern "C" {
+
+// [softmax kernels' partial results | loss_origin scratch [B] | per-block loss partials]
+size_t mtam_softmax_ce_workspace(int32_t B, int32_t D, int32_t rows) {
+  return mtam::ce_workspace_bytes(B, D, rows) + mtam::align_up((size_t)B * sizeof(float), 256) +
+         mtam::align_up((size_t)mtam::cdiv(B, 32) * sizeof(float), 256);
+}
+
+int mtam_softmax_ce_forward(int32_t gemm_mode, const float* pred, int32_t B, int32_t D, const float* table, int32_t rows,
+                            const int32_t* target, float* lse_out, float* target_logit_out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  using namespace mtam;
+  if (!pred || !table || !target || !lse_out || !target_logit_out || !workspace || B < 1 || rows < 1)
+    return set_error(MTAM_ERR_INVALID, "mtam_softmax_ce_forward: bad argument");
+  if (workspace_bytes < mtam_softmax_ce_workspace(B, D, rows)) return set_error(MTAM_ERR_WORKSPACE, "mtam_softmax_ce_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  // rows whose target lies outside this range keep a target logit of 0 (the range that owns it writes it)
+  MTAM_CUDA_CHECK(cudaMemsetAsync(target_logit_out, 0, (size_t)B * sizeof(float), st));
+  const size_t base = ce_workspace_bytes(B, D, rows);
+  float* loss_origin = (float*)((char*)workspace + base);                // lse - target logit of THIS range: scratch
+  float* block_partial = (float*)((char*)workspace + base + align_up((size_t)B * sizeof(float), 256));
+  int n_partial = 0;
+  return ce_forward(gemm_mode, D, pred, table, target, B, rows, workspace, target_logit_out, lse_out, loss_origin, block_partial,
+                    &n_partial, st);
+}
+
+int mtam_softmax_ce_backward(int32_t gemm_mode, const float* pred, int32_t B, int32_t D, const float* table, int32_t rows,
+                             const int32_t* target, const float* lse, float inv_batch, float* dtable, float* dpred,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace mtam;
+  if (!pred || !table || !target || !lse || !dtable || !dpred || !workspace || B < 1 || rows < 1)
+    return set_error(MTAM_ERR_INVALID, "mtam_softmax_ce_backward: bad argument");
+  if (workspace_bytes < mtam_softmax_ce_workspace(B, D, rows)) return set_error(MTAM_ERR_WORKSPACE, "mtam_softmax_ce_backward: workspace too small");
+  return ce_backward(gemm_mode, D, pred, table, target, lse, B, rows, inv_batch, workspace, dtable, dpred, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+

@@ -470,6 +470,43 @@ def score_topk(pred: torch.Tensor, table: torch.Tensor, k: int, row_begin: int =
     return idx, sc
 
 
+def softmax_ce_forward(pred: torch.Tensor, table: torch.Tensor, target: torch.Tensor, gemm_mode: int = _lib.GEMM_TF32X3,
+                       workspace: Optional[torch.Tensor] = None):
+    """Log-sum-exp of pred x table^T per pred row and the target's logit (mtam_softmax_ce_forward).  `table` is the
+    whole catalogue or one shard; `target` (int32) is relative to it -- rows whose target lies outside get logit 0."""
+    lib = _lib.load()
+    B, D = pred.shape
+    rows = table.shape[0]
+    if workspace is None:
+        workspace = torch.empty(int(lib.mtam_softmax_ce_workspace(B, D, rows)), dtype=torch.uint8, device=pred.device)
+    lse = torch.empty(B, dtype=torch.float32, device=pred.device)
+    tl = torch.empty(B, dtype=torch.float32, device=pred.device)
+    check(lib.mtam_softmax_ce_forward(gemm_mode, pred.data_ptr(), B, D, table.data_ptr(), rows, target.data_ptr(),
+                                      lse.data_ptr(), tl.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                      torch.cuda.current_stream(pred.device).cuda_stream), "mtam_softmax_ce_forward")
+    return lse, tl
+
+
+def softmax_ce_backward(pred: torch.Tensor, table: torch.Tensor, target: torch.Tensor, lse: torch.Tensor, inv_batch: float,
+                        gemm_mode: int = _lib.GEMM_TF32X3, workspace: Optional[torch.Tensor] = None,
+                        dtable: Optional[torch.Tensor] = None):
+    """Gradients of mean cross-entropy w.r.t. the rows of `table` (complete) and w.r.t. pred (this table's share), given
+    the global log-sum-exp (mtam_softmax_ce_backward)."""
+    lib = _lib.load()
+    B, D = pred.shape
+    rows = table.shape[0]
+    if workspace is None:
+        workspace = torch.empty(int(lib.mtam_softmax_ce_workspace(B, D, rows)), dtype=torch.uint8, device=pred.device)
+    if dtable is None:
+        dtable = torch.empty((rows, D), dtype=torch.float32, device=pred.device)
+    dpred = torch.empty((B, D), dtype=torch.float32, device=pred.device)
+    check(lib.mtam_softmax_ce_backward(gemm_mode, pred.data_ptr(), B, D, table.data_ptr(), rows, target.data_ptr(),
+                                       lse.data_ptr(), float(inv_batch), dtable.data_ptr(), dpred.data_ptr(),
+                                       workspace.data_ptr(), workspace.numel(),
+                                       torch.cuda.current_stream(pred.device).cuda_stream), "mtam_softmax_ce_backward")
+    return dtable, dpred
+
+
 def merge_topk(idx_lists: torch.Tensor, score_lists: torch.Tensor):
     """Merges [n_lists, B, k] per-shard top-k lists (shard order = index order) into [B, k] (mtam_merge_topk)."""
     lib = _lib.load()

@@ -26,7 +26,7 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import check
 from .engine import (DeviceBatch, Engine, gather, merge_topk, scatter_add, scatter_add_workspace, score_topk,
-                     sort_indices)
+                     softmax_ce_backward, softmax_ce_forward, sort_indices)
 
 
 class DataParallel:
@@ -149,6 +149,12 @@ class DataParallel:
         return float(self.eng.read_scalars()[_lib.S_LOSS])
 
 
+def combine_lse(lse_per_shard: torch.Tensor) -> torch.Tensor:
+    """[n_shards, B] per-shard log-sum-exps -> [B] global: m + log(sum_r exp(lse_r - m)), shards in index order."""
+    m = lse_per_shard.max(dim=0).values
+    return m + torch.log(torch.exp(lse_per_shard - m).sum(dim=0))
+
+
 def shard_rows(total_rows: int, world: int) -> int:
     """Rows per shard of a row-sharded table: rank r owns [r*rows, min((r+1)*rows, total_rows))."""
     return (total_rows + world - 1) // world
@@ -163,7 +169,12 @@ class ShardedCatalogue:
       lookup(ids)  : all-to-all of the ids to their owners, local gather (mtam_gather), all-to-all of the rows back;
       topk(pred,k) : all-gather of pred, every rank scores its shard and keeps a local top-k with GLOBAL row numbers
                      (mtam_score_topk), all-gather of the [B,k] lists, k-way merge (mtam_merge_topk; ties -> lower
-                     global index is preserved because shard order = index order).
+                     global index is preserved because shard order = index order);
+      softmax_ce   : the training loss against the sharded table (base_model.py:316-321): all-gather of pred and
+                     targets, per-shard log-sum-exp + target logit (mtam_softmax_ce_forward), all-gather of the
+                     [B] log-sum-exps and all-reduce of the target logits, per-shard backward with the global
+                     log-sum-exp (mtam_softmax_ce_backward): the shard's table gradient is complete and purely local
+                     (no table all-reduce; Adam runs on the shard only), dpred is reduce-scattered.
     Results equal the unsharded ones bit for bit (rows are copies; scores are the same fp32 dot products).
     """
 
@@ -208,6 +219,27 @@ class ShardedCatalogue:
         out = torch.empty_like(back)
         out[srt.perm.long()] = back
         return out.reshape(*ids.shape, self.D)
+
+    def softmax_ce(self, pred: torch.Tensor, target: torch.Tensor, gemm_mode: int = _lib.GEMM_TF32X3):
+        """pred [B_local, D], target [B_local] int32 global item ids -> (loss_origin [B_local] = -log softmax at the
+        target, dpred [B_local, D] and dshard [shard rows, D] for the MEAN loss over the global batch)."""
+        W, Bl = self.world, pred.shape[0]
+        dev = pred.device
+        allp = torch.empty((W * Bl, self.D), dtype=torch.float32, device=dev)
+        allt = torch.empty(W * Bl, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allp, pred.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(allt, target.contiguous(), group=self.group)
+        rel = (allt - self.row_begin).contiguous()
+        lse_r, tl = softmax_ce_forward(allp, self.shard, rel, gemm_mode)
+        all_lse = torch.empty((W, W * Bl), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(all_lse, lse_r, group=self.group)
+        dist.all_reduce(tl, group=self.group)
+        lse = combine_lse(all_lse)
+        dshard, dp = softmax_ce_backward(allp, self.shard, rel, lse, 1.0 / (W * Bl), gemm_mode)
+        dpred = torch.empty((Bl, self.D), dtype=torch.float32, device=dev)
+        dist.reduce_scatter_tensor(dpred, dp, group=self.group)
+        mine = slice(self.rank * Bl, (self.rank + 1) * Bl)
+        return (lse - tl)[mine], dpred, dshard
 
     def topk(self, pred: torch.Tensor, k: int = 50):
         """Full-catalogue top-k for this rank's pred rows [B_local, D] -> (idx [B_local,k] int32 global, score)."""

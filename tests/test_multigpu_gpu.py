@@ -73,6 +73,25 @@ def _rank_main(rank, world, port, q):
     si, ss = cat.topk(pred, k)
     fi, fs = E.score_topk(pred, table, k)
     out["topk_exact"] = bool(torch.equal(si, fi) and torch.equal(ss, fs))
+    # sharded softmax cross-entropy (sharded log-sum-exp) == the unsharded one on the concatenated batch
+    tgt = torch.randint(0, V, (24,), generator=g2, dtype=torch.int32).to(dev)
+    tgt[0] = V - 1
+    lo, dpr, dsh = cat.softmax_ce(pred, tgt)
+    ps, ts = [], []
+    for r in range(world):                       # every rank can replay the other's draws from its seed
+        gr = torch.Generator().manual_seed(100 + r)
+        torch.randint(0, V, (7, 33), generator=gr, dtype=torch.int32)
+        ps.append(torch.randn((24, D), generator=gr))
+        t = torch.randint(0, V, (24,), generator=gr, dtype=torch.int32); t[0] = V - 1
+        ts.append(t)
+    allp, allt = torch.cat(ps).to(dev), torch.cat(ts).to(dev)
+    lse_f, tl_f = E.softmax_ce_forward(allp, table, allt)
+    dT_f, dp_f = E.softmax_ce_backward(allp, table, allt, lse_f, 1.0 / allp.shape[0])
+    mine = slice(rank * 24, (rank + 1) * 24)
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+    out["ce_loss_err"] = rel(lo, (lse_f - tl_f)[mine])
+    out["ce_dpred_err"] = rel(dpr, dp_f[mine])
+    out["ce_dtable_err"] = rel(dsh, dT_f[cat.row_begin:cat.row_end])
     torch.cuda.synchronize()
     q.put((rank, out))
     dist.barrier()
@@ -99,6 +118,7 @@ def test_two_gpu_dp_and_sharded_catalogue():
         assert res[r]["replicas_identical_dense"] and res[r]["replicas_identical_gather"], "replicas diverged"
         assert res[r]["lookup_exact"], "sharded lookup differs from the local gather"
         assert res[r]["topk_exact"], "sharded top-k differs from the unsharded one"
+        assert res[r]["ce_loss_err"] < 1e-5 and res[r]["ce_dpred_err"] < 1e-5 and res[r]["ce_dtable_err"] < 1e-5, res[r]
     for mode in ("dense", "gather"):
         assert res[0][f"loss_err_{mode}"] < 2e-5, res[0]
         assert res[0][f"param_err_{mode}"] < 1e-4, res[0]

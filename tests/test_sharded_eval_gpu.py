@@ -89,6 +89,51 @@ def _same_topk(ei, es, ti, ts):
         assert min(near) <= 4e-6 * scale[r, 0], (r, c, es[r, max(c - 1, 0):c + 2])
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["fp32", "tf32x3"])
+@pytest.mark.parametrize("V,B,D,shards", [(5003, 37, 64, 4), (20011, 130, 64, 8), (3709, 9, 32, 3)])
+def test_sharded_softmax_ce_equals_unsharded_and_reference(V, B, D, shards, mode):
+    """Sharded log-sum-exp: per-shard mtam_softmax_ce_forward, lse combined over shards, target logit summed,
+    per-shard backward with the global lse -> the same loss / dpred / table gradient as the unsharded call, and both
+    equal log_softmax cross-entropy (base_model.py:316-321) in float64."""
+    import torch
+    from mtamrecommender_b200 import engine as E
+    from mtamrecommender_b200.parallel import combine_lse, shard_rows
+    g = torch.Generator().manual_seed(V + 7)
+    table = (torch.rand(V, D, generator=g) - 0.5) * 0.6
+    pred = torch.randn(B, D, generator=g)
+    tgt = torch.randint(0, V, (B,), generator=g, dtype=torch.int32)
+    tgt[0], tgt[1] = 0, V - 1
+    dt, dp, dtg = table.cuda(), pred.cuda(), tgt.cuda()
+    lse_f, tl_f = E.softmax_ce_forward(dp, dt, dtg, gemm_mode=mode)
+    dT_f, dP_f = E.softmax_ce_backward(dp, dt, dtg, lse_f, 1.0 / B, gemm_mode=mode)
+    # float64 reference
+    logits = pred.double() @ table.double().T
+    logits.requires_grad_(False)
+    p64, t64 = pred.double().requires_grad_(True), table.double().requires_grad_(True)
+    lo = -torch.log_softmax(p64 @ t64.T, dim=1)[torch.arange(B), tgt.long()]
+    lo.mean().backward()
+    rel = lambda a, b: float((a.double().cpu() - b).norm() / b.norm())
+    assert rel(lse_f - tl_f, lo.detach()) < 1e-5
+    assert rel(dP_f, p64.grad) < 1e-5 and rel(dT_f, t64.grad) < 1e-5
+    # shards
+    S = shard_rows(V, shards)
+    lses, tls = [], []
+    for r in range(shards):
+        lo_r, hi_r = r * S, min(V, (r + 1) * S)
+        l, t = E.softmax_ce_forward(dp, dt[lo_r:hi_r].clone(), (dtg - lo_r).contiguous(), gemm_mode=mode)
+        lses.append(l); tls.append(t)
+    lse = combine_lse(torch.stack(lses))
+    tl = torch.stack(tls).sum(0)
+    assert torch.allclose(lse, lse_f, rtol=0, atol=2e-6) and torch.equal(tl, tl_f)
+    dP = torch.zeros_like(dP_f)
+    for r in range(shards):
+        lo_r, hi_r = r * S, min(V, (r + 1) * S)
+        dsh, dpp = E.softmax_ce_backward(dp, dt[lo_r:hi_r].clone(), (dtg - lo_r).contiguous(), lse, 1.0 / B, gemm_mode=mode)
+        dP += dpp
+        assert rel(dsh, t64.grad[lo_r:hi_r]) < 1e-5
+    assert rel(dP, p64.grad) < 1e-5
+
+
 def test_sort_then_sorted_scatter_equals_scatter_add():
     import torch
     from mtamrecommender_b200 import engine as E
