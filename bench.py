@@ -213,6 +213,10 @@ def run_cuda(args, w):
     dev = f"cuda:{local}"
     torch.cuda.set_device(dev)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mtam_nccl_%h_%p.log")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # that level printf()s the banner to stdout
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(dev))
     mc = E.ModelConfig(kind=w["kind"], max_batch=w["B"], L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
                        item_count=w["items"], category_count=w["cats"],

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (tid == 0) CE_TRACE(10, 0);     // CTA set up
 
   // epilogue thread geometry: TMEM lane quadrant = warp % 4; the two warps of a quadrant split the columns
   const int quad = warp & 3, half = (warp >> 2) & 1;
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tid == 0) CE_TRACE(11, 0);     // stationary Q tile in TMEM
 
   if (warp >= kEpiWarps && warp < kWarpS) {
     // ================= producers: global -> registers -> split -> swizzled shared tiles =================
@@ -458,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       constexpr int OC = D / 2;
       mbar_wait(&bars.o_full, 0);
       tc_fence_after();
+      if (tid == 0) CE_TRACE(12, 0);   // accumulator complete
       float* dst = nullptr;
       if (qvalid)
         dst = ((MODE == CE_DP) ? a.dpred_partial + ((int64_t)blockIdx.x * a.B + qrow) * D : a.dTable + (int64_t)qrow * D) + half * OC;
@@ -475,6 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) CE_TRACE(13, 0);       // results stored
   if (warp == kWarpS) {
     __syncwarp();
     tmem_dealloc(tmem, TMEM_COLS);

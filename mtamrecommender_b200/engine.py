@@ -82,12 +82,15 @@ class Engine:
         self.workspace_bytes = int(sizes.workspace_bytes)
         dev = self.device
         self.params = torch.zeros(self.n_floats, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros(self.n_floats, dtype=torch.float32, device=dev)
+        # the step's scalars (loss pieces, norms) and the squared-norm accumulator sit right behind the grads arena, so a
+        # data-parallel driver reduces the dense tail of the arena and these in ONE collective
+        self._grads_all = torch.zeros(self.n_floats + 16, dtype=torch.float32, device=dev)
+        self.grads = self._grads_all[:self.n_floats]
         self.adam_m = torch.zeros(self.n_floats, dtype=torch.float32, device=dev)
         self.adam_v = torch.zeros(self.n_floats, dtype=torch.float32, device=dev)
         self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=dev)
-        self.scalars = torch.zeros(_lib.S_COUNT, dtype=torch.float32, device=dev)
-        self.norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.scalars = self._grads_all[self.n_floats: self.n_floats + _lib.S_COUNT]
+        self.norm_sq = self._grads_all[self.n_floats + _lib.S_COUNT: self.n_floats + _lib.S_COUNT + 1]
         h = C.c_void_p()
         check(self.lib.mtam_create(C.byref(self.c_cfg), self.params.data_ptr(), self.grads.data_ptr(),
                                    self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.workspace.data_ptr(),

@@ -26,7 +26,7 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import check
 from .engine import (DeviceBatch, Engine, gather, merge_topk, scatter_add, scatter_add_workspace, score_topk,
-                     softmax_ce_backward, softmax_ce_forward, sort_indices)
+                     scatter_add_sorted, softmax_ce_backward, softmax_ce_forward, sort_indices)
 
 
 class DataParallel:
@@ -71,6 +71,8 @@ class DataParallel:
             rows = c.item_rows + c.category_rows + c.position_rows
             self.sp = torch.zeros((rows, D), dtype=torch.float32, device=dev)   # [item | category | position]
         self.scatter_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self.user_sort_ws = torch.empty(max(int(engine.lib.mtam_sort_workspace(W * B, c.user_rows)), 16), dtype=torch.uint8,
+                                        device=dev)
         self.comm = torch.cuda.Stream(dev)
         self.ev_item = torch.cuda.Event()
         self.ev_item.record(torch.cuda.current_stream(dev))   # materialises the cudaEvent_t
@@ -97,6 +99,14 @@ class DataParallel:
         T = B * L
         c = eng.c_cfg
         main = torch.cuda.current_stream(eng.device)
+        # the user ids are known before the step: gather and sort them beside the forward pass
+        sv0 = None
+        self.comm.wait_stream(main)
+        has_user = eng.cfg.kind != "PISTREC"
+        if has_user:
+            with torch.cuda.stream(self.comm):
+                g_user = self._gather(self.g_user, batch.t["user_id"])
+                user_sorted = sort_indices(g_user, c.user_rows, self.user_sort_ws)
         eng.forward_backward_device(batch, global_batch=B * W)
         sv = _lib.SparseView()
         check(eng.lib.mtam_sparse_pieces(eng.h, C.byref(sv)), "mtam_sparse_pieces")
@@ -105,13 +115,12 @@ class DataParallel:
         self.comm.wait_event(self.ev_item)
         with torch.cuda.stream(self.comm):
             dist.all_reduce(eng.grads[item_lo:item_hi], group=self.group)
-        # 2. the rest of the dense pieces, the loss scalars, the squared norm of the un-deduplicated sparse pieces
-        dist.all_reduce(eng.scalars[:3], group=self.group)
-        dist.all_reduce(eng.norm_sq, group=self.group)
+        # 2. the rest of the dense pieces, the loss scalars, the squared norm of the un-deduplicated sparse pieces: they
+        #    sit back to back behind the item table in the engine's grads allocation -- one collective
         dense_begin = int(sv.dense_begin)
         if item_lo > dense_begin:
             dist.all_reduce(eng.grads[dense_begin:item_lo], group=self.group)
-        dist.all_reduce(eng.grads[item_hi:], group=self.group)
+        dist.all_reduce(eng._grads_all[item_hi: eng.n_floats + _lib.S_COUNT + 1], group=self.group)
         main.wait_stream(self.comm)
         eng.finish_grads(scatter_local=False)          # adds the squared norm of the (global) dense pieces
         # 3. sparse pieces
@@ -135,13 +144,13 @@ class DataParallel:
             scatter_add(self._grad_region(int(sv.item_offset), c.item_rows), g_item, g_dE2[:, :D], self.scatter_ws)
             scatter_add(self._grad_region(int(sv.category_offset), c.category_rows), g_cat, g_dE2[:, D:], self.scatter_ws)
             scatter_add(self._grad_region(int(sv.position_offset), c.position_rows), g_pos, g_dEp, self.scatter_ws)
-        g_user = None
-        if sv.has_user:
-            g_user = self._gather(self.g_user, batch.t["user_id"])
+        if bool(sv.has_user) != has_user:
+            raise RuntimeError("user-table gradient pieces do not match the model kind")
+        if has_user:
             g_dEu = self._gather(self.g_dEu, self._ws_view(sv.user_rows, B, D))
-            scatter_add(self._grad_region(int(sv.user_offset), c.user_rows), g_user, g_dEu, self.scatter_ws)
+            scatter_add_sorted(self._grad_region(int(sv.user_offset), c.user_rows), user_sorted, g_dEu, self.scatter_ws)
         eng.apply(lr)
-        if g_user is not None:   # apply() re-zeroes only the local users' rows of the grads arena
+        if has_user:   # apply() re-zeroes only the local users' rows of the grads arena
             self._grad_region(int(sv.user_offset), c.user_rows).index_fill_(0, g_user.long(), 0.0)
 
     def train_step(self, feed: Dict[str, np.ndarray], lr: float) -> float:

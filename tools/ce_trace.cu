@@ -1,3 +1,4 @@
+// usage: ce_trace.bin [0 = forward | 1 = dpred pass | 2 = dTable pass]
 // Developer probe: pipeline timeline of the tensor-core CE kernels (events of CTA (0,0), cycles relative to the first).
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -DMTAM_CE_TRACE \
 //   -I mtamrecommender_b200/csrc tools/ce_trace.cu mtamrecommender_b200/csrc/{ce.cu,util.cu} -o tools/ce_trace.bin
@@ -33,7 +34,7 @@ int main(int argc, char** argv) {
     if (mode == 0) ce_forward_tc(D, pred, table, tg, B, V, ws, tlogit, lse, lo, bp, &np, 0);
     else {
       if (rep == 0) ce_forward_tc(D, pred, table, tg, B, V, ws, tlogit, lse, lo, bp, &np, 0);
-      ce_backward_tc(D, pred, table, tg, lse, B, V, 1.f / B, ws, dT, dp, 0);
+      ce_backward_tc(D, pred, table, tg, lse, B, V, 1.f / B, ws, dT, dp, 0, mode == 2 ? 2 : (mode == 1 ? 1 : 3));
     }
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
@@ -45,13 +46,17 @@ int main(int argc, char** argv) {
   long long t0 = h[0];
   const char* names[] = {"prod xk_full", "mma  S wait ok", "mma  S issued", "epi0 s_full ok", "epi0 arrived", "mma  g_full ok",
                          "mma  PV issued", "prod xm_full", "epi1 s_full ok", "epi1 arrived"};
+  const int first = mode == 2 ? 0 : 20;     // the dTable pass has 16 tiles per CTA: show them all, from the CTA's start
+  const long long base = mode == 2 ? h[10 * 64] : h[0 * 64 + 20];
   printf("%-16s", "tile");
-  for (int i = 0; i < 12; ++i) printf("%8d", i + 20);
+  for (int i = 0; i < (mode == 2 ? 16 : 12); ++i) printf("%8d", i + first);
   printf("\n");
   for (int s = 0; s < 10; ++s) {
     printf("%-16s", names[s]);
-    for (int i = 20; i < 32; ++i) printf("%8lld", h[s * 64 + i] ? h[s * 64 + i] - h[0 * 64 + 20] : -1);
+    for (int i = first; i < first + (mode == 2 ? 16 : 12); ++i) printf("%8lld", h[s * 64 + i] ? h[s * 64 + i] - base : -1);
     printf("\n");
   }
+  printf("CTA set up %lld, Q in TMEM %lld, accumulator complete %lld, stored %lld (cycles from set-up)\n", h[10 * 64] - base,
+         h[11 * 64] - base, h[12 * 64] - base, h[13 * 64] - base);
   return 0;
 }
