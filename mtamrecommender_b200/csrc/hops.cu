@@ -400,7 +400,7 @@ __device__ __forceinline__ float dot16(const float* __restrict__ row, const floa
 struct HopCtaSmem {
   int RS, X, K, V, dX, vec, mv, part, part2, sc, dps, dA, dM, dsum, total;   // offsets in floats
 };
-__host__ __device__ inline HopCtaSmem hop_cta_layout(int D, int H, int L, bool bwd) {
+__host__ __device__ inline HopCtaSmem hop_cta_layout(int D, int H, int L, int N, bool bwd) {
   HopCtaSmem o;
   const int C = D / 16, Lp = (L + 3) & ~3;
   o.RS = D + 4;
@@ -408,7 +408,7 @@ __host__ __device__ inline HopCtaSmem hop_cta_layout(int D, int H, int L, bool b
   o.X = p; p += L * o.RS;
   o.K = p; p += L * o.RS;
   o.V = p; p += L * o.RS;
-  o.dX = p; p += bwd ? L * D : 0;
+  o.dX = p; p += bwd ? N * (Lp + D) : 0;   // bwd: per hop dM[L] and qt[D] -- dX = sum_i dM_i (x) qt_i is formed once at the end
   o.vec = p; p += 6 * D;          // fwd: q, Q, qt;  bwd: dq, dy, Q, qt, dQpre, dqt
   o.mv = p; p += 2 * HC_T;
   o.part = p; p += C * Lp;
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(HC_T) hop_fwd_cta_kernel(HopArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x, t = threadIdx.x, w = t >> 5, lane = t & 31;
   const int L = a.L, H = a.H, N = a.N, dh = D / H, Lp = (L + 3) & ~3;
-  const HopCtaSmem o = hop_cta_layout(D, H, L, false);
+  const HopCtaSmem o = hop_cta_layout(D, H, L, N, false);
   const int RS = o.RS;
   float *Xs = sm + o.X, *Ks = sm + o.K, *Vs = sm + o.V, *qv = sm + o.vec, *Qv = qv + D, *qtv = Qv + D, *mv = sm + o.mv,
         *pa = sm + o.part, *pz = sm + o.part2, *sc = sm + o.sc;
@@ -596,9 +596,9 @@ __global__ void __launch_bounds__(HC_T) hop_bwd_cta_kernel(HopArgs a, HopGradArg
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x, t = threadIdx.x, w = t >> 5, lane = t & 31;
   const int L = a.L, H = a.H, N = a.N, dh = D / H, Lp = (L + 3) & ~3;
-  const HopCtaSmem o = hop_cta_layout(D, H, L, true);
+  const HopCtaSmem o = hop_cta_layout(D, H, L, N, true);
   const int RS = o.RS;
-  float *Xs = sm + o.X, *Ks = sm + o.K, *Vs = sm + o.V, *dXs = sm + o.dX, *dqv = sm + o.vec, *dyv = dqv + D, *Qv = dyv + D,
+  float *Xs = sm + o.X, *Ks = sm + o.K, *Vs = sm + o.V, *dMs = sm + o.dX, *qts = dMs + N * Lp, *dqv = sm + o.vec, *dyv = dqv + D, *Qv = dyv + D,
         *qtv = Qv + D, *dQpv = qtv + D, *dqtv = dQpv + D, *mv = sm + o.mv, *part = sm + o.part, *ps = sm + o.sc,
         *dps = sm + o.dps, *dA = sm + o.dA, *dMv = sm + o.dM, *dsum = sm + o.dsum;
   const float sqrt_dh = sqrtf((float)dh);
@@ -607,7 +607,6 @@ __global__ void __launch_bounds__(HC_T) hop_bwd_cta_kernel(HopArgs a, HopGradArg
   const int ldkv = 2 * N * D;
   const int64_t tok0 = (int64_t)b * L;
   load_rows_async<D>(Xs, RS, a.X + tok0 * D, D, len);
-  for (int e = t; e < L * D; e += HC_T) dXs[e] = 0.f;
   if (w == 0) {   // backward of the final layer norm
     const int d0 = lane * VPL;
     float dp[VPL], gm[VPL], xh[VPL], dq[VPL];
@@ -699,7 +698,9 @@ __global__ void __launch_bounds__(HC_T) hop_bwd_cta_kernel(HopArgs a, HopGradArg
       mv[t] = aq;
       mv[HC_T + t] = at;
     }
-    // dK, dV (relu-masked, written once; masked keys get zeros), dX accumulated in shared memory
+    // dK, dV (relu-masked, written once; masked keys get zeros); this hop's rank-1 share of dX is kept as (dM, qt)
+    if (t < D) qts[i * D + t] = qtv[t];
+    for (int j = t; j < len; j += HC_T) dMs[i * Lp + j] = dMv[j];
     for (int e = t; e < L * (D / 4); e += HC_T) {
       const int j = e / (D / 4), d = (e % (D / 4)) * 4, h = d / dh;
       float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
@@ -708,16 +709,11 @@ __global__ void __launch_bounds__(HC_T) hop_bwd_cta_kernel(HopArgs a, HopGradArg
         const float4 vv = *reinterpret_cast<const float4*>(Vs + j * RS + d);
         const float4 q4 = *reinterpret_cast<const float4*>(Qv + d);
         const float4 y4 = *reinterpret_cast<const float4*>(dyv + d);
-        const float4 t4 = *reinterpret_cast<const float4*>(qtv + d);
-        const float da = dA[h * Lp + j], p = ps[h * Lp + j], dm = dMv[j];
+        const float da = dA[h * Lp + j], p = ps[h * Lp + j];
         dk.x = kk.x > 0.f ? da * q4.x : 0.f; dk.y = kk.y > 0.f ? da * q4.y : 0.f;
         dk.z = kk.z > 0.f ? da * q4.z : 0.f; dk.w = kk.w > 0.f ? da * q4.w : 0.f;
         dv.x = vv.x > 0.f ? p * y4.x : 0.f; dv.y = vv.y > 0.f ? p * y4.y : 0.f;
         dv.z = vv.z > 0.f ? p * y4.z : 0.f; dv.w = vv.w > 0.f ? p * y4.w : 0.f;
-        float4* dx = reinterpret_cast<float4*>(dXs + j * D + d);
-        float4 x = *dx;
-        x.x = fmaf(dm, t4.x, x.x); x.y = fmaf(dm, t4.y, x.y); x.z = fmaf(dm, t4.z, x.z); x.w = fmaf(dm, t4.w, x.w);
-        *dx = x;
       }
       float* dst = g.dKV + (tok0 + j) * ldkv + (int64_t)i * 2 * D + d;
       __stcs(reinterpret_cast<float4*>(dst), dk);
@@ -756,19 +752,25 @@ __global__ void __launch_bounds__(HC_T) hop_bwd_cta_kernel(HopArgs a, HopGradArg
   if (t < D) g.dq0[(int64_t)b * D + t] = dqv[t];
   for (int e = t; e < len * (D / 4); e += HC_T) {
     const int j = e / (D / 4), d = (e % (D / 4)) * 4;
-    *reinterpret_cast<float4*>(g.dX + (tok0 + j) * D + d) = *reinterpret_cast<const float4*>(dXs + j * D + d);
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = N - 1; i >= 0; --i) {     // the order the hops were walked in
+      const float dm = dMs[i * Lp + j];
+      const float4 t4 = *reinterpret_cast<const float4*>(qts + i * D + d);
+      x.x = fmaf(dm, t4.x, x.x); x.y = fmaf(dm, t4.y, x.y); x.z = fmaf(dm, t4.z, x.z); x.w = fmaf(dm, t4.w, x.w);
+    }
+    *reinterpret_cast<float4*>(g.dX + (tok0 + j) * D + d) = x;
   }
 }
 
-static bool hop_cta_ok(int D, int H, int L, bool bwd, size_t* smem) {
+static bool hop_cta_ok(int D, int H, int L, int N, bool bwd, size_t* smem) {
   if (D % H != 0 || (D / H) % 16 != 0) return false;
-  *smem = (size_t)hop_cta_layout(D, H, L, bwd).total * sizeof(float);
+  *smem = (size_t)hop_cta_layout(D, H, L, N, bwd).total * sizeof(float);
   return *smem <= 220 * 1024;
 }
 // hop_backward writes every dKV element itself when it takes the CTA-per-sequence path
-bool hop_backward_writes_all_dkv(int D, int H, int L) {
+bool hop_backward_writes_all_dkv(int D, int H, int L, int N) {
   size_t smem;
-  return hop_cta_ok(D, H, L, true, &smem);
+  return hop_cta_ok(D, H, L, N, true, &smem);
 }
 
 size_t hop_smem_bytes(int D, int H, int L, bool bwd) {
@@ -780,7 +782,7 @@ int hop_forward(const HopArgs& a, cudaStream_t st) {
   if (a.H < 1 || a.H > 32 || (32 % a.H) != 0 || (a.D % a.H) != 0)
     return set_error(-1, "attention: num_heads=%d must divide 32 and num_units", a.H);
   size_t csmem;
-  if (hop_cta_ok(a.D, a.H, a.L, false, &csmem)) {
+  if (hop_cta_ok(a.D, a.H, a.L, a.N, false, &csmem)) {
 #define HOP_FWD_CTA(DD)                                                                                               \
   do {                                                                                                                \
     MTAM_CUDA_CHECK(cudaFuncSetAttribute(hop_fwd_cta_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)); \
@@ -816,7 +818,7 @@ int hop_forward(const HopArgs& a, cudaStream_t st) {
 
 int hop_backward(const HopArgs& a, const HopGradArgs& g, cudaStream_t st) {
   size_t csmem;
-  if (hop_cta_ok(a.D, a.H, a.L, true, &csmem)) {
+  if (hop_cta_ok(a.D, a.H, a.L, a.N, true, &csmem)) {
 #define HOP_BWD_CTA(DD)                                                                                               \
   do {                                                                                                                \
     MTAM_CUDA_CHECK(cudaFuncSetAttribute(hop_bwd_cta_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)); \

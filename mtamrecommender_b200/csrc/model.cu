@@ -442,7 +442,7 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   // hops
   phase(h, MTAM_PH_HOP_BWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.dX, 0, (size_t)T * D * sizeof(float), st));
-  if (!hop_backward_writes_all_dkv(D, c.H, L))   // the warp-per-sequence kernels leave masked keys untouched
+  if (!hop_backward_writes_all_dkv(D, c.H, L, N))   // the warp-per-sequence kernels leave masked keys untouched
     MTAM_CUDA_CHECK(cudaMemsetAsync(w.dKV, 0, (size_t)T * 2 * N * D * sizeof(float), st));
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.GB, 0, (size_t)B * 5 * N * L * sizeof(float), st));
   MTAM_TRY(transpose_dd(P + l.Wq, w.WqT, D, N, st));

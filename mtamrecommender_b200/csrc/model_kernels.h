@@ -75,7 +75,7 @@ struct HopGradArgs {
 };
 size_t hop_smem_bytes(int D, int H, int L, bool bwd);
 int hop_forward(const HopArgs& a, cudaStream_t st);
-bool hop_backward_writes_all_dkv(int D, int H, int L);
+bool hop_backward_writes_all_dkv(int D, int H, int L, int N);
 int hop_backward(const HopArgs& a, const HopGradArgs& g, cudaStream_t st);
 int transpose_dd(const float* src, float* dst, int D, int count, cudaStream_t st);
 
