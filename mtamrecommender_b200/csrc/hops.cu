@@ -398,7 +398,7 @@ __device__ __forceinline__ float dot16(const float* __restrict__ row, const floa
 }
 
 struct HopCtaSmem {
-  int RS, X, K, V, dX, vec, mv, part, part2, sc, dps, dA, dM, dsum, total;   // offsets in floats
+  int RS, X, K, V, dX, vec, mv, part, part2, sc, dps, dA, dM, dsum, bs, total;   // offsets in floats
 };
 __host__ __device__ inline HopCtaSmem hop_cta_layout(int D, int H, int L, int N, bool bwd) {
   HopCtaSmem o;
@@ -418,6 +418,7 @@ __host__ __device__ inline HopCtaSmem hop_cta_layout(int D, int H, int L, int N,
   o.dA = p; p += bwd ? H * Lp : 0;
   o.dM = p; p += bwd ? Lp : 0;
   o.dsum = p; p += 32;
+  o.bs = p; p += bwd ? (HC_T / 32) * (D / 4) * 8 : 0;   // per-warp column sums of this sequence's dK | dV rows
   o.total = p;
   return o;
 }
@@ -701,6 +702,7 @@ __global__ void __launch_bounds__(HC_T) hop_bwd_cta_kernel(HopArgs a, HopGradArg
     // dK, dV (relu-masked, written once; masked keys get zeros); this hop's rank-1 share of dX is kept as (dM, qt)
     if (t < D) qts[i * D + t] = qtv[t];
     for (int j = t; j < len; j += HC_T) dMs[i * Lp + j] = dMv[j];
+    float4 sk = make_float4(0.f, 0.f, 0.f, 0.f), sv = sk;   // this thread's share of the column sums (bias gradient)
     for (int e = t; e < L * (D / 4); e += HC_T) {
       const int j = e / (D / 4), d = (e % (D / 4)) * 4, h = d / dh;
       float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = dk;
@@ -718,8 +720,31 @@ __global__ void __launch_bounds__(HC_T) hop_bwd_cta_kernel(HopArgs a, HopGradArg
       float* dst = g.dKV + (tok0 + j) * ldkv + (int64_t)i * 2 * D + d;
       __stcs(reinterpret_cast<float4*>(dst), dk);
       __stcs(reinterpret_cast<float4*>(dst + D), dv);
+      sk.x += dk.x; sk.y += dk.y; sk.z += dk.z; sk.w += dk.w;
+      sv.x += dv.x; sv.y += dv.y; sv.z += dv.z; sv.w += dv.w;
+    }
+    {  // a thread always lands on the same 4 columns (HC_T is a multiple of D/4): lanes, then warps, in a fixed order
+      float* bsw = sm + o.bs;
+#pragma unroll
+      for (int off = D / 4; off < 32; off <<= 1) {
+        sk.x += __shfl_xor_sync(0xffffffffu, sk.x, off); sk.y += __shfl_xor_sync(0xffffffffu, sk.y, off);
+        sk.z += __shfl_xor_sync(0xffffffffu, sk.z, off); sk.w += __shfl_xor_sync(0xffffffffu, sk.w, off);
+        sv.x += __shfl_xor_sync(0xffffffffu, sv.x, off); sv.y += __shfl_xor_sync(0xffffffffu, sv.y, off);
+        sv.z += __shfl_xor_sync(0xffffffffu, sv.z, off); sv.w += __shfl_xor_sync(0xffffffffu, sv.w, off);
+      }
+      if (lane < D / 4) {
+        float4* dstb = reinterpret_cast<float4*>(bsw + ((w * (D / 4)) + (t % (D / 4))) * 8);
+        dstb[0] = sk; dstb[1] = sv;
+      }
     }
     __syncthreads();
+    for (int c = t; c < 2 * D; c += HC_T) {
+      const int half = c / D, dc = c % D;
+      float s = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < HC_T / 32; ++ww) s += sm[o.bs + ((ww * (D / 4)) + dc / 4) * 8 + half * 4 + (dc & 3)];
+      g.BKV[((int64_t)b * N + i) * 2 * D + c] = s;
+    }
     if (t < D) {
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll

@@ -39,7 +39,7 @@ struct Workspace {
   float *Qin, *Qr, *Qt, *AA, *PA, *ZZ, *DK, *GT, *XH, *RSTD, *XHF, *RSTDF, *pred;
   float *tlogit, *lse, *loss_origin;
   // gradients of activations
-  float *dpred, *dX, *dKV, *DOUT, *DQP, *DQT, *GB, *dq0, *WqT, *WtT, *dGX, *vec_partial, *dR, *dE2, *dEp, *dEu;
+  float *dpred, *dX, *dKV, *DOUT, *DQP, *DQT, *BKV, *GB, *dq0, *WqT, *WtT, *dGX, *vec_partial, *dR, *dE2, *dEp, *dEu;
   // partial-sum buffers and device scalars
   float *l2_partial, *sq_partial, *ce_partial, *norm_partial, *dev_scalars;  // dev_scalars: [16]
   float *bU, *bIP, *bdot, *bbpos, *browsum, *bcolsum, *bloss, *bdU, *bdIP, *bdINp, *bdIN, *bdbneg, *bl2, *bsq;  // BPRMF
@@ -219,6 +219,7 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
     w.dKV = b.take<float>(T * 2 * N * D);
     w.DOUT = b.take<float>(B * N * D);
     w.DQP = b.take<float>(B * N * D);
+    w.BKV = b.take<float>(B * 2 * N * D);
     w.DQT = b.take<float>(B * N * D);
     w.GB = b.take<float>(B * 5 * N * L);
     w.dq0 = b.take<float>(B * D);
@@ -442,14 +443,15 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   // hops
   phase(h, MTAM_PH_HOP_BWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.dX, 0, (size_t)T * D * sizeof(float), st));
-  if (!hop_backward_writes_all_dkv(D, c.H, L, N))   // the warp-per-sequence kernels leave masked keys untouched
+  const bool kv_bias_fused = hop_backward_writes_all_dkv(D, c.H, L, N);   // = the CTA-per-sequence path is taken
+  if (!kv_bias_fused)   // the warp-per-sequence kernels leave masked keys untouched
     MTAM_CUDA_CHECK(cudaMemsetAsync(w.dKV, 0, (size_t)T * 2 * N * D * sizeof(float), st));
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.GB, 0, (size_t)B * 5 * N * L * sizeof(float), st));
   MTAM_TRY(transpose_dd(P + l.Wq, w.WqT, D, N, st));
   MTAM_TRY(transpose_dd(P + l.Wt, w.WtT, D, N, st));
   HopArgs a = hop_args(h, bt);
   HopGradArgs g;
-  g.dpred = w.dpred; g.WqT = w.WqT; g.WtT = w.WtT; g.dX = w.dX; g.dKV = w.dKV; g.DOUT = w.DOUT; g.DQP = w.DQP;
+  g.dpred = w.dpred; g.WqT = w.WqT; g.WtT = w.WtT; g.dX = w.dX; g.dKV = w.dKV; g.DOUT = w.DOUT; g.DQP = w.DQP; g.BKV = w.BKV;
   g.DQT = w.DQT; g.GB = w.GB; g.dq0 = w.dq0;
   MTAM_TRY(hop_backward(a, g, st));
   // hop parameter gradients
@@ -463,6 +465,9 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
     cb.job[4] = ColsumJob{w.DQP, N * D, nullptr, 0, N * D, G + l.bq};
     cb.job[5] = ColsumJob{w.GB, 5 * N * L, nullptr, 0, 5 * N * L, G + l.gate};
     cb.n_jobs = 6;
+    // the K,V bias gradient: the CTA-per-sequence backward leaves per-sequence column sums of dKV ([B, 2ND] instead of
+    // a second pass over the [B*L, 2ND] rows)
+    if (kv_bias_fused) cb.job[cb.n_jobs++] = ColsumJob{w.BKV, 2 * N * D, nullptr, 0, 2 * N * D, G + l.bkv};
     MTAM_TRY(colsum_multi_f32(cb, B, st));
   }
   // dWq_i = Qin_i^T dQpre_i, dWt_i = Qin_i^T dQt_i: the N hops of each in one batched split-K launch
@@ -470,7 +475,7 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
                                 w.gemm_ws, w.gemm_ws_bytes, st));
   MTAM_TRY(gemm_atb_batched_f32(N, D, D, B, w.Qin, D, (int64_t)B * D, w.DQT, N * D, D, G + l.Wt, D, (int64_t)D * D,
                                 w.gemm_ws, w.gemm_ws_bytes, st));
-  MTAM_TRY(colsum(h, w.dKV, 2 * N * D, nullptr, 0, (int)T, 2 * N * D, G + l.bkv, st));
+  if (!kv_bias_fused) MTAM_TRY(colsum(h, w.dKV, 2 * N * D, nullptr, 0, (int)T, 2 * N * D, G + l.bkv, st));
   MTAM_TRY(gemm(h, 1, 0, D, 2 * N * D, (int)T, w.X, D, w.dKV, 2 * N * D, G + l.Wkv, 2 * N * D, e0, st));
   MTAM_TRY(gemm(h, 0, 1, (int)T, D, 2 * N * D, w.dKV, 2 * N * D, P + l.Wkv, 2 * N * D, w.dX, D, eacc, st));
   // T-GRU

@@ -72,6 +72,7 @@ struct HopGradArgs {
   float* DQT;                  // [B][N][D]  d(q Wt)
   float* GB;                   // [B][N*5*L] per-sequence gate-parameter gradients, pre-zeroed
   float* dq0;                  // [B][D]
+  float* BKV;                  // [B][N][2D] per-sequence column sums of dKV (CTA-per-sequence path only)
 };
 size_t hop_smem_bytes(int D, int H, int L, bool bwd);
 int hop_forward(const HopArgs& a, cudaStream_t st);
