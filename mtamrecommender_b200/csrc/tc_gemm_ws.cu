@@ -30,8 +30,9 @@ using namespace tc;
 namespace {
 
 constexpr int WM = 128, WK = 32;
-constexpr int NSA = 3, NSB = 3;
-constexpr int kWEpi = 0, kWA = 4, kWB = 8, kWMma = 12, kWThreads = 13 * 32;
+constexpr int NSA = 3, NSB = 4;
+constexpr int kBGroups = 3;                        // B-producer groups of two warps, one chunk in flight each
+constexpr int kWEpi = 0, kWA = 4, kWB = 8, kWMma = kWB + 2 * kBGroups, kWThreads = (kWMma + 1) * 32;
 constexpr uint32_t COL_ACC = 0, COL_A = 256;      // accumulators: 2 x BN columns; A ring: NSA x (32 hi + 32 lo)
 
 struct WsArgs {
@@ -170,17 +171,18 @@ __global__ void __launch_bounds__(kWThreads, 1) tc_gemm_ws_kernel(const WsArgs g
       stash(vb2, c + 1);
     }
   } else if (warp >= kWB && warp < kWMma) {
-    // ================= B producers: two groups of two warps take alternate chunks =================
+    // ================= B producers: kBGroups groups of two warps take the chunks round-robin =================
     // fence.proxy.async (a MEMBAR) would wait for a prefetched chunk's global loads, so instead of prefetching
-    // inside one thread, one group's load latency is overlapped with the other group's split + store.
+    // inside one thread, one group's load latency is overlapped with the other groups' split + store: kBGroups chunks
+    // (16 KB each at BN = 128) are in flight per SM, enough to cover the HBM latency.
     const int grp = (warp - kWB) >> 1, pt = tid & 63;
     constexpr int R = TB ? BN : 32, NBLK = TB ? 1 : BN / 32;   // tile = NBLK blocks of [R x 32] floats
     constexpr int PER = R * 8 * NBLK / 64;
     const bool vb = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
     ChunkIter it;
     it.init(g, units);
-    if (grp == 1 && it.valid) it.next(g, units);
-    for (int c = grp; it.valid; c += 2) {
+    for (int s = 0; s < grp && it.valid; ++s) it.next(g, units);
+    for (int c = grp; it.valid; c += kBGroups) {
       const int n0 = it.nt * BN, k0 = it.k0, kend = it.kend;
       const int r0 = TB ? n0 : k0, c0 = TB ? k0 : n0, rmax = TB ? g.N : kend, cmax = TB ? kend : g.N;
       float4 v[PER];
@@ -216,8 +218,7 @@ __global__ void __launch_bounds__(kWThreads, 1) tc_gemm_ws_kernel(const WsArgs g
       fence_proxy_async();
       mbar_arrive(&bars.b_full[sb]);
       if (pt == 0) WS_TRACE(2, c);
-      it.next(g, units);
-      if (it.valid) it.next(g, units);
+      for (int s = 0; s < kBGroups && it.valid; ++s) it.next(g, units);
     }
   } else if (warp == kWMma) {
     // ================= MMA issuer =================
