@@ -70,3 +70,17 @@ def test_calculate_topk_host_restatement():
     top = np.array([[5, 7, 9], [1, 2, 3], [4, 4, 4]])
     hr, nd = base_model.calculate_topK(None, 3, top, [9, 8, 4], 0, 3)
     assert abs(hr - 2 / 3) < 1e-12 and abs(nd - (math.log(2) / math.log(4) + 1.0) / 3) < 1e-12
+
+
+def test_combine_lse_is_logsumexp_over_shards():
+    """The sharded softmax's host-side combination (parallel.combine_lse): [n_shards, B] per-shard log-sum-exps -> the
+    log-sum-exp over the whole catalogue, also when one shard dominates by hundreds of units."""
+    import torch
+    from mtamrecommender_b200.parallel import combine_lse, shard_rows
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(6, 1000, generator=g, dtype=torch.float64) * 5
+    logits[0, 3] = 400.0
+    S = shard_rows(1000, 8)
+    per = torch.stack([torch.logsumexp(logits[:, r * S:(r + 1) * S], dim=1) for r in range(8)])
+    assert torch.allclose(combine_lse(per), torch.logsumexp(logits, dim=1), rtol=1e-13, atol=0)
+    assert shard_rows(10_000_003, 8) == 1_250_001 and shard_rows(7, 8) == 1
