@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
 
   // the step's saved activations are independent of the recurrence: the loads of step t-1 are issued at the top of
   // step t and land while its two matrix-vector loops run
-  struct StepIn { float r, u, c, Tg, hold, x, dl; };
+  struct StepIn { float r, u, c, Tg, hold, x, dl, dx; };
   auto fetch = [&](int t, StepIn (&v)[2]) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
       v[i].hold = ld_nc_pred(Hs + tok * D + n, live);      // h_{t-1}: Hs is shifted by one (leading zero row)
       v[i].x = ld_nc_pred(X + tok * D + n, live);
       v[i].dl = ld_nc_pred(timelast + tok, live);
+      v[i].dx = ld_cg_pred(dX + tok * D + n, live);         // dX[t] is updated in place: read it a step ahead too
     }
   };
   // part of this thread's weight column lives in registers for all L steps (D <= 64): the candidate path
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
         float a = fmaxf(apre, 0.f), s = fmaxf(spre, 0.f);
         float dpa = (apre > 0.f) ? dpT * kw2 : 0.f;
         float dps = (spre > 0.f) ? dpT * tw12 : 0.f;
-        dX[tok * D + n] += dpa * kw1;
+        dX[tok * D + n] = fmaf(dpa, kw1, cur[i].dx);   // each element is read (a step earlier) and written exactly once
         dhacc[i] = fmaf(dpa, hw1, dhacc[i]);
         g[0] = fmaf(dpa, x, g[0]); g[1] += dpa; g[2] = fmaf(dpa, hold, g[2]);
         g[3] = fmaf(dps, dl, g[3]); g[4] += dps;
