@@ -451,11 +451,19 @@ __global__ void __launch_bounds__(HC_T) hop_fwd_cta_kernel(HopArgs a) {
       const float* Wq = a.Wq + (int64_t)i * D * D + (int64_t)part * KP * D + d;
       const float* Wt = a.Wt + (int64_t)i * D * D + (int64_t)part * KP * D + d;
       float aq = 0.f, at = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < KP; ++k) {
-        const float qk = qv[part * KP + k];
-        aq = fmaf(qk, __ldg(Wq + k * D), aq);
-        at = fmaf(qk, __ldg(Wt + k * D), at);
+      // the weight columns come from L2: 2 x WB loads in flight per thread, then their FMAs (same order as a plain loop)
+      constexpr int WB = KP < 16 ? KP : 16;
+#pragma unroll
+      for (int k0 = 0; k0 < KP; k0 += WB) {
+        float wq[WB], wt[WB];
+#pragma unroll
+        for (int j = 0; j < WB; ++j) { wq[j] = __ldg(Wq + (k0 + j) * D); wt[j] = __ldg(Wt + (k0 + j) * D); }
+#pragma unroll
+        for (int j = 0; j < WB; ++j) {
+          const float qk = qv[part * KP + k0 + j];
+          aq = fmaf(qk, wq[j], aq);
+          at = fmaf(qk, wt[j], at);
+        }
       }
       mv[t] = aq;
       mv[HC_T + t] = at;
@@ -760,9 +768,16 @@ __global__ void __launch_bounds__(HC_T) hop_bwd_cta_kernel(HopArgs a, HopGradArg
       const float* WqT = g.WqT + (int64_t)i * D * D + (int64_t)pt * KP * D + d;
       const float* WtT = g.WtT + (int64_t)i * D * D + (int64_t)pt * KP * D + d;
       float acc = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < KP; ++k)
-        acc = fmaf(dQpv[pt * KP + k], __ldg(WqT + k * D), fmaf(dqtv[pt * KP + k], __ldg(WtT + k * D), acc));
+      constexpr int WB = KP < 16 ? KP : 16;
+#pragma unroll
+      for (int k0 = 0; k0 < KP; k0 += WB) {
+        float wq[WB], wt[WB];
+#pragma unroll
+        for (int j = 0; j < WB; ++j) { wq[j] = __ldg(WqT + (k0 + j) * D); wt[j] = __ldg(WtT + (k0 + j) * D); }
+#pragma unroll
+        for (int j = 0; j < WB; ++j)
+          acc = fmaf(dQpv[pt * KP + k0 + j], wq[j], fmaf(dqtv[pt * KP + k0 + j], wt[j], acc));
+      }
       mv[t] = acc;
     }
     __syncthreads();
