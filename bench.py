@@ -200,6 +200,22 @@ def cpu_baseline(w, seconds_budget=25.0):
 
 # ---------------------------------------------------------------------------------------------
 def run_cuda(args, w):
+    """Stdout carries exactly one JSON line: while the run is in progress file descriptor 1 points at stderr, so that
+    whatever a native library prints there (NCCL's version banner at NCCL_DEBUG=VERSION, for one) cannot precede it."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_cuda(args, w)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if line is not None:
+        print(line, flush=True)
+
+
+def _run_cuda(args, w):
     import torch
     import torch.distributed as dist
     from mtamrecommender_b200 import engine as E
@@ -372,8 +388,7 @@ def run_cuda(args, w):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if out is not None:
-        print(json.dumps(out), flush=True)
+    return json.dumps(out) if out is not None else None
 
 
 def eval_topk_bench(eng, batches, w, pk, k=50, reps=10):
