@@ -84,3 +84,27 @@ def test_combine_lse_is_logsumexp_over_shards():
     per = torch.stack([torch.logsumexp(logits[:, r * S:(r + 1) * S], dim=1) for r in range(8)])
     assert torch.allclose(combine_lse(per), torch.logsumexp(logits, dim=1), rtol=1e-13, atol=0)
     assert shard_rows(10_000_003, 8) == 1_250_001 and shard_rows(7, 8) == 1
+
+
+def test_bench_stdout_carries_only_the_json_line(tmp_path):
+    """bench.run_cuda points file descriptor 1 at stderr while the arm runs: output of native libraries (NCCL's banner)
+    and stray prints end up on stderr, the JSON line alone on stdout."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "t.py"
+    script.write_text(
+        "import ctypes, sys\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import bench\n"
+        "def fake(args, w):\n"
+        "    libc = ctypes.CDLL(None); libc.puts(b'banner from a C library'); libc.fflush(None)\n"
+        "    print('python-level noise')\n"
+        "    return '{\"ok\": 1}'\n"
+        "bench._run_cuda = fake\n"
+        "bench.run_cuda(None, None)\n")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == '{"ok": 1}'
+    assert "banner from a C library" in r.stderr and "python-level noise" in r.stderr
