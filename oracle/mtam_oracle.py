@@ -33,6 +33,9 @@ TA_SASREC = "TA_SASREC"        # 'Time_Aware_Self_Attention_Model'      Model/at
 TISASREC = "TISASREC"          # 'Ti_Self_Attention_Model'              Model/attention_baseline_models.py:66-84
 BPRMF = "BPRMF"                # 'bpr'                                  Model/BPRMF.py:10-59
 KINDS = (MTAM, PISTREC, SASREC, TA_SASREC, TISASREC, BPRMF)
+# Oracle-only so far (the next widening step): no CUDA path is built for these yet.
+MTAM_VIA_T_GRU = "MTAM_VIA_T_GRU"   # 'MTAM_via_T_GRU': the T-GRU outputs are the memory   Model/MTAMRec_model.py:167-204
+NEXT_KINDS = (MTAM_VIA_T_GRU,)
 
 MASK_VALUE = float(-2 ** 32 + 1)   # time_aware_attention.py:392 -> fp32 -4294967296.0
 LN_EPS_BLOCK = 1e-8                 # Time_Aware_Attention.normalize  time_aware_attention.py:7-34
@@ -88,8 +91,11 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
     if cfg.kind == BPRMF:
         s["embedding_layer/item_b"] = (cfg.V, 1)       # BPRMF.py:34-35
         return s
-    if cfg.kind == MTAM:
+    if cfg.kind in (MTAM, MTAM_VIA_T_GRU):
         g = "ShortTermIntentEncoder/"
+        if cfg.kind == MTAM_VIA_T_GRU:                 # layer_norm(short_term_intent) inside this scope, MTAMRec_model.py:186
+            s[g + "LayerNorm/beta"] = (D,)
+            s[g + "LayerNorm/gamma"] = (D,)
         s[g + "gates/kernel"] = (2 * D, 2 * D)         # time_aware_rnn.py:166-169
         s[g + "gates/bias"] = (2 * D,)
         s[g + "candidate/kernel"] = (2 * D, D)
@@ -104,13 +110,13 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
         for dn in ("dense", "dense_1", "dense_2"):       # Q, K, V  (time_aware_attention.py:249-253)
             s[b + dn + "/kernel"] = (D, D)
             s[b + dn + "/bias"] = (D,)
-        if cfg.kind in (MTAM, PISTREC, TA_SASREC):
+        if cfg.kind in (MTAM, MTAM_VIA_T_GRU, PISTREC, TA_SASREC):
             s[b + att + "/_time_input_w"] = (D, D)
             for v in GATE_LIVE + GATE_DEAD:
                 s[b + att + "/" + v] = (Tq, L)
         s[b + att + "/ln/beta"] = (D,)
         s[b + att + "/ln/gamma"] = (D,)
-    top = "NextItemDecoder" if cfg.kind == MTAM else "UserHistoryEncoder"
+    top = "NextItemDecoder" if cfg.kind in (MTAM, MTAM_VIA_T_GRU) else "UserHistoryEncoder"
     s[top + "/LayerNorm/beta"] = (D,)
     s[top + "/LayerNorm/gamma"] = (D,)
     return s
@@ -341,16 +347,22 @@ def forward(cfg: OracleConfig, params: Dict[str, torch.Tensor], feed: Dict[str, 
 
     X = torch.relu(torch.cat([Ei, Ec], 2) @ p["position_embedding/dense4emb/kernel"]) + Ep   # :95-103
     out["X"] = X
-    if cfg.kind == MTAM:
+    if cfg.kind in (MTAM, MTAM_VIA_T_GRU):
         g = "ShortTermIntentEncoder/"
         rnn = tgru_new(X, fl["timelast_list"], seq_len, p, g)
         out["rnn"] = rnn
         pos = (seq_len - 2).clamp(min=0)                               # mask_index-1, MTAMRec_model.py:75-79
         q = rnn[torch.arange(B), pos][:, None, :]                      # gather_indexes net_utils.py:82-92
+        memory = X                                                     # MTAM: user_history = the embedded behaviours (:65)
+        if cfg.kind == MTAM_VIA_T_GRU:
+            # the memory is the T-GRU's output sequence (zeros from step seq_len-1 on, dynamic_rnn), keys still masked
+            # by seq_length; the query is layer-normed first                       MTAMRec_model.py:180-189
+            memory = rnn
+            q = _ln(q[:, 0], p[g + "LayerNorm/gamma"], p[g + "LayerNorm/beta"], LN_EPS_FINAL)[:, None, :]
         out["short_term_intent"] = q[:, 0]
         tq = fl["target_item_time"][:, None]
         for i in range(N):
-            q = attention_block("time_aware", q, X, tq, fl["time_list"], seq_len,
+            q = attention_block("time_aware", q, memory, tq, fl["time_list"], seq_len,
                                 torch.ones_like(seq_len), p,
                                 f"NextItemDecoder/decoder/num_blocks_{i}/", "vanilla_attention", H)
         hyb = q.reshape(B, D)

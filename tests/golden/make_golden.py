@@ -20,6 +20,8 @@ CASES = {
     "TISASREC": dict(L=7, D=32, H=2, N=2, user_count=12, item_count=60, category_count=5),
     "SASREC": dict(L=7, D=32, H=2, N=2, user_count=12, item_count=60, category_count=5),
     "BPRMF": dict(L=7, D=32, H=1, N=1, user_count=12, item_count=60, category_count=5),
+    # oracle-only so far (O.NEXT_KINDS): pinned now so that the CUDA path of the next round has a fixed target
+    "MTAM_VIA_T_GRU": dict(L=9, D=32, H=2, N=2, user_count=12, item_count=60, category_count=5),
 }
 
 

@@ -134,10 +134,17 @@ def test_record_construction_and_feed_padding():
 
 
 # ---- finite differences ----------------------------------------------------------------------
-@pytest.mark.parametrize("kind", [O.MTAM, O.PISTREC, O.TISASREC, O.SASREC])
+@pytest.mark.parametrize("kind", [O.MTAM, O.PISTREC, O.TISASREC, O.SASREC, O.MTAM_VIA_T_GRU])
 def test_oracle_gradients_by_finite_differences(kind):
     cfg = O.OracleConfig(kind=kind, L=6, D=32, H=2, N=2, user_count=5, item_count=20, category_count=3)
     P = {k: v.astype(np.float64) for k, v in O.init_params(cfg, 8).items()}
+    if kind == O.MTAM_VIA_T_GRU:
+        # its memory rows are exactly zero from step seq_len-1 on, so with the zero-initialised biases the K,V ReLU
+        # pre-activations of those (unmasked) keys sit exactly on the kink, where no derivative exists: move off it
+        brng = np.random.default_rng(5)
+        for k in P:
+            if k.endswith("/bias"):
+                P[k] = P[k] + 0.1 * brng.standard_normal(P[k].shape)
     feed = O.synth_batch(cfg, 4, 9)
     fwd, grads, _ = O.loss_and_grads(cfg, P, feed)
     rng = np.random.default_rng(0)
@@ -156,3 +163,31 @@ def test_oracle_gradients_by_finite_differences(kind):
         fd = (loss_at(Pp) - loss_at(Pm)) / (2 * eps)
         an = float((grads[name] * d).sum())
         assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)) + 1e-8, (name, fd, an)
+
+
+def test_mtam_via_t_gru_restatement_structure():
+    """MTAM_via_T_GRU (Model/MTAMRec_model.py:167-204, oracle-only so far): the memory is the T-GRU output sequence --
+    zero from step seq_len-1 on (dynamic_rnn) yet unmasked up to seq_len -- and the query is layer-normed inside the
+    ShortTermIntentEncoder scope, which adds exactly one LayerNorm pair to MTAM's variables."""
+    kw = dict(L=8, D=32, H=2, N=2, user_count=9, item_count=40, category_count=4)
+    a, b = O.OracleConfig(kind=O.MTAM, **kw), O.OracleConfig(kind=O.MTAM_VIA_T_GRU, **kw)
+    extra = set(O.param_shapes(b)) - set(O.param_shapes(a))
+    assert extra == {"ShortTermIntentEncoder/LayerNorm/beta", "ShortTermIntentEncoder/LayerNorm/gamma"}
+    assert set(O.param_shapes(a)) <= set(O.param_shapes(b))
+    P = {k: torch.tensor(v, dtype=torch.float64) for k, v in O.init_params(b, 3).items()}
+    feed = O.synth_batch(b, 5, 11)
+    out = O.forward(b, P, feed)
+    n = feed["seq_length"]
+    rnn = out["rnn"].numpy()
+    for r in range(5):
+        assert np.all(rnn[r, n[r] - 1:] == 0) and np.any(rnn[r, n[r] - 2] != 0)
+    q = out["short_term_intent"].numpy()                 # layer-normed query: zero mean, unit variance (gamma 1, beta 0)
+    assert np.allclose(q.mean(1), 0, atol=1e-12) and np.allclose(q.var(1), 1, atol=1e-6)
+    # the embedded behaviours reach the prediction only through the T-GRU now: changing the mask-token step's item
+    # (position seq_len-1, which the T-GRU never consumes) leaves pred unchanged, unlike in MTAM
+    f2 = {k: v.copy() for k, v in feed.items()}
+    for r in range(5):
+        f2["item_list"][r, n[r] - 1] = 3
+    Pa = {k: v for k, v in P.items() if k in O.param_shapes(a)}
+    assert np.array_equal(O.forward(b, P, f2)["pred"].numpy(), out["pred"].numpy())
+    assert not np.array_equal(O.forward(a, Pa, f2)["pred"].numpy(), O.forward(a, Pa, feed)["pred"].numpy())
