@@ -153,7 +153,7 @@ def run_reference(args, w):
     from oracle.cpu_port import TorchPort
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = min(w["B"], args.cpu_batch)
+    Bs = w["B"] if args.cpu_batch <= 0 else min(w["B"], args.cpu_batch)   # default: the workload's own batch size
     cfg = O.OracleConfig(kind=O.MTAM, L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
                          item_count=w["items"], category_count=w["cats"])
     port = TorchPort(cfg, O.init_params(cfg, 1234))
@@ -169,8 +169,12 @@ def run_reference(args, w):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": args.workload, **{k: w[k] for k in ("B", "L", "D", "N", "H", "items")},
-                      "note": "TF 1.14 cannot run in this image; torch-CPU fp32 port of the same graph (oracle/cpu_port.py)"},
+           "config": {"workload": args.workload, "model": "MTAM", "batch_per_gpu": Bs, "global_batch": Bs,
+                      "seq_len": w["L"], "num_units": w["D"], "num_blocks": w["N"], "num_heads": w["H"],
+                      "item_count": w["items"], "user_count": w["users"], "category_count": w["cats"],
+                      "host_processes": 1,
+                      "note": "TF 1.14 cannot run in this image; torch-CPU fp32 port of the same graph (oracle/cpu_port.py); "
+                              "one host process whatever --gpus says"},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -182,14 +186,14 @@ def cpu_baseline(w, seconds_budget=25.0):
     from oracle.cpu_port import TorchPort
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = min(w["B"], 256)
+    Bs = w["B"]
     cfg = O.OracleConfig(kind=O.MTAM, L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
                          item_count=w["items"], category_count=w["cats"])
     port = TorchPort(cfg, O.init_params(cfg, 1234))
     feed = make_feeds(dict(w, B=Bs), 1, 99)[0]
     port.train_step(feed, LR)
     n, t0 = 0, time.perf_counter()
-    while n < 3 or (time.perf_counter() - t0 < seconds_budget / 3 and n < 8):
+    while n < 3 or (time.perf_counter() - t0 < seconds_budget / 2 and n < 16):
         port.train_step(feed, LR)
         n += 1
     dt = time.perf_counter() - t0
@@ -229,10 +233,6 @@ def _run_cuda(args, w):
     dev = f"cuda:{local}"
     torch.cuda.set_device(dev)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/mtam_nccl_%h_%p.log")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # that level printf()s the banner to stdout
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(dev))
     mc = E.ModelConfig(kind=w["kind"], max_batch=w["B"], L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
                        item_count=w["items"], category_count=w["cats"],
@@ -511,12 +511,11 @@ def main():
     ap.add_argument("--gemm-mode", default="tf32x3", choices=["tf32x3", "fp32"],
                     help="dense contractions: tcgen05 3-term-split TF32 (fp32-class accuracy) or exact fp32 FFMA")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-batch", type=int, default=256, help="sequences per step of the CPU arm (bounded sample)")
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="sequences per step of the CPU arm; 0 = the workload's own batch size (the default)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
-        if args.steps == 20 and args.warmup == 5:
-            args.steps, args.warmup = 5, 1
         run_reference(args, w)
     else:
         run_cuda(args, w)

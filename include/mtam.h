@@ -295,6 +295,15 @@ int mtam_score_topk(int32_t gemm_mode, const float* pred, int32_t B, int32_t D, 
                     int32_t row_begin, int32_t row_end, int32_t k, int32_t* idx_out, float* score_out,
                     void* workspace, size_t workspace_bytes, void* stream);
 size_t mtam_score_topk_workspace(int32_t B, int32_t rows, int32_t k);
+/* The filter pass of mtam_score_topk (MTAM_GEMM_TF32X3) on its own: bmax[b*ld + j] = max over the items of bucket j
+ * (bucket_size = 16 or 64 consecutive rows of item_table[0, rows)) of <pred_b, row> computed on tcgen05 (3xTF32).
+ * ld >= 8*ceil(ceil(rows/128)*(128/bucket_size) / 8) floats.  Entries past ceil(rows/bucket_size) are unspecified.
+ * Exposed so that the filter can be checked against exhaustive scoring (base_model.py:194-195). */
+int mtam_score_bucket_max(const float* pred, int32_t B, int32_t D, const float* item_table, int32_t rows,
+                          int32_t bucket_size, float* bmax, int32_t ld, void* stream);
+/* Tuning: row ranges longer than `rows` use buckets of 64 items in the filter pass, shorter ones buckets of 16
+ * (default 2^21; 0 restores it).  Process-wide; the result of mtam_score_topk does not depend on it. */
+int mtam_set_topk_bucket_crossover(int32_t rows);
 
 /* Softmax cross-entropy of base_model.output (base_model.py:316-321) against item rows [table, table + rows*D) -- the
  * whole catalogue or one shard of a row-sharded table (sharded log-sum-exp).  `target` is relative to the

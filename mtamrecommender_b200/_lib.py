@@ -98,6 +98,8 @@ SIGNATURES = {
     "mtam_eval_topk": (C.c_int, [_VP, C.POINTER(Batch), _I32, _VP, _VP, _VP]),
     "mtam_score_topk": (C.c_int, [_I32, _VP, _I32, _I32, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _SZ, _VP]),
     "mtam_score_topk_workspace": (_SZ, [_I32, _I32, _I32]),
+    "mtam_score_bucket_max": (C.c_int, [_VP, _I32, _I32, _VP, _I32, _I32, _VP, _I32, _VP]),
+    "mtam_set_topk_bucket_crossover": (C.c_int, [_I32]),
     "mtam_merge_topk": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _VP, _VP, _VP]),
     "mtam_softmax_ce_workspace": (_SZ, [_I32, _I32, _I32]),
     "mtam_softmax_ce_forward": (C.c_int, [_I32, _VP, _I32, _I32, _VP, _I32, _VP, _VP, _VP, _VP, _SZ, _VP]),

@@ -192,19 +192,22 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
     constexpr int PER = 64 * (D / 4) / kProd;
     const int nu = n * UPT;
     float4 ra[PER];
-    // unit u: wait for its bulk copy, pull this thread's pieces out of the staging slot, hand the slot back
+    // unit u: wait for its bulk copy and pull this thread's pieces out of the staging slot.  The slot is handed back
+    // in stash(), AFTER the split stores have consumed the loaded registers: an mbarrier arrive does not wait for
+    // loads still in flight (they compile to generic LD.E.128 with their own scoreboard), so arriving right after
+    // issuing them lets the loader's next bulk copy overwrite the slot under them (seen as rare wrong logits of the
+    // tile two ahead, round-1 GPUTEST failure at 10 M rows).
     auto fetch = [&](float4 (&r)[PER], int u) {
       const int sl = u % NSG;
       const int x0 = xt_begin * BX + u * 64;
       mbar_wait(&bars.stg_full[sl], (u / NSG) & 1);
-      const float4* src = reinterpret_cast<const float4*>(Stg + sl * SLOT);
+      const uint32_t src = smem_u32(Stg + sl * SLOT);
 #pragma unroll
       for (int j = 0; j < PER; ++j) {
         const int q = pt + j * kProd;
-        r[j] = src[q];
+        r[j] = lds128(src + (uint32_t)q * 16u);
         if (x0 + q / (D / 4) >= xmax) r[j] = make_float4(0.f, 0.f, 0.f, 0.f);   // rows the copy did not cover
       }
-      mbar_arrive(&bars.stg_empty[sl]);
     };
     auto stash = [&](const float4 (&r)[PER], int u) {
       const int i = u / UPT, hrow = (u % UPT) * 64;
@@ -217,6 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
         const int row = hrow + q / (D / 4), c4 = q % (D / 4);
         store_chunk_split<false>(xs + (c4 >> 3) * XT, xs + KC * XT + (c4 >> 3) * XT, row, c4 & 7, r[j]);
       }
+      mbar_arrive(&bars.stg_empty[u % NSG]);     // every register of r[] has been read by the stores above
       if (hrow + 64 == BX) {
         fence_proxy_async();
         mbar_arrive(&bars.xk_full[st]);

@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(256) hr_ndcg_kernel(const int32_t* __restrict_
 constexpr int kBucketPad = 14;                       // buckets kept beyond k
 constexpr int kMaxSel = KMAX + kBucketPad;           // 78
 // bucket size: per pred row the maxima cost rows/bs*8 B of traffic and the rescoring (k+14)*bs*4D B, equal near 2 M rows
-constexpr int kSmallBucketMaxRows = 1 << 21;
+constexpr int kSmallBucketMaxRowsDefault = 1 << 21;
+static int g_small_bucket_max_rows = kSmallBucketMaxRowsDefault;   // mtam_set_topk_bucket_crossover
 constexpr int kMaxGroups = 16384 - 1;                    // groups of 32 buckets per pred row that fit in shared memory
 
 __device__ __forceinline__ uint32_t order_key(float x) {   // monotone float -> uint32 (every real key > 0)
@@ -445,7 +446,7 @@ static size_t refine_smem_bytes(int D, int n_buckets, int bs, int n_sel, int k) 
 struct TcTopkPlan { int bs, ld, n_buckets, n_sel, chunk_rows; };
 static TcTopkPlan tc_topk_plan(int B, int rows, int k, size_t ws_bytes) {
   TcTopkPlan p;
-  p.bs = rows > kSmallBucketMaxRows ? 64 : 16;
+  p.bs = rows > g_small_bucket_max_rows ? 64 : 16;
   p.ld = cdiv(cdiv(rows, 128) * (128 / p.bs), 8) * 8;
   p.n_buckets = cdiv(rows, p.bs);
   p.n_sel = std::min(p.n_buckets, k + kBucketPad);
@@ -455,7 +456,7 @@ static TcTopkPlan tc_topk_plan(int B, int rows, int k, size_t ws_bytes) {
   return p;
 }
 static size_t tc_topk_workspace_bytes(int B, int rows) {
-  const int bs = rows > kSmallBucketMaxRows ? 64 : 16;
+  const int bs = rows > g_small_bucket_max_rows ? 64 : 16;
   const size_t ld = (size_t)cdiv(cdiv(rows, 128) * (128 / bs), 8) * 8;
   // bucket maxima of up to B pred rows; beyond 1 GiB the pred rows are processed in chunks of >= 128
   const size_t cap_rows = std::max<size_t>(128, ((size_t)1 << 30) / (ld * sizeof(float)) / 128 * 128);
@@ -557,6 +558,21 @@ int mtam_score_topk(int32_t gemm_mode, const float* pred, int32_t B, int32_t D, 
     return mtam::set_error(MTAM_ERR_INVALID, "mtam_score_topk: null argument");
   return mtam::score_topk(gemm_mode, pred, B, D, item_table, row_begin, row_end, k, idx_out, score_out, workspace, workspace_bytes,
                           (cudaStream_t)stream);
+}
+
+int mtam_set_topk_bucket_crossover(int32_t rows) {
+  if (rows < 0) return mtam::set_error(MTAM_ERR_INVALID, "mtam_set_topk_bucket_crossover: rows < 0");
+  mtam::g_small_bucket_max_rows = rows == 0 ? mtam::kSmallBucketMaxRowsDefault : rows;
+  return 0;
+}
+
+int mtam_score_bucket_max(const float* pred, int32_t B, int32_t D, const float* item_table, int32_t rows, int32_t bucket_size,
+                          float* bmax, int32_t ld, void* stream) {
+  if (!pred || !item_table || !bmax || B < 1 || rows < 1)
+    return mtam::set_error(MTAM_ERR_INVALID, "mtam_score_bucket_max: bad argument");
+  const int need = mtam::cdiv(mtam::cdiv(rows, 128) * (128 / std::max(bucket_size, 1)), 8) * 8;
+  if (ld < need) return mtam::set_error(MTAM_ERR_INVALID, "mtam_score_bucket_max: ld=%d < %d", ld, need);
+  return mtam::ce_bucket_max_tc(D, pred, B, item_table, rows, bucket_size, bmax, ld, (cudaStream_t)stream);
 }
 
 int mtam_merge_topk(const int32_t* in_idx, const float* in_score, int32_t n_lists, int32_t B, int32_t k, int32_t* out_idx,

@@ -113,7 +113,9 @@ class Engine:
             offs[k] = (total, n)
             total += (n * 4 + 255) // 256 * 256
         self._pinned_all = torch.empty(total, dtype=torch.uint8).pin_memory()
-        self._dev_all = torch.empty(total, dtype=torch.uint8, device=dev)
+        # zero-filled: a step run on the staging buffers before any upload (graph capture) must see valid ids
+        self._pinned_all.zero_()
+        self._dev_all = torch.zeros(total, dtype=torch.uint8, device=dev)
         for k in FEED_KEYS:
             o, n = offs[k]
             shape = (B, L) if k.endswith("_list") else (B,)
@@ -213,6 +215,7 @@ class Engine:
         B = int(len(feed["user_id"]))
         if B < 1 or B > self.cfg.max_batch:
             raise ValueError(f"batch size {B} outside [1, {self.cfg.max_batch}]")
+        self._validate_ids(feed, B)
         if self._h2d_done is not None:
             self._h2d_done.synchronize()          # the previous feed's DMA must have left the pinned buffer
         for k in FEED_KEYS:
@@ -222,6 +225,21 @@ class Engine:
             self._h2d_done = torch.cuda.Event()
         self._h2d_done.record(torch.cuda.current_stream(self.device))
         return DeviceBatch({k: self._dev[k][:B] for k in FEED_KEYS}, B)
+
+    def _validate_ids(self, feed, B: int) -> None:
+        """The gather / scatter kernels index the tables unchecked (as tf.gather does on the GPU): reject feeds whose
+        ids fall outside the tables, or whose lengths fall outside [2, L], on the host."""
+        c = self.cfg
+        bounds = (("user_id", c.user_count + 3), ("item_list", c.item_count + 3), ("target_item_id", c.item_count + 3),
+                  ("category_list", c.category_count + 3), ("position_list", c.L + 3))
+        for k, hi in bounds:
+            a = np.asarray(feed[k])
+            if a.size and (int(a.min()) < 0 or int(a.max()) >= hi):
+                raise ValueError(f"feed array {k}: ids outside [0, {hi})")
+        if c.kind != "BPRMF":
+            sl = np.asarray(feed["seq_length"])
+            if sl.size and (int(sl.min()) < 2 or int(sl.max()) > c.L):
+                raise ValueError(f"feed array seq_length: values outside [2, {c.L}]")
 
     def upload_records(self, records) -> DeviceBatch:
         """A `PackedRecords` view (DataHandle/record_store.py) -> padded by mtam_pack_records straight into the
@@ -339,7 +357,13 @@ class Engine:
         """Captures mtam_train_step on the staging batch buffers (fixed addresses) into a CUDA graph.
         `train_step_graph` then only advances the host-side Adam state and replays it."""
         batch = DeviceBatch({k: v[:B] for k, v in self._dev.items()}, B)
+        if self._h2d_done is None:
+            # nothing uploaded yet: the staging buffers hold zeros (valid pad ids); lengths must be >= 2
+            self._dev["seq_length"].fill_(2)
         t0 = self.adam_step()
+        # the warm-up step and the capture run the optimizer with lr = 0: weights stay, but the Adam moments would absorb
+        # that batch's gradient -- keep them (and the gradient arena) as they were
+        m0, v0 = self.adam_m.clone(), self.adam_v.clone()
         # high priority: the captured main chain is scheduled ahead of the library's side streams (the softmax
         # dTable pass running beside the backward chain fills whatever the chain leaves free)
         s = torch.cuda.Stream(self.device, priority=-1)
@@ -354,7 +378,11 @@ class Engine:
             check(self.lib.mtam_prepare_step(self.h, 0.0, s.cuda_stream), "mtam_prepare_step")
         with torch.cuda.graph(g, stream=s):
             self.train_step_device(batch, 0.0)
+        torch.cuda.synchronize(self.device)
         self.set_adam_step(t0)
+        self.adam_m.copy_(m0)
+        self.adam_v.copy_(v0)
+        del m0, v0
         self._graph, self._graph_B = g, B
         return raise_if
 

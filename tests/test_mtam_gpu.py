@@ -129,14 +129,35 @@ def test_cuda_graph_step_matches_eager():
     eng.train_step(feed, 1e-3); eng.train_step(feed, 5e-4)
     ref = eng.params.clone()
     eng.set_params(P); eng.adam_m.zero_(); eng.adam_v.zero_(); eng.set_adam_step(0); eng.grads.zero_()
-    eng.upload(feed)
+    # capture must leave weights, Adam moments and the step counter exactly as they were (the warm-up inside runs
+    # with lr = 0 and its moments are rolled back)
     eng.capture_train_graph(32)
-    eng.set_params(P); eng.adam_m.zero_(); eng.adam_v.zero_(); eng.set_adam_step(0); eng.grads.zero_()
+    assert eng.adam_step() == 0 and float(eng.adam_m.abs().max()) == 0.0 and float(eng.adam_v.abs().max()) == 0.0
     eng.upload(feed)
     eng.train_step_graph(1e-3); eng.train_step_graph(5e-4)
     torch.cuda.synchronize()
     assert bool((ref == eng.params).all())
     assert eng.adam_step() == 2
+
+
+def test_graph_capture_on_a_fresh_engine_and_feed_validation():
+    """Capture before any upload runs on zero-filled staging buffers (pad ids, length 2), never on garbage; feeds with
+    ids outside the tables are rejected on the host (the gather kernels index unchecked)."""
+    import torch
+    cfg, P, feed, eng = make(D=64, L=12, N=2, H=1, B=32, items=500, users=50, cats=11)
+    before = eng.params.clone()
+    eng.capture_train_graph(32)
+    torch.cuda.synchronize()
+    assert bool((before == eng.params).all()) and eng.adam_step() == 0 and float(eng.adam_v.abs().max()) == 0.0
+    l_graph = eng.train_step(feed, 1e-3)
+    _, _, _, eng2 = make(D=64, L=12, N=2, H=1, B=32, items=500, users=50, cats=11)
+    assert l_graph == eng2.train_step(feed, 1e-3) and bool((eng2.params == eng.params).all())
+    bad = dict(feed); bad["item_list"] = feed["item_list"].copy(); bad["item_list"][0, 0] = 503
+    with pytest.raises(ValueError):
+        eng.upload(bad)
+    bad = dict(feed); bad["seq_length"] = feed["seq_length"].copy(); bad["seq_length"][3] = 1
+    with pytest.raises(ValueError):
+        eng.upload(bad)
 
 
 def test_errors_are_loud():
