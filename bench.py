@@ -431,8 +431,9 @@ def bandwidth_kernels(eng, dev, pk, n=8192 * 200, D=64, rows=10_000_003):
     (2.56 GB) table, inputs far larger than L2.  Two id distributions: `uniform` (every row distinct with high
     probability: no cache reuse, the roofline case) and `zipf_pad` (Zipf(1.05) ids with 45 % pad id 0, the shape of a
     ragged batch: hot rows are served from L2, so the algorithmic-byte rate can exceed the HBM peak).
-    scatter_add = whole op (index sort + segmented reduce); scatter_add_sorted = the segmented reduce alone on
-    pre-sorted indices, which is how a train step runs it (the sort depends only on the batch ids and is overlapped)."""
+    scatter_add = whole op (one-sweep index sort + segmented reduce, each distinct dst row written once);
+    scatter_add_sorted = the segmented reduce alone on pre-sorted indices, which is how a train step runs it (the sort
+    depends only on the batch ids and is overlapped); *_accumulate = the `dst +=` form."""
     import torch
     from mtamrecommender_b200 import engine as E
     from mtamrecommender_b200.synth import ZipfSampler
@@ -469,14 +470,21 @@ def bandwidth_kernels(eng, dev, pk, n=8192 * 200, D=64, rows=10_000_003):
             r = {"rows": n, "D": D, "table_rows": rows, "unique": nu}
             r["gather"] = entry(n * (4 + 2 * D * 4), t(lambda: E.gather(table, idx, out)))
             b = n * (4 + D * 4) + nu * D * 4
-            r["scatter_add"] = entry(b, t(lambda: E.scatter_add(dst, idx, out, ws), reps=5))
+            # the graded op: the IndexedSlices aggregation (read idx + rows once, write each distinct row once;
+            # accumulate=False never reads dst).  `_accumulate` = the += form, which must also READ the touched dst
+            # rows: its second figure counts that traffic.
+            r["scatter_add"] = entry(b, t(lambda: E.scatter_add(dst, idx, out, ws, accumulate=False), reps=5))
+            r["scatter_add_accumulate"] = entry(b, t(lambda: E.scatter_add(dst, idx, out, ws), reps=5),
+                                                bytes_incl_dst_read=b + nu * D * 4)
+            r["sort_indices_ms"] = t(lambda: E.sort_indices(idx, rows, ws), reps=5)
             srt = E.sort_indices(idx, rows)
             ws2 = torch.empty(max(int(_lib_sorted_ws(n, D)), 16), dtype=torch.uint8, device=dev)
-            # dst += needs the touched dst rows read as well as written: the second figure counts that traffic
-            r["scatter_add_sorted"] = entry(b, t(lambda: E.scatter_add_sorted(dst, srt, out, ws2), reps=5),
-                                            bytes_incl_dst_read=b + nu * D * 4)
-            r["scatter_add_sorted"]["achieved_GBs_incl_dst_read"] = (b + nu * D * 4) / r["scatter_add_sorted"]["ms"] / 1e6
-            r["scatter_add_sorted"]["frac_incl_dst_read"] = r["scatter_add_sorted"]["achieved_GBs_incl_dst_read"] / pk["hbm"]
+            r["scatter_add_sorted"] = entry(b, t(lambda: E.scatter_add_sorted(dst, srt, out, ws2, accumulate=False), reps=5))
+            r["scatter_add_sorted_accumulate"] = entry(b, t(lambda: E.scatter_add_sorted(dst, srt, out, ws2), reps=5),
+                                                       bytes_incl_dst_read=b + nu * D * 4)
+            for k in ("scatter_add_accumulate", "scatter_add_sorted_accumulate"):
+                r[k]["achieved_GBs_incl_dst_read"] = (b + nu * D * 4) / r[k]["ms"] / 1e6
+                r[k]["frac_incl_dst_read"] = r[k]["achieved_GBs_incl_dst_read"] / pk["hbm"]
             res[dist] = r
             del idx, srt, ws2
         del table, out, dst, ws

@@ -149,29 +149,34 @@ int mtam_gather(const float* table, int32_t table_rows, int32_t D, const int32_t
 /* Bytes of scratch mtam_scatter_add needs for n indices into a table of `table_rows` rows. */
 size_t mtam_scatter_add_workspace(int64_t n, int32_t table_rows, int32_t D);
 
-/* dst[idx[i],:] += rows[i,:]  for i in [0,n)  -- the gradient of tf.nn.embedding_lookup
- * (tf.gradients -> IndexedSlices -> unsorted_segment_sum, base_model.py:292,296).
- * Deterministic: stable radix sort of (idx, i) then a segmented reduction that adds the rows of
- * one index in ascending i, then one add into dst per distinct index.  `ld_rows` (>= D) is the row
- * stride of `rows` in floats.  If `unique_idx`/`n_unique`
- * are non-null they receive the distinct indices (ascending) and their count (device). */
+/* Aggregation of the rows of equal indices -- the gradient of tf.nn.embedding_lookup
+ * (tf.gradients -> IndexedSlices -> unsorted_segment_sum, base_model.py:292,296):
+ *   accumulate != 0:  dst[idx[i],:] += rows[i,:]  for i in [0,n)
+ *   accumulate == 0:  dst[r,:] = sum of rows[i,:] over {i : idx[i] == r} for every r that occurs in idx; other rows of
+ *                     dst are not touched (on a zeroed dst both forms give the same result; this one never reads dst).
+ * Deterministic: stable radix sort of (idx, i), then a segmented reduction that adds the rows of one index in
+ * ascending i and writes each distinct row of dst exactly once.  `ld_rows` (>= D) is the row stride of `rows` in
+ * floats.  If `unique_idx`/`n_unique` are non-null they receive the distinct indices (ascending) and their count
+ * (device). */
 int mtam_scatter_add(float* dst, int32_t table_rows, int32_t D, const int32_t* idx, const float* rows,
-                     int32_t ld_rows, int64_t n, void* workspace, size_t workspace_bytes, int32_t* unique_idx,
-                     int32_t* n_unique, void* stream);
+                     int32_t ld_rows, int64_t n, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                     int32_t* unique_idx, int32_t* n_unique, void* stream);
 
 /* The two halves of mtam_scatter_add, separately callable: the index sort depends only on the batch's ids, so a
  * training step runs it off the critical path (and once per id list, however many tables share it); the
  * segmented reduction is the HBM-bound part.
- *  mtam_sort_indices: stable LSD radix sort of (keys[i], i), keys in [0, key_bound).  *keys_sorted and *perm
- *    (perm[j] = original position of the j-th smallest key) point INTO the workspace on return.
- *  mtam_scatter_add_sorted: dst[keys_sorted[j],:] += rows[perm[j],:] (perm NULL: rows already in sorted order),
- *    rows of one key added in ascending j.  dst rows are D floats apart. */
+ *  mtam_sort_indices: stable radix sort of (keys[i], i), keys in [0, key_bound), one sweep over the data per 8-bit
+ *    digit (decoupled look-back).  *keys_sorted and *perm (perm[j] = original position of the j-th smallest key)
+ *    point INTO the workspace on return.
+ *  mtam_scatter_add_sorted: dst[keys_sorted[j],:] (+)= rows[perm[j],:] (perm NULL: rows already in sorted order),
+ *    rows of one key added in ascending j, `accumulate` as above.  dst rows are D floats apart. */
 size_t mtam_sort_workspace(int64_t n, int32_t key_bound);
 int mtam_sort_indices(const int32_t* keys, int64_t n, int32_t key_bound, void* workspace, size_t workspace_bytes,
                       const int32_t** keys_sorted, const int32_t** perm, void* stream);
 size_t mtam_scatter_add_sorted_workspace(int64_t n, int32_t D);
 int mtam_scatter_add_sorted(float* dst, int32_t D, const int32_t* keys_sorted, const int32_t* perm, const float* rows,
-                            int32_t ld_rows, int64_t n, void* workspace, size_t workspace_bytes, void* stream);
+                            int32_t ld_rows, int64_t n, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                            void* stream);
 
 /* ---- model --------------------------------------------------------------------------------- */
 

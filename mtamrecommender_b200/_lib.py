@@ -67,11 +67,11 @@ SIGNATURES = {
     "mtam_pack_records": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _VP]),
     "mtam_gather": (C.c_int, [_VP, _I32, _I32, _VP, _I64, _VP, _VP]),
     "mtam_scatter_add_workspace": (_SZ, [_I64, _I32, _I32]),
-    "mtam_scatter_add": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _I32, _I64, _VP, _SZ, _VP, _VP, _VP]),
+    "mtam_scatter_add": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _I32, _I64, _I32, _VP, _SZ, _VP, _VP, _VP]),
     "mtam_sort_workspace": (_SZ, [_I64, _I32]),
     "mtam_sort_indices": (C.c_int, [_VP, _I64, _I32, _VP, _SZ, C.POINTER(_VP), C.POINTER(_VP), _VP]),
     "mtam_scatter_add_sorted_workspace": (_SZ, [_I64, _I32]),
-    "mtam_scatter_add_sorted": (C.c_int, [_VP, _I32, _VP, _VP, _VP, _I32, _I64, _VP, _SZ, _VP]),
+    "mtam_scatter_add_sorted": (C.c_int, [_VP, _I32, _VP, _VP, _VP, _I32, _I64, _I32, _VP, _SZ, _VP]),
     "mtam_plan": (C.c_int, [C.POINTER(Config), C.POINTER(Sizes)]),
     "mtam_create": (C.c_int, [C.POINTER(Config), _VP, _VP, _VP, _VP, _VP, _SZ, C.POINTER(_VP)]),
     "mtam_destroy": (C.c_int, [_VP]),

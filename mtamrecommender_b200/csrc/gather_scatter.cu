@@ -161,153 +161,18 @@ int exclusive_scan_i32(const int* in, int* out, int64_t n, int* tmp, int* total_
 }
 
 // =============================================================================================
-// stable LSD radix sort of (key=row id, val=token index), 8 bits per pass
-// =============================================================================================
-constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS, RS_WARPS = RS_THREADS / 32;
-
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const int32_t* __restrict__ keys, int64_t n,
-                                                             int shift, int* __restrict__ hist, int nblk) {
-  __shared__ int h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  int64_t base = (int64_t)blockIdx.x * RS_TILE;
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int i = 0; i < RS_ITEMS; ++i) {
-    int64_t j = base + i * RS_THREADS + threadIdx.x;
-    int d = (j < n) ? ((keys[j] >> shift) & 255) : 256;
-    unsigned m = __match_any_sync(0xffffffffu, d);           // one shared-memory atomic per distinct digit per warp
-    if (d < 256 && lane == (__ffs(m) - 1)) atomicAdd(&h[d], __popc(m));
-  }
-  __syncthreads();
-  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
-}
-
-// Stable: an item's destination = (scanned count of its digit before this block) + (same digit in
-// earlier warps of the block) + (same digit earlier in this warp's contiguous segment).
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const int32_t* __restrict__ keys_in,
-                                                                const int32_t* __restrict__ vals_in,
-                                                                int32_t* __restrict__ keys_out,
-                                                                int32_t* __restrict__ vals_out, int64_t n,
-                                                                int shift, const int* __restrict__ offs,
-                                                                int nblk) {
-  __shared__ int wcnt[RS_WARPS][257];
-  for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
-  __syncthreads();
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)w * (32 * RS_ITEMS);
-  int32_t key[RS_ITEMS];
-  int rank[RS_ITEMS], dig[RS_ITEMS];
-#pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    int64_t j = wbase + r * 32 + lane;
-    bool valid = j < n;
-    int32_t k = valid ? keys_in[j] : 0;
-    int d = valid ? ((k >> shift) & 255) : 256;
-    unsigned m = __match_any_sync(0xffffffffu, d);
-    int old = wcnt[w][d];
-    __syncwarp();
-    if (lane == (__ffs(m) - 1)) wcnt[w][d] = old + __popc(m);
-    __syncwarp();
-    rank[r] = old + __popc(m & ((1u << lane) - 1u));
-    key[r] = k;
-    dig[r] = d;
-  }
-  __syncthreads();
-  {
-    int d = threadIdx.x;  // 256 threads <-> 256 digits
-    int run = offs[d * nblk + blockIdx.x];
-#pragma unroll
-    for (int ww = 0; ww < RS_WARPS; ++ww) {
-      int c = wcnt[ww][d];
-      wcnt[ww][d] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    int64_t j = wbase + r * 32 + lane;
-    if (j < n) {
-      int dst = wcnt[w][dig[r]] + rank[r];
-      keys_out[dst] = key[r];
-      vals_out[dst] = vals_in ? vals_in[j] : (int32_t)j;
-    }
-  }
-}
-
-static int radix_passes(int table_rows) {
-  int bits = 1;
-  while ((1ll << bits) < (long long)table_rows) ++bits;
-  return (bits + 7) / 8;
-}
-
-struct SortPlan {
-  int64_t n;
-  int nblk, passes;
-  size_t hist_ints, scan_ints;
-};
-static SortPlan sort_plan(int64_t n, int table_rows) {
-  SortPlan p;
-  p.n = n;
-  p.nblk = cdiv(n, RS_TILE);
-  p.passes = radix_passes(table_rows);
-  p.hist_ints = (size_t)256 * p.nblk;
-  p.scan_ints = scan_tmp_ints((int64_t)p.hist_ints);
-  return p;
-}
-
-size_t sort_workspace_bytes(int64_t n, int table_rows) {
-  SortPlan p = sort_plan(n, table_rows);
-  Bump b(nullptr, 0);
-  b.take<int32_t>(n); b.take<int32_t>(n); b.take<int32_t>(n); b.take<int32_t>(n);
-  b.take<int>(p.hist_ints); b.take<int>(p.scan_ints);
-  return b.off + 256;
-}
-
-// Sorts idx[0..n) ascending, stable.  On return *keys_sorted / *perm point into the workspace.
-int sort_by_row(const int32_t* idx, int64_t n, int table_rows, void* ws, size_t ws_bytes,
-                const int32_t** keys_sorted, const int32_t** perm, cudaStream_t st) {
-  SortPlan p = sort_plan(n, table_rows);
-  Bump b(ws, ws_bytes);
-  int32_t* ka = b.take<int32_t>(n);
-  int32_t* kb = b.take<int32_t>(n);
-  int32_t* va = b.take<int32_t>(n);
-  int32_t* vb = b.take<int32_t>(n);
-  int* hist = b.take<int>(p.hist_ints);
-  int* stmp = b.take<int>(p.scan_ints);
-  if (!b.ok()) return set_error(MTAM_ERR_WORKSPACE, "sort: workspace %zu < %zu", ws_bytes, b.off);
-  const int32_t* kin = idx;
-  const int32_t* vin = nullptr;
-  int32_t* kout = ka;
-  int32_t* vout = va;
-  for (int pass = 0; pass < p.passes; ++pass) {
-    int shift = pass * 8;
-    rs_hist_kernel<<<p.nblk, RS_THREADS, 0, st>>>(kin, n, shift, hist, p.nblk);
-    MTAM_TRY(exclusive_scan_i32(hist, hist, (int64_t)p.hist_ints, stmp, nullptr, st));
-    rs_scatter_kernel<<<p.nblk, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, hist, p.nblk);
-    MTAM_LAUNCHES(1);
-    MTAM_LAUNCH_CHECK();
-    kin = kout;
-    vin = vout;
-    kout = (kout == ka) ? kb : ka;
-    vout = (vout == va) ? vb : va;
-  }
-  *keys_sorted = kin;
-  *perm = vin;
-  return 0;
-}
-
-// =============================================================================================
-// multi-level segmented reduction over sorted keys
-// A warp owns a tile of SR_CH consecutive sorted entries (lanes across D, full-line coalesced row
-// reads).  Runs that end inside the tile are added to dst directly (at most one such add per key
-// per level); the tile's last run is carried to the next level, whose input is the dense, still
-// sorted list of carries.  Summation order is a pure function of the sorted order: deterministic.
+// multi-level segmented reduction over sorted keys  (the sort itself: radix_sort.cu)
+//
+// Every destination row is written EXACTLY ONCE.  A CTA owns a contiguous piece of the sorted list; every run of equal
+// keys that lies strictly inside the piece is reduced and written at once; the piece's first and last runs (which may
+// continue in the neighbouring pieces) are carried -- as two (key, partial row) entries per CTA -- to the next level,
+// whose input is that short, still sorted list.  The last level is a single CTA and writes everything.  Hence
+//   * the result is a pure function of the sorted order (bit-reproducible), and
+//   * the write can be a plain store (`accumulate == 0`: dst[key] = sum of its rows; rows of dst that no key names
+//     are left alone) -- no read of dst at all -- or an add into the existing row (`accumulate != 0`).
 // =============================================================================================
 constexpr int SR_CH = 64;
 constexpr int SR_WARPS = 4;
-constexpr int SR_G = 8;   // entries whose row loads are in flight together
 
 template <int VEC> struct VecT;
 template <> struct VecT<1> { using T = float; };
@@ -320,117 +185,231 @@ __device__ __forceinline__ void vzero(float4& a) { a = make_float4(0.f, 0.f, 0.f
 __device__ __forceinline__ void vadd(float& a, const float& b) { a += b; }
 __device__ __forceinline__ void vadd(float2& a, const float2& b) { a.x += b.x; a.y += b.y; }
 __device__ __forceinline__ void vadd(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-// fire-and-forget reduction into global memory (RED.ADD, no return value, no load latency on the
-// critical path).  Deterministic here because a destination row receives at most one add per level.
-__device__ __forceinline__ void vred(float* p, const float& a) { atomicAdd(p, a); }
-__device__ __forceinline__ void vred(float* p, const float2& a) { atomicAdd(reinterpret_cast<float2*>(p), a); }
-__device__ __forceinline__ void vred(float* p, const float4& a) { atomicAdd(reinterpret_cast<float4*>(p), a); }
+// the one write of a destination row: plain streaming store, or a fire-and-forget reduction (RED.ADD, no return value)
+template <bool ACC> __device__ __forceinline__ void vput(float* p, const float& a) { if (ACC) atomicAdd(p, a); else *p = a; }
+template <bool ACC> __device__ __forceinline__ void vput(float* p, const float2& a) {
+  if (ACC) atomicAdd(reinterpret_cast<float2*>(p), a); else *reinterpret_cast<float2*>(p) = a;
+}
+template <bool ACC> __device__ __forceinline__ void vput(float* p, const float4& a) {
+  if (ACC) atomicAdd(reinterpret_cast<float4*>(p), a); else *reinterpret_cast<float4*>(p) = a;
+}
 
-// D == 32*VEC: each lane owns VEC contiguous floats of a row (one 128-bit / 64-bit / 32-bit access).
-// A CTA of SRV_WARPS warps owns SRV_WARPS consecutive 64-entry tiles.  Every warp reduces its tile: runs that begin
-// and end inside the tile are added to dst at once; the tile's first run ("head", it may continue the previous
-// tile's last run) and last run ("tail") go to shared memory, where warp 0 stitches the tiles together in order,
-// adds every run that ends inside the CTA to dst (one add per key per CTA) and carries the CTA's last run to the
-// next level.  So a level shrinks the list 64*SRV_WARPS-fold.
-// Entries per warp: 64 on the big first level (8 groups of 8 rows in flight), 8 on the short carry lists of the later
-// levels, where one group per warp keeps the launch a single round of loads deep.
+// D == 32*VEC (rows of 128 / 256 / 512 bytes): persistent kernel, one CTA per SM, 8 warps.  A warp owns a CONTIGUOUS range
+// of the sorted list and walks it in chunks of R rows.  The rows of a chunk are fetched through the permutation by
+// bulk asynchronous copies (cp.async.bulk, the TMA engine: one copy per row, issued by the lane that holds the row's
+// index) into a per-warp ring of NBUF shared-memory buffers, so NBUF-1 chunks -- 8 warps x 2 x 8 KB = 128 KB per SM at
+// D = 64 -- are in flight while the warp reduces the chunk that has landed, and no register holds data in flight.
+// Runs that begin and end inside the warp's range are written at once; the range's first run ("head") and last run
+// ("tail") go to shared memory, where warp 0 stitches the CTA's 8 ranges together in order, writes every run that lies
+// strictly inside the CTA and carries the CTA's first and last runs to the next level (2 entries per CTA, <= 296 in
+// all: the second level is a single CTA).
 constexpr int SRV_WARPS = 8;
+constexpr int SRV_NBUF = 3;
 
-template <int VEC, int CH>
-__global__ void __launch_bounds__(SRV_WARPS * 32) seg_reduce_vec_kernel(
+__device__ __forceinline__ uint32_t sr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sr_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sr_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sr_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sr_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sr_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sr_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(sr_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void sr_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(sr_smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();      // a protocol error traps instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void sr_lds(float& v, uint32_t a) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); }
+__device__ __forceinline__ void sr_lds(float2& v, uint32_t a) {
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+}
+__device__ __forceinline__ void sr_lds(float4& v, uint32_t a) {
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+}
+
+template <int VEC> struct SrvGeom {
+  static constexpr int D = 32 * VEC, ROWB = D * 4;
+  static constexpr int R = VEC == 4 ? 16 : 32;                  // rows per chunk
+  static constexpr int BUFB = R * ROWB;                         // 4 / 8 / 8 KB
+  static constexpr size_t smem = (size_t)SRV_WARPS * SRV_NBUF * BUFB + 128;
+};
+
+template <int VEC, bool ACC>
+__global__ void __launch_bounds__(SRV_WARPS * 32, 1) seg_reduce_vec_kernel(
     const int32_t* __restrict__ keys, const float* __restrict__ src, int ld_src,
-    const int32_t* __restrict__ perm, int64_t n, int ld_dst, float* __restrict__ dst,
+    const int32_t* __restrict__ perm, int64_t n, int64_t per_warp, int ld_dst, float* __restrict__ dst,
     int32_t* __restrict__ carry_keys, float* __restrict__ carry_rows) {
   using V = typename VecT<VEC>::T;
-  constexpr int D = 32 * VEC;
+  using G = SrvGeom<VEC>;
+  constexpr int D = G::D, R = G::R;
+  constexpr int CPR = G::ROWB / 16;          // 16-byte pieces per row: 8 / 16 / 32
+  constexpr int RPI = 32 / CPR;              // rows one warp-wide cp.async covers: 4 / 2 / 1
+  extern __shared__ uint8_t sr_dyn[];
   __shared__ V s_head[SRV_WARPS][32], s_tail[SRV_WARPS][32];
   __shared__ int32_t s_hkey[SRV_WARPS], s_tkey[SRV_WARPS];
   __shared__ int s_single[SRV_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t tile = (int64_t)blockIdx.x * SRV_WARPS + w;
-  const int64_t ntiles = (n + CH - 1) / CH;
-  if (tile < ntiles) {
-    const int64_t start = tile * CH;
-    const int cnt = (int)min((int64_t)CH, n - start);
-    // tile keys / source rows: two coalesced loads, broadcast later with shuffles
-    const int l0 = min(lane, cnt - 1), l1 = min(lane + 32, cnt - 1);   // clamp: entries past the end alias the last one
-    int32_t k0 = keys[start + l0], k1 = keys[start + l1];
-    int32_t r0 = perm ? perm[start + l0] : (int32_t)(start + l0);
-    int32_t r1 = perm ? perm[start + l1] : (int32_t)(start + l1);
-    V acc, head;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sr_dyn) + 127) & ~(uintptr_t)127) +
+                  (size_t)w * SRV_NBUF * G::BUFB;
+  const uint32_t ring_s = sr_smem_u32(ring);
+  const int64_t start = ((int64_t)blockIdx.x * SRV_WARPS + w) * per_warp;
+  const int64_t end = min(n, start + per_warp);
+  if (start < end) {
+    const int nchunks = (int)((end - start + R - 1) / R);
+    // chunk c -> buffer c % NBUF: lane l keeps the key of entry l; the rows travel as 16-byte cp.async pieces (RPI rows
+    // per warp-wide instruction), one commit group per chunk
+    auto issue = [&](int c) -> int32_t {
+      const int b = c % SRV_NBUF;
+      const int64_t s0 = start + (int64_t)c * R;
+      const int cnt = (int)min((int64_t)R, end - s0);
+      const int l = min(lane, cnt - 1);      // entries past the end alias the last one (their copies are skipped)
+      const int32_t k = __ldg(keys + s0 + l);
+      const int32_t row = perm ? __ldg(perm + s0 + l) : (int32_t)(s0 + l);
+      const int piece = lane % CPR, sub = lane / CPR;
+      const uint32_t dst_s = ring_s + (uint32_t)b * G::BUFB + (uint32_t)piece * 16u;
+#pragma unroll
+      for (int i = 0; i < R; i += RPI) {
+        const int e = i + sub;
+        const int32_t r = __shfl_sync(0xffffffffu, row, e & 31);
+        if (e < cnt) {
+          const float* g = src + (int64_t)r * ld_src + piece * 4;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s + (uint32_t)e * G::ROWB), "l"(g) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      return k;
+    };
+    int32_t kq[SRV_NBUF];                    // keys of the chunks in flight (lane l: entry l)
+#pragma unroll
+    for (int c = 0; c < SRV_NBUF - 1; ++c) {
+      if (c < nchunks) kq[c] = issue(c);
+      else { kq[c] = 0; asm volatile("cp.async.commit_group;" ::: "memory"); }
+    }
+    V acc;
     vzero(acc);
-    vzero(head);
-    int32_t cur = __shfl_sync(0xffffffffu, k0, 0);
+    int32_t cur = __shfl_sync(0xffffffffu, kq[0], 0);
     const int32_t hkey = cur;
     bool first_run = true;
-    for (int i0 = 0; i0 < cnt; i0 += SR_G) {
-      V x[SR_G];
-      int32_t kk[SR_G];
+    float* outp = dst + lane * VEC;          // where the open run's row goes
+    float* const dst_lane = dst + lane * VEC;
+    const int64_t ldd = ld_dst;
+    {
+      V z;
+      vzero(z);
+      s_head[w][lane] = z;
+    }
+    for (int c0 = 0; c0 < nchunks; c0 += SRV_NBUF) {
 #pragma unroll
-      for (int u = 0; u < SR_G; ++u) {     // unconditional, independent loads: SR_G rows in flight
-        int i = i0 + u;
-        int32_t ka = __shfl_sync(0xffffffffu, k0, i & 31), kb = __shfl_sync(0xffffffffu, k1, i & 31);
-        int32_t ra = __shfl_sync(0xffffffffu, r0, i & 31), rb = __shfl_sync(0xffffffffu, r1, i & 31);
-        kk[u] = (i < 32) ? ka : kb;
-        int32_t row = (i < 32) ? ra : rb;
-        x[u] = __ldg(reinterpret_cast<const V*>(src + (int64_t)row * ld_src) + lane);
-      }
-#pragma unroll
-      for (int u = 0; u < SR_G; ++u) {
-        if (i0 + u < cnt) {
-          if (kk[u] != cur) {              // warp-uniform: the run of `cur` ended
-            if (first_run) { head = acc; first_run = false; }
-            else vred(dst + (int64_t)cur * ld_dst + lane * VEC, acc);
-            vzero(acc);
-            cur = kk[u];
+      for (int u = 0; u < SRV_NBUF; ++u) {
+        const int c = c0 + u;
+        if (c < nchunks) {                   // warp-uniform
+          // refill the buffer consumed at the previous step
+          const int un = (u + SRV_NBUF - 1) % SRV_NBUF;
+          if (c + SRV_NBUF - 1 < nchunks) kq[un] = issue(c + SRV_NBUF - 1);
+          else asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group %0;" ::"n"(SRV_NBUF - 1) : "memory");
+          __syncwarp();
+          const int cnt = (int)min((int64_t)R, end - (start + (int64_t)c * R));
+          const int32_t kmine = kq[u];
+          const int32_t kprev = __shfl_up_sync(0xffffffffu, kmine, 1);
+          // bit i: entry i opens a new run
+          unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && kmine != (lane == 0 ? cur : kprev));
+          const uint32_t rows_s = ring_s + (uint32_t)u * G::BUFB + (uint32_t)lane * (VEC * 4);
+#pragma unroll 8
+          for (int i = 0; i < cnt; ++i) {
+            V x;
+            sr_lds(x, rows_s + (uint32_t)i * G::ROWB);
+            if ((starts >> i) & 1u) {        // warp-uniform: the open run ended
+              // the range's first run may continue the previous range's last one: it goes to shared memory
+              if (first_run) { s_head[w][lane] = acc; first_run = false; }
+              else vput<ACC>(outp, acc);
+              vzero(acc);
+              cur = __shfl_sync(0xffffffffu, kmine, i);
+              outp = dst_lane + (int64_t)cur * ldd;
+            }
+            vadd(acc, x);
           }
-          vadd(acc, x[u]);
+          __syncwarp();                      // every lane is done with the buffer before it is refilled
         }
       }
     }
-    s_head[w][lane] = head;
-    s_tail[w][lane] = acc;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    s_tail[w][lane] = acc;                   // the open (last) run
     if (lane == 0) { s_hkey[w] = hkey; s_tkey[w] = cur; s_single[w] = first_run ? 1 : 0; }
   }
   __syncthreads();
   if (w != 0) return;
-  const int nw = (int)min((int64_t)SRV_WARPS, ntiles - (int64_t)blockIdx.x * SRV_WARPS);
+  const bool only = gridDim.x == 1;         // the last level: nothing is carried
+  const int64_t cta_first = (int64_t)blockIdx.x * SRV_WARPS * per_warp;
+  const int nw = (int)min((int64_t)SRV_WARPS, (n - cta_first + per_warp - 1) / per_warp);
   V cacc;
   vzero(cacc);
   int32_t ckey = 0;
-  bool cvalid = false;
+  bool cvalid = false, first_emit = !only;  // the CTA's first closed run is carried, not written
+  // a run that closed inside the CTA: write it, unless it is the CTA's first one
+  auto emit = [&](int32_t key, const V& v) {
+    if (first_emit) {
+      if (lane == 0) carry_keys[2 * blockIdx.x] = key;
+      reinterpret_cast<V*>(carry_rows + (int64_t)(2 * blockIdx.x) * D)[lane] = v;
+      first_emit = false;
+    } else {
+      vput<ACC>(dst + (int64_t)key * ld_dst + lane * VEC, v);
+    }
+  };
   for (int q = 0; q < nw; ++q) {
     const int32_t hk = s_hkey[q], tk = s_tkey[q];
     const V ta = s_tail[q][lane];
-    if (s_single[q]) {                      // the whole tile is one run
+    if (s_single[q]) {                      // the whole range is one run
       if (cvalid && tk == ckey) vadd(cacc, ta);
       else {
-        if (cvalid) vred(dst + (int64_t)ckey * ld_dst + lane * VEC, cacc);
+        if (cvalid) emit(ckey, cacc);
         ckey = tk; cacc = ta; cvalid = true;
       }
     } else {
       V ha = s_head[q][lane];
       if (cvalid && hk == ckey) {           // the head run continues the pending run and ends here
         vadd(cacc, ha);
-        vred(dst + (int64_t)ckey * ld_dst + lane * VEC, cacc);
+        emit(ckey, cacc);
       } else {
-        if (cvalid) vred(dst + (int64_t)ckey * ld_dst + lane * VEC, cacc);
-        vred(dst + (int64_t)hk * ld_dst + lane * VEC, ha);
+        if (cvalid) emit(ckey, cacc);
+        emit(hk, ha);
       }
       ckey = tk; cacc = ta; cvalid = true;
     }
   }
-  const int64_t nctas = (ntiles + SRV_WARPS - 1) / SRV_WARPS;
-  if (blockIdx.x == nctas - 1) {
-    vred(dst + (int64_t)ckey * ld_dst + lane * VEC, cacc);
+  if (only) {
+    vput<ACC>(dst + (int64_t)ckey * ld_dst + lane * VEC, cacc);
   } else {
-    if (lane == 0) carry_keys[blockIdx.x] = ckey;
-    reinterpret_cast<V*>(carry_rows + (int64_t)blockIdx.x * D)[lane] = cacc;
+    if (first_emit) {                       // the whole CTA is one run: it travels as the head, the tail is an empty piece
+      emit(ckey, cacc);
+      vzero(cacc);
+    }
+    if (lane == 0) carry_keys[2 * blockIdx.x + 1] = ckey;
+    reinterpret_cast<V*>(carry_rows + (int64_t)(2 * blockIdx.x + 1) * D)[lane] = cacc;
   }
 }
 
-// any D <= 256: lanes stride across the row
-template <int MAXV>
+// geometry of a vector-kernel level of m entries: entries per warp (a multiple of 32) and CTAs (<= one per SM)
+static void srv_level(int64_t m, int64_t* per_warp, int* ctas) {
+  int64_t pw = std::max<int64_t>(64, (m + (int64_t)kNumSMs * SRV_WARPS - 1) / ((int64_t)kNumSMs * SRV_WARPS));
+  pw = (pw + 31) / 32 * 32;
+  *per_warp = pw;
+  *ctas = (int)((m + pw * SRV_WARPS - 1) / (pw * SRV_WARPS));
+}
+
+// any D <= 256: lanes stride across the row; one warp = one piece of SR_CH entries (first and last run carried)
+template <int MAXV, bool ACC>
 __global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_level_kernel(
     const int32_t* __restrict__ keys, const float* __restrict__ src, int ld_src,
     const int32_t* __restrict__ perm, int64_t n, int D, int ld_dst, float* __restrict__ dst,
@@ -439,6 +418,7 @@ __global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_level_kernel(
   const int64_t tile = (int64_t)blockIdx.x * SR_WARPS + (threadIdx.x >> 5);
   const int64_t ntiles = (n + SR_CH - 1) / SR_CH;
   if (tile >= ntiles) return;
+  const bool only = ntiles == 1;
   const int64_t start = tile * SR_CH;
   const int cnt = (int)min((int64_t)SR_CH, n - start);
   const int l0 = min(lane, cnt - 1), l1 = min(lane + 32, cnt - 1);
@@ -449,6 +429,20 @@ __global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_level_kernel(
 #pragma unroll
   for (int v = 0; v < MAXV; ++v) acc[v] = 0.f;
   int32_t cur = __shfl_sync(0xffffffffu, k0, 0);
+  bool first_emit = !only;
+  auto emit = [&](int32_t key, int slot) {    // slot >= 0: carry entry, else the row's one write
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+      const int d = lane + 32 * v;
+      if (d < D) {
+        if (slot >= 0) carry_rows[(tile * 2 + slot) * D + d] = acc[v];
+        else if (ACC) atomicAdd(dst + (int64_t)key * ld_dst + d, acc[v]);
+        else dst[(int64_t)key * ld_dst + d] = acc[v];
+      }
+      acc[v] = 0.f;
+    }
+    if (slot >= 0 && lane == 0) carry_keys[tile * 2 + slot] = key;
+  };
   for (int i0 = 0; i0 < cnt; i0 += 4) {
     float x[4][MAXV];
     int32_t kk[4];
@@ -467,12 +461,8 @@ __global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_level_kernel(
     for (int u = 0; u < 4; ++u) {
       if (i0 + u < cnt) {
         if (kk[u] != cur) {
-#pragma unroll
-          for (int v = 0; v < MAXV; ++v) {
-            int d = lane + 32 * v;
-            if (d < D) atomicAdd(dst + (int64_t)cur * ld_dst + d, acc[v]);
-            acc[v] = 0.f;
-          }
+          if (first_emit) { emit(cur, 0); first_emit = false; }
+          else emit(cur, -1);
           cur = kk[u];
         }
 #pragma unroll
@@ -480,38 +470,32 @@ __global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_level_kernel(
       }
     }
   }
-  if (tile == ntiles - 1) {
-#pragma unroll
-    for (int v = 0; v < MAXV; ++v) {
-      int d = lane + 32 * v;
-      if (d < D) atomicAdd(dst + (int64_t)cur * ld_dst + d, acc[v]);
-    }
+  if (only) {
+    emit(cur, -1);
   } else {
-    if (lane == 0) carry_keys[tile] = cur;
-#pragma unroll
-    for (int v = 0; v < MAXV; ++v) {
-      int d = lane + 32 * v;
-      if (d < D) carry_rows[tile * D + d] = acc[v];
-    }
+    if (first_emit) emit(cur, 0);           // one run: it travels as the head; the tail is an empty piece of the same key
+    emit(cur, 1);
   }
 }
 
 size_t seg_reduce_workspace_bytes(int64_t n, int D) {
+  // carries of one level: the vector kernels leave 2 per CTA (<= 2*148), the generic kernel 2 per 64 entries
   Bump b(nullptr, 0);
   int64_t m = n;
   while (true) {
     int64_t nt = (m + SR_CH - 1) / SR_CH;
     if (nt <= 1) break;
-    b.take<int32_t>(nt - 1);
-    b.take<float>((nt - 1) * D);
-    m = nt - 1;
+    b.take<int32_t>(2 * nt);
+    b.take<float>(2 * nt * D);
+    m = 2 * nt;
   }
   return b.off + 256;
 }
 
-// dst[keys[i],:] += src[perm ? perm[i] : i, :]  over sorted keys
+// accumulate != 0: dst[keys[i],:] += src[perm ? perm[i] : i, :];  accumulate == 0: dst[key,:] = the sum of its rows
+// (rows of dst no key names are not touched).  Keys sorted ascending.
 int seg_reduce_sorted(const int32_t* keys_sorted, const int32_t* perm, const float* src, int ld_src, int64_t n,
-                      int D, float* dst, int ld_dst, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      int D, float* dst, int ld_dst, void* ws, size_t ws_bytes, cudaStream_t st, int accumulate) {
   if (n <= 0) return 0;
   if (D > 256) return set_error(MTAM_ERR_INVALID, "seg_reduce: D=%d > 256", D);
   Bump b(ws, ws_bytes);
@@ -522,43 +506,54 @@ int seg_reduce_sorted(const int32_t* keys_sorted, const int32_t* perm, const flo
   int64_t m = n;
   while (m > 0) {
     int maxv = (D + 31) / 32;
-    const bool vec_ok = (D == 32 || D == 64 || D == 128) && (lds % (D / 32) == 0) && (ld_dst % (D / 32) == 0) &&
+    // bulk copies need 16-byte aligned rows; vector stores need aligned destination rows
+    const bool vec_ok = (D == 32 || D == 64 || D == 128) && (lds % 4 == 0) && (ld_dst % (D / 32) == 0) &&
                         ((uintptr_t)s % 16 == 0) && ((uintptr_t)dst % 16 == 0);
-    const int wch = (m > 65536) ? 64 : 8;            // entries per warp of the vector kernel at this level
-    const int ch = vec_ok ? wch * SRV_WARPS : SR_CH; // entries folded into one carry at this level
-    int64_t nt = (m + ch - 1) / ch;
+    int64_t per_warp = 0;
+    int ctas = 0;
+    int64_t nt;                                   // pieces at this level (each leaves 2 carries)
+    if (vec_ok) { srv_level(m, &per_warp, &ctas); nt = ctas; }
+    else nt = (m + SR_CH - 1) / SR_CH;
     int32_t* ck = nullptr;
     float* cr = nullptr;
     if (nt > 1) {
-      ck = b.take<int32_t>(nt - 1);
-      cr = b.take<float>((nt - 1) * D);
+      ck = b.take<int32_t>(2 * nt);
+      cr = b.take<float>(2 * nt * D);
       if (!b.ok()) return set_error(MTAM_ERR_WORKSPACE, "seg_reduce: workspace %zu < %zu", ws_bytes, b.off);
     }
-    int blocks = vec_ok ? (int)nt : cdiv(nt, SR_WARPS);
 #define SRV_LAUNCH(VEC_)                                                                                              \
   do {                                                                                                                \
-    if (wch == 64) seg_reduce_vec_kernel<VEC_, 64><<<blocks, SRV_WARPS * 32, 0, st>>>(k, s, lds, pm, m, ld_dst, dst, ck, cr); \
-    else seg_reduce_vec_kernel<VEC_, 8><<<blocks, SRV_WARPS * 32, 0, st>>>(k, s, lds, pm, m, ld_dst, dst, ck, cr);    \
+    const size_t sm_ = SrvGeom<VEC_>::smem;                                                                           \
+    if (accumulate) {                                                                                                 \
+      MTAM_CUDA_CHECK(cudaFuncSetAttribute(seg_reduce_vec_kernel<VEC_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
+      seg_reduce_vec_kernel<VEC_, true><<<ctas, SRV_WARPS * 32, sm_, st>>>(k, s, lds, pm, m, per_warp, ld_dst, dst, ck, cr); \
+    } else {                                                                                                          \
+      MTAM_CUDA_CHECK(cudaFuncSetAttribute(seg_reduce_vec_kernel<VEC_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
+      seg_reduce_vec_kernel<VEC_, false><<<ctas, SRV_WARPS * 32, sm_, st>>>(k, s, lds, pm, m, per_warp, ld_dst, dst, ck, cr); \
+    }                                                                                                                 \
+  } while (0)
+#define SRL_LAUNCH(MAXV_)                                                                                             \
+  do {                                                                                                                \
+    const int blocks = cdiv(nt, SR_WARPS);                                                                            \
+    if (accumulate) seg_reduce_level_kernel<MAXV_, true><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr); \
+    else seg_reduce_level_kernel<MAXV_, false><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);           \
   } while (0)
     if (vec_ok && D == 32) SRV_LAUNCH(1);
     else if (vec_ok && D == 64) SRV_LAUNCH(2);
     else if (vec_ok && D == 128) SRV_LAUNCH(4);
-    else if (maxv <= 1)
-      seg_reduce_level_kernel<1><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);
-    else if (maxv <= 2)
-      seg_reduce_level_kernel<2><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);
-    else if (maxv <= 4)
-      seg_reduce_level_kernel<4><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);
-    else
-      seg_reduce_level_kernel<8><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);
+    else if (maxv <= 1) SRL_LAUNCH(1);
+    else if (maxv <= 2) SRL_LAUNCH(2);
+    else if (maxv <= 4) SRL_LAUNCH(4);
+    else SRL_LAUNCH(8);
 #undef SRV_LAUNCH
+#undef SRL_LAUNCH
     MTAM_LAUNCH_CHECK();
     if (nt <= 1) break;
     k = ck;
     pm = nullptr;
     s = cr;
     lds = D;
-    m = nt - 1;
+    m = 2 * nt;
   }
   return 0;
 }
@@ -602,7 +597,7 @@ size_t scatter_add_workspace_bytes(int64_t n, int table_rows, int D) {
 
 int scatter_add_rows(float* dst, int table_rows, int D, int ld_dst, const int32_t* idx, const float* rows,
                      int ld_src, int64_t n, void* ws, size_t ws_bytes, int32_t* unique_idx, int32_t* n_unique,
-                     cudaStream_t st) {
+                     cudaStream_t st, int accumulate) {
   if (n <= 0) {
     if (n_unique) MTAM_CUDA_CHECK(cudaMemsetAsync(n_unique, 0, sizeof(int32_t), st));
     return 0;
@@ -615,7 +610,7 @@ int scatter_add_rows(float* dst, int table_rows, int D, int ld_dst, const int32_
   char* w = (char*)ws;
   const int32_t *ks, *pm;
   MTAM_TRY(sort_by_row(idx, n, table_rows, w, s1, &ks, &pm, st));
-  MTAM_TRY(seg_reduce_sorted(ks, pm, rows, ld_src, n, D, dst, ld_dst, w + s1, s2, st));
+  MTAM_TRY(seg_reduce_sorted(ks, pm, rows, ld_src, n, D, dst, ld_dst, w + s1, s2, st, accumulate));
   if (unique_idx && n_unique) MTAM_TRY(unique_sorted(ks, n, w + s1 + s2, s3, unique_idx, n_unique, st));
   return 0;
 }
@@ -635,13 +630,13 @@ extern "C" size_t mtam_scatter_add_workspace(int64_t n, int32_t table_rows, int3
 }
 
 extern "C" int mtam_scatter_add(float* dst, int32_t table_rows, int32_t D, const int32_t* idx, const float* rows,
-                                int32_t ld_rows, int64_t n, void* workspace, size_t workspace_bytes, int32_t* unique_idx,
-                                int32_t* n_unique, void* stream) {
+                                int32_t ld_rows, int64_t n, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                                int32_t* unique_idx, int32_t* n_unique, void* stream) {
   if (!dst || n < 0 || (n > 0 && (!idx || !rows || !workspace)))
     return mtam::set_error(MTAM_ERR_INVALID, "mtam_scatter_add: null/negative argument");
   if (ld_rows < D) return mtam::set_error(MTAM_ERR_INVALID, "mtam_scatter_add: ld_rows < D");
   return mtam::scatter_add_rows(dst, table_rows, D, D, idx, rows, ld_rows, n, workspace, workspace_bytes, unique_idx,
-                                n_unique, (cudaStream_t)stream);
+                                n_unique, (cudaStream_t)stream, accumulate);
 }
 
 extern "C" size_t mtam_sort_workspace(int64_t n, int32_t key_bound) { return mtam::sort_workspace_bytes(n, key_bound); }
@@ -660,11 +655,11 @@ extern "C" int mtam_sort_indices(const int32_t* keys, int64_t n, int32_t key_bou
 extern "C" size_t mtam_scatter_add_sorted_workspace(int64_t n, int32_t D) { return mtam::seg_reduce_workspace_bytes(n, D); }
 
 extern "C" int mtam_scatter_add_sorted(float* dst, int32_t D, const int32_t* keys_sorted, const int32_t* perm,
-                                       const float* rows, int32_t ld_rows, int64_t n, void* workspace,
+                                       const float* rows, int32_t ld_rows, int64_t n, int32_t accumulate, void* workspace,
                                        size_t workspace_bytes, void* stream) {
   if (!dst || n < 0 || (n > 0 && (!keys_sorted || !rows || !workspace)))
     return mtam::set_error(MTAM_ERR_INVALID, "mtam_scatter_add_sorted: null/negative argument");
   if (ld_rows < D) return mtam::set_error(MTAM_ERR_INVALID, "mtam_scatter_add_sorted: ld_rows < D");
   return mtam::seg_reduce_sorted(keys_sorted, perm, rows, ld_rows, n, D, dst, D, workspace, workspace_bytes,
-                                 (cudaStream_t)stream);
+                                 (cudaStream_t)stream, accumulate);
 }

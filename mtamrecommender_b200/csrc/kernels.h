@@ -11,16 +11,18 @@ namespace mtam {
 int gather_rows(const float* table, int D, const int32_t* idx, int64_t n, float* out, cudaStream_t st);
 size_t scan_tmp_ints(int64_t n);
 int exclusive_scan_i32(const int* in, int* out, int64_t n, int* tmp, int* total_out, cudaStream_t st);
+// radix_sort.cu: stable one-sweep radix sort of (row id, token index)
 size_t sort_workspace_bytes(int64_t n, int table_rows);
 int sort_by_row(const int32_t* idx, int64_t n, int table_rows, void* ws, size_t ws_bytes,
                 const int32_t** keys_sorted, const int32_t** perm, cudaStream_t st);
+// accumulate != 0: dst[key] += sum of the key's rows; == 0: dst[key] = that sum (one plain store per touched row)
 size_t seg_reduce_workspace_bytes(int64_t n, int D);
 int seg_reduce_sorted(const int32_t* keys_sorted, const int32_t* perm, const float* src, int ld_src, int64_t n,
-                      int D, float* dst, int ld_dst, void* ws, size_t ws_bytes, cudaStream_t st);
+                      int D, float* dst, int ld_dst, void* ws, size_t ws_bytes, cudaStream_t st, int accumulate = 1);
 size_t scatter_add_workspace_bytes(int64_t n, int table_rows, int D);
 int scatter_add_rows(float* dst, int table_rows, int D, int ld_dst, const int32_t* idx, const float* rows,
                      int ld_src, int64_t n, void* ws, size_t ws_bytes, int32_t* unique_idx, int32_t* n_unique,
-                     cudaStream_t st);
+                     cudaStream_t st, int accumulate = 1);
 
 // ---- gemm.cu (fp32 FFMA GEMM with fused epilogues) --------------------------------------------
 // C[M,N] = epi( op(A)[M,K] * op(B)[K,N] ), row-major storage with leading dimensions.

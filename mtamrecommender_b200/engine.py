@@ -421,7 +421,9 @@ def scatter_add_workspace(n: int, table_rows: int, D: int) -> int:
 
 
 def scatter_add(dst: torch.Tensor, idx: torch.Tensor, rows: torch.Tensor, workspace: Optional[torch.Tensor] = None,
-                want_unique: bool = False):
+                want_unique: bool = False, accumulate: bool = True):
+    """dst[idx[i]] += rows[i] (mtam_scatter_add); accumulate=False: dst[r] = sum of the rows whose index is r, other
+    rows of dst untouched, dst never read."""
     lib = _lib.load()
     n = idx.numel()
     R, D = dst.shape
@@ -430,7 +432,7 @@ def scatter_add(dst: torch.Tensor, idx: torch.Tensor, rows: torch.Tensor, worksp
     uniq = torch.empty(max(n, 1), dtype=torch.int32, device=dst.device) if want_unique else None
     nuniq = torch.zeros(1, dtype=torch.int32, device=dst.device) if want_unique else None
     check(lib.mtam_scatter_add(dst.data_ptr(), R, D, idx.data_ptr(), rows.data_ptr(), rows.stride(0), n,
-                               workspace.data_ptr(),
+                               1 if accumulate else 0, workspace.data_ptr(),
                                workspace.numel(), uniq.data_ptr() if want_unique else None,
                                nuniq.data_ptr() if want_unique else None,
                                torch.cuda.current_stream(dst.device).cuda_stream), "mtam_scatter_add")
@@ -466,8 +468,8 @@ def sort_indices(keys: torch.Tensor, key_bound: int, workspace: Optional[torch.T
 
 
 def scatter_add_sorted(dst: torch.Tensor, sorted_idx: SortedIndices, rows: torch.Tensor,
-                       workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dst[keys_sorted[j]] += rows[perm[j]] -- the segmented-reduction half of scatter_add."""
+                       workspace: Optional[torch.Tensor] = None, accumulate: bool = True) -> torch.Tensor:
+    """dst[keys_sorted[j]] (+)= rows[perm[j]] -- the segmented-reduction half of scatter_add."""
     lib = _lib.load()
     n = sorted_idx.keys_sorted.numel()
     R, D = dst.shape
@@ -475,8 +477,9 @@ def scatter_add_sorted(dst: torch.Tensor, sorted_idx: SortedIndices, rows: torch
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=dst.device)
     check(lib.mtam_scatter_add_sorted(dst.data_ptr(), D, sorted_idx.keys_sorted.data_ptr(), sorted_idx.perm.data_ptr(),
-                                      rows.data_ptr(), rows.stride(0), n, workspace.data_ptr(), workspace.numel(),
-                                      torch.cuda.current_stream(dst.device).cuda_stream), "mtam_scatter_add_sorted")
+                                      rows.data_ptr(), rows.stride(0), n, 1 if accumulate else 0, workspace.data_ptr(),
+                                      workspace.numel(), torch.cuda.current_stream(dst.device).cuda_stream),
+          "mtam_scatter_add_sorted")
     return dst
 
 

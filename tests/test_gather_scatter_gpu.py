@@ -71,3 +71,41 @@ def test_scatter_add_strided_rows_and_empty():
     dst0 = torch.zeros(R, D, device="cuda")
     E.scatter_add(dst0, idx[:0].cuda(), wide[:0, :D].contiguous())
     assert not bool(dst0.any())
+
+
+@pytest.mark.parametrize("n,bound", [(1, 10), (31, 5), (8191, 300), (8192, 70000), (8193, 256), (100_000, 1 << 24),
+                                     (1_000_003, 10_000_003), (300_000, 3)])
+def test_sort_indices_is_a_stable_sort(n, bound):
+    """mtam_sort_indices: keys ascending, equal keys in ascending original position (stability is what makes the
+    scatter-add deterministic), perm a permutation.  Sizes straddle the 8192-key tile and all 1..4 digit passes."""
+    import torch
+    from mtamrecommender_b200 import engine as E
+    g = torch.Generator().manual_seed(n + bound)
+    keys = torch.randint(0, bound, (n,), generator=g, dtype=torch.int32)
+    keys[: n // 3] = 0
+    keys[-1] = bound - 1
+    s = E.sort_indices(keys.cuda(), bound)
+    want_k, want_p = torch.sort(keys.long(), stable=True)
+    assert torch.equal(s.keys_sorted.cpu().long(), want_k)
+    assert torch.equal(s.perm.cpu().long(), want_p)
+
+
+@pytest.mark.parametrize("R,D,n", [(1000, 64, 5000), (53, 64, 51200), (100003, 64, 51200), (300, 128, 1), (7, 1, 5000),
+                                   (1 << 17, 32, 200000), (2_000_003, 64, 700000), (5, 64, 70000), (90, 48, 4000)])
+def test_scatter_overwrite_mode_never_reads_dst(R, D, n):
+    """accumulate=False: touched rows hold exactly the sum of their rows (whatever dst held, NaN included), untouched
+    rows keep their content; identical, bit for bit, to accumulate=True on a zeroed dst."""
+    import torch
+    from mtamrecommender_b200 import engine as E
+    g = torch.Generator().manual_seed(R + 7 * n)
+    idx = torch.randint(0, R, (n,), generator=g, dtype=torch.int32)
+    idx[: n // 3] = 0
+    rows = torch.randn(n, D, generator=g).cuda()
+    ref = torch.zeros(R, D, device="cuda")
+    E.scatter_add(ref, idx.cuda(), rows)
+    dst = torch.full((R, D), float("nan"), device="cuda")
+    E.scatter_add(dst, idx.cuda(), rows, accumulate=False)
+    touched = torch.zeros(R, dtype=torch.bool)
+    touched[idx.long()] = True
+    assert torch.equal(dst[touched.cuda()], ref[touched.cuda()])
+    assert bool(torch.isnan(dst[~touched.cuda()]).all())
