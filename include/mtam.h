@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MTAM_ABI_VERSION 1
+#define MTAM_ABI_VERSION 2
 
 typedef enum {
   MTAM_OK = 0,
@@ -54,6 +54,14 @@ typedef enum {
   MTAM_GEMM_TF32X3 = 1      /* tcgen05 kind::tf32, 3-term error-compensated split (fp32-class accuracy) */
 } mtam_gemm_mode;
 
+/* base_model.init_optimizer (base_model.py:71-80).  Adam is what every preset uses; any name the reference does not
+ * know falls through to plain gradient descent.  RMSProp / Adadelta are not built: TF applies them lazily to the rows an
+ * IndexedSlices gradient names, which needs per-row slot bookkeeping no preset exercises. */
+typedef enum {
+  MTAM_OPT_ADAM = 0,        /* tf.train.AdamOptimizer(lr): beta1 0.9, beta2 0.999, eps 1e-8, non-lazy sparse apply */
+  MTAM_OPT_SGD = 1          /* tf.train.GradientDescentOptimizer(lr) */
+} mtam_optimizer;
+
 typedef struct {
   int32_t abi_version;      /* MTAM_ABI_VERSION */
   int32_t kind;             /* mtam_kind */
@@ -70,7 +78,12 @@ typedef struct {
   float clip;               /* FLAGS.max_gradient_norm (base_model.py:294) */
   float beta1, beta2, eps;  /* tf.train.AdamOptimizer defaults (base_model.py:76) */
   int32_t gemm_mode;        /* mtam_gemm_mode */
-  int32_t reserved[7];
+  int32_t optimizer;        /* mtam_optimizer */
+  float dropout;            /* FLAGS.dropout: attention dropout of SASREC / TISASREC (multihead_attention.py:179,
+                               time_aware_attention.py:198); the other kinds have none.  Active in every forward pass,
+                               evaluation included, as in the reference (is_training=True is hard-coded) */
+  uint32_t dropout_seed;    /* keys the keep mask together with the forward-call counter (mtam_set_dropout_state) */
+  int32_t reserved[4];
 } mtam_config;
 
 typedef struct {
@@ -237,6 +250,10 @@ int mtam_scatter_sparse_into(mtam_handle h, float* item_dst, float* category_dst
 
 /* BPR-MF only: fixes the negative item id that `tf.random_uniform([1], 0, item_count)` (BPRMF.py:43) would
  * draw, so a run can be reproduced; item_id < 0 restores the per-step draw from the handle's own generator. */
+/* Attention dropout state: the keep mask of forward call number `counter` is a pure function of (seed, counter, block,
+ * element) -- csrc/selfattn.cu sa_keep(); tests restate it to give the oracle the same mask.  The next forward pass
+ * (train or eval) uses exactly `counter`, later ones count up from it. */
+int mtam_set_dropout_state(mtam_handle h, uint32_t seed, uint32_t counter);
 int mtam_set_bpr_negative(mtam_handle h, int32_t item_id);
 
 /* Per-step host half of mtam_apply: advances the Adam step (beta powers) and enqueues a one-thread

@@ -11,9 +11,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmtam_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 KINDS = {"MTAM": 0, "PISTREC": 1, "SASREC": 2, "TA_SASREC": 3, "TISASREC": 4, "BPRMF": 5}
 GEMM_FP32, GEMM_TF32X3 = 0, 1
+OPTIMIZERS = {"adam": 0, "sgd": 1}
 S_LOSS, S_LOSS_ORIGIN, S_L2_NORM, S_GLOBAL_NORM, S_CLIP_SCALE, S_COUNT = 0, 1, 2, 3, 4, 8
 PARAM_DEAD, PARAM_TABLE = 1, 2
 NAME_MAX = 160
@@ -24,7 +25,8 @@ class Config(C.Structure):
                 ("D", C.c_int32), ("H", C.c_int32), ("N", C.c_int32), ("user_rows", C.c_int32),
                 ("item_rows", C.c_int32), ("category_rows", C.c_int32), ("position_rows", C.c_int32),
                 ("reg", C.c_float), ("clip", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
-                ("eps", C.c_float), ("gemm_mode", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("eps", C.c_float), ("gemm_mode", C.c_int32), ("optimizer", C.c_int32), ("dropout", C.c_float),
+                ("dropout_seed", C.c_uint32), ("reserved", C.c_int32 * 4)]
 
 
 class Sizes(C.Structure):
@@ -86,6 +88,7 @@ SIGNATURES = {
     "mtam_finish_grads": (C.c_int, [_VP, _VP, _I32, _VP]),
     "mtam_apply": (C.c_int, [_VP, C.c_double, _VP, _VP, _VP]),
     "mtam_set_bpr_negative": (C.c_int, [_VP, _I32]),
+    "mtam_set_dropout_state": (C.c_int, [_VP, C.c_uint32, C.c_uint32]),
     "mtam_set_item_grad_event": (C.c_int, [_VP, _VP]),
     "mtam_scatter_sparse_into": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "mtam_prepare_step": (C.c_int, [_VP, C.c_double, _VP]),

@@ -66,7 +66,13 @@ __device__ long long g_ce_trace[16 * 64];
 // TMEM columns: Q hi/lo (A operand of S); S double-buffered (G hi overwrites S in place); G lo double-buffered;
 // O accumulator.  Forward: S buffers are 128 columns wide and nothing else follows.
 constexpr uint32_t COL_QH = 0, COL_QL = 64, COL_S0 = 128, TMEM_COLS = 512;
-constexpr uint32_t COL_GL0 = 256, COL_O = 384;     // PV modes (S buffers 64 wide: 128, 192; G lo: 256, 320)
+constexpr uint32_t COL_GL0 = 256, COL_O = 384;     // PV modes (S buffers 64 wide: 128, 192; G lo: 256, 320; O: 384, 448)
+// The tensor core adds into its fp32 accumulator with truncation, so a chain of n accumulating MMAs drifts by about
+// n * 2^-24 of the accumulated magnitude -- always towards zero.  Over the thousand MMAs a CTA of the backward passes
+// feeds into O that is 5e-5, far outside fp32-class accuracy (seen as 4e-5 relative error of dpred at 100 K items).
+// O is therefore double-buffered and PROMOTED: every kPromote X tiles (96 MMAs) the epilogue warps pull the chunk's
+// accumulator out of TMEM and add it to a register accumulator with ordinary round-to-nearest fp32 adds.
+constexpr int kPromote = 4;
 constexpr int MAXST = 4;
 
 struct CeTcArgs {
@@ -87,7 +93,7 @@ struct CeTcArgs {
 
 struct Bars {
   uint64_t xk_full[MAXST], xk_empty[MAXST], xm_full[MAXST], xm_empty[MAXST], stg_full[MAXST], stg_empty[MAXST], s_full[2],
-      s_empty[2], g_full[2], sg_empty[2], o_full;
+      s_empty[2], g_full[2], sg_empty[2], o_full[2], o_empty[2];
 };
 
 template <int D, int MODE>
@@ -139,7 +145,11 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       mbar_init(&bars.g_full[s], kEpi);
       mbar_init(&bars.sg_empty[s], 1);
     }
-    mbar_init(&bars.o_full, 1);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars.o_full[s], 1);
+      mbar_init(&bars.o_empty[s], kEpi);
+    }
     fence_mbar_init();
   }
   if (warp == kWarpS) tmem_alloc(&tmem_slot, TMEM_COLS);
@@ -298,25 +308,28 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       constexpr uint32_t idO = idesc_tf32(QM, D, 0, 1);
       for (int j = 0; j < n; ++j) {
         const int st = j % NST, use = j / NST, b = j & 1;
+        const int chunk = j / kPromote, ob = chunk & 1;       // O chunk of kPromote tiles -> accumulator ob
         mbar_wait(&bars.xm_full[st], use & 1);
         mbar_wait(&bars.g_full[b], (j >> 1) & 1);
+        if (j % kPromote == 0 && chunk >= 2) mbar_wait(&bars.o_empty[ob], ((chunk >> 1) - 1) & 1);   // drained
         tc_fence_after();
         CE_TRACE(5, j);
         const uint32_t xmh = desc_lo(smem_u32(Xs + st * STAGE + 2 * KC * XT), BX * 128);
         const uint32_t ghi = tmem + COL_S0 + b * SW, glo = tmem + COL_GL0 + b * SW;
+        const uint32_t oacc = tmem + COL_O + ob * 64;
 #pragma unroll
         for (int ks = 0; ks < BX / 8; ++ks) {
           const uint64_t bh = desc_join(xmh + ((ks * 1024) >> 4), kDescHiMN);
           const uint64_t bl = desc_join(xmh + ((KC * XT * 4 + ks * 1024) >> 4), kDescHiMN);
-          mma_tf32_ts(tmem + COL_O, glo + ks * 8, bh, idO, (j | ks) != 0);
-          mma_tf32_ts(tmem + COL_O, ghi + ks * 8, bl, idO, true);
-          mma_tf32_ts(tmem + COL_O, ghi + ks * 8, bh, idO, true);
+          mma_tf32_ts(oacc, glo + ks * 8, bh, idO, ((j % kPromote) | ks) != 0);
+          mma_tf32_ts(oacc, ghi + ks * 8, bl, idO, true);
+          mma_tf32_ts(oacc, ghi + ks * 8, bh, idO, true);
         }
         mma_commit(&bars.xm_empty[st]);
         mma_commit(&bars.sg_empty[b]);
+        if (j % kPromote == kPromote - 1 || j == n - 1) mma_commit(&bars.o_full[ob]);
         CE_TRACE(6, j);
       }
-      mma_commit(&bars.o_full);
     }
   } else {
     // ================= epilogue warps: thread = one Q row (TMEM lane) x half of the tile's columns =================
@@ -329,6 +342,25 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       if (MODE == CE_DP) nl2 = -__ldg(a.lse + qrow) * kLog2e;
     }
     const float gscale = qvalid ? a.inv_batch : 0.f;
+    constexpr int OC = D / 2;     // O columns per thread
+    float osum[PV ? OC : 1];      // promoted accumulator (see kPromote)
+#pragma unroll
+    for (int c = 0; c < (PV ? OC : 1); ++c) osum[c] = 0.f;
+    // adds O chunk `chunk` (complete once its last tile's MMAs have run) to osum and hands the buffer back
+    auto drain = [&](int chunk) {
+      const int ob = chunk & 1;
+      mbar_wait(&bars.o_full[ob], (chunk >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < OC; c += 16) {
+        float v[16];
+        tmem_ld16(lane_base + COL_O + ob * 64 + half * OC + c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) osum[(PV ? c : 0) + (PV ? j : 0)] += v[j];
+      }
+      tc_fence_before();
+      mbar_arrive(&bars.o_empty[ob]);
+    };
     for (int i = 0; i < n; ++i) {
       const int st = i % NST, b = i & 1, ub = i >> 1;
       const int x0 = (xt_begin + i) * BX + half * HC;
@@ -456,27 +488,20 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       tc_fence_before();
       mbar_arrive(&bars.g_full[b]);
       if (lane == 0 && quad == 0) CE_TRACE(4 + 5 * half, i);
+      // the chunk that ended with tile i-1 has had this tile's epilogue time to finish its MMAs: promote it
+      if (PV && i >= 1 && (i - 1) % kPromote == kPromote - 1) drain((i - 1) / kPromote);
     }
     if (MODE == CE_BMAX) {
     } else if (MODE == CE_FWD) {
       if (qvalid) a.ms_partial[(int64_t)(blockIdx.x * 2 + half) * a.B + qrow] = make_float2(m, s);
     } else {
-      constexpr int OC = D / 2;
-      mbar_wait(&bars.o_full, 0);
-      tc_fence_after();
+      if (PV) drain((n - 1) / kPromote);     // the last chunk (every earlier one was promoted inside the loop)
       if (tid == 0) CE_TRACE(12, 0);   // accumulator complete
-      float* dst = nullptr;
-      if (qvalid)
-        dst = ((MODE == CE_DP) ? a.dpred_partial + ((int64_t)blockIdx.x * a.B + qrow) * D : a.dTable + (int64_t)qrow * D) + half * OC;
+      if (qvalid) {
+        float* dst = ((MODE == CE_DP) ? a.dpred_partial + ((int64_t)blockIdx.x * a.B + qrow) * D : a.dTable + (int64_t)qrow * D) + half * OC;
 #pragma unroll
-      for (int c = 0; c < OC; c += 16) {
-        float v[16];
-        tmem_ld16(lane_base + COL_O + half * OC + c, v);
-        if (dst) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(dst + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
+        for (int c = 0; c < (PV ? OC : 0); c += 4)
+          *reinterpret_cast<float4*>(dst + c) = make_float4(osum[c], osum[c + 1], osum[c + 2], osum[c + 3]);
       }
     }
   }

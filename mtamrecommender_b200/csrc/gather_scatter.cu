@@ -244,11 +244,12 @@ template <int VEC> struct SrvGeom {
   static constexpr size_t smem = (size_t)SRV_WARPS * SRV_NBUF * BUFB + 128;
 };
 
+// one CTA's share of a level: CTA `cta` of `nctas`
 template <int VEC, bool ACC>
-__global__ void __launch_bounds__(SRV_WARPS * 32, 1) seg_reduce_vec_kernel(
-    const int32_t* __restrict__ keys, const float* __restrict__ src, int ld_src,
-    const int32_t* __restrict__ perm, int64_t n, int64_t per_warp, int ld_dst, float* __restrict__ dst,
-    int32_t* __restrict__ carry_keys, float* __restrict__ carry_rows) {
+__device__ __forceinline__ void srv_level_cta(const int32_t* __restrict__ keys, const float* __restrict__ src, int ld_src,
+                                              const int32_t* __restrict__ perm, int64_t n, int64_t per_warp, int ld_dst,
+                                              float* __restrict__ dst, int32_t* __restrict__ carry_keys,
+                                              float* __restrict__ carry_rows, int cta, int nctas) {
   using V = typename VecT<VEC>::T;
   using G = SrvGeom<VEC>;
   constexpr int D = G::D, R = G::R;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(SRV_WARPS * 32, 1) seg_reduce_vec_kernel(
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sr_dyn) + 127) & ~(uintptr_t)127) +
                   (size_t)w * SRV_NBUF * G::BUFB;
   const uint32_t ring_s = sr_smem_u32(ring);
-  const int64_t start = ((int64_t)blockIdx.x * SRV_WARPS + w) * per_warp;
+  const int64_t start = ((int64_t)cta * SRV_WARPS + w) * per_warp;
   const int64_t end = min(n, start + per_warp);
   if (start < end) {
     const int nchunks = (int)((end - start + R - 1) / R);
@@ -273,8 +274,8 @@ __global__ void __launch_bounds__(SRV_WARPS * 32, 1) seg_reduce_vec_kernel(
       const int64_t s0 = start + (int64_t)c * R;
       const int cnt = (int)min((int64_t)R, end - s0);
       const int l = min(lane, cnt - 1);      // entries past the end alias the last one (their copies are skipped)
-      const int32_t k = __ldg(keys + s0 + l);
-      const int32_t row = perm ? __ldg(perm + s0 + l) : (int32_t)(s0 + l);
+      const int32_t k = __ldcg(keys + s0 + l);   // (L2: the second level reads what other CTAs of this launch wrote)
+      const int32_t row = perm ? __ldcg(perm + s0 + l) : (int32_t)(s0 + l);
       const int piece = lane % CPR, sub = lane / CPR;
       const uint32_t dst_s = ring_s + (uint32_t)b * G::BUFB + (uint32_t)piece * 16u;
 #pragma unroll
@@ -350,8 +351,8 @@ __global__ void __launch_bounds__(SRV_WARPS * 32, 1) seg_reduce_vec_kernel(
   }
   __syncthreads();
   if (w != 0) return;
-  const bool only = gridDim.x == 1;         // the last level: nothing is carried
-  const int64_t cta_first = (int64_t)blockIdx.x * SRV_WARPS * per_warp;
+  const bool only = nctas == 1;             // the last level: nothing is carried
+  const int64_t cta_first = (int64_t)cta * SRV_WARPS * per_warp;
   const int nw = (int)min((int64_t)SRV_WARPS, (n - cta_first + per_warp - 1) / per_warp);
   V cacc;
   vzero(cacc);
@@ -360,8 +361,8 @@ __global__ void __launch_bounds__(SRV_WARPS * 32, 1) seg_reduce_vec_kernel(
   // a run that closed inside the CTA: write it, unless it is the CTA's first one
   auto emit = [&](int32_t key, const V& v) {
     if (first_emit) {
-      if (lane == 0) carry_keys[2 * blockIdx.x] = key;
-      reinterpret_cast<V*>(carry_rows + (int64_t)(2 * blockIdx.x) * D)[lane] = v;
+      if (lane == 0) carry_keys[2 * cta] = key;
+      reinterpret_cast<V*>(carry_rows + (int64_t)(2 * cta) * D)[lane] = v;
       first_emit = false;
     } else {
       vput<ACC>(dst + (int64_t)key * ld_dst + lane * VEC, v);
@@ -395,9 +396,31 @@ __global__ void __launch_bounds__(SRV_WARPS * 32, 1) seg_reduce_vec_kernel(
       emit(ckey, cacc);
       vzero(cacc);
     }
-    if (lane == 0) carry_keys[2 * blockIdx.x + 1] = ckey;
-    reinterpret_cast<V*>(carry_rows + (int64_t)(2 * blockIdx.x + 1) * D)[lane] = cacc;
+    if (lane == 0) carry_keys[2 * cta + 1] = ckey;
+    reinterpret_cast<V*>(carry_rows + (int64_t)(2 * cta + 1) * D)[lane] = cacc;
   }
+}
+
+// Level 1 on every CTA; the CTA that finishes last (a counter in global memory, zeroed by the host) then runs level 2
+// -- the 2 * gridDim.x <= 296 carried pieces -- alone, in the same launch.
+template <int VEC, bool ACC>
+__global__ void __launch_bounds__(SRV_WARPS * 32, 1) seg_reduce_vec_kernel(
+    const int32_t* __restrict__ keys, const float* __restrict__ src, int ld_src,
+    const int32_t* __restrict__ perm, int64_t n, int64_t per_warp, int ld_dst, float* __restrict__ dst,
+    int32_t* __restrict__ carry_keys, float* __restrict__ carry_rows, unsigned* __restrict__ done_ctas) {
+  srv_level_cta<VEC, ACC>(keys, src, ld_src, perm, n, per_warp, ld_dst, dst, carry_keys, carry_rows, (int)blockIdx.x,
+                          (int)gridDim.x);
+  if (gridDim.x == 1) return;
+  __shared__ unsigned s_ticket;
+  __threadfence();                          // this CTA's carries (written by warp 0) before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(done_ctas, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  const int64_t m = 2 * (int64_t)gridDim.x;
+  const int64_t pw = ((m + SRV_WARPS - 1) / SRV_WARPS + 31) / 32 * 32;
+  srv_level_cta<VEC, ACC>(carry_keys, carry_rows, 32 * VEC, nullptr, m, pw, ld_dst, dst, nullptr, nullptr, 0, 1);
 }
 
 // geometry of a vector-kernel level of m entries: entries per warp (a multiple of 32) and CTAs (<= one per SM)
@@ -481,6 +504,9 @@ __global__ void __launch_bounds__(SR_WARPS * 32) seg_reduce_level_kernel(
 size_t seg_reduce_workspace_bytes(int64_t n, int D) {
   // carries of one level: the vector kernels leave 2 per CTA (<= 2*148), the generic kernel 2 per 64 entries
   Bump b(nullptr, 0);
+  b.take<unsigned>(4);
+  b.take<int32_t>(2 * kNumSMs);
+  b.take<float>((size_t)2 * kNumSMs * D);
   int64_t m = n;
   while (true) {
     int64_t nt = (m + SR_CH - 1) / SR_CH;
@@ -499,21 +525,44 @@ int seg_reduce_sorted(const int32_t* keys_sorted, const int32_t* perm, const flo
   if (n <= 0) return 0;
   if (D > 256) return set_error(MTAM_ERR_INVALID, "seg_reduce: D=%d > 256", D);
   Bump b(ws, ws_bytes);
+  // bulk staging needs 16-byte aligned rows; vector stores need aligned destination rows
+  const bool vec_ok = (D == 32 || D == 64 || D == 128) && (ld_src % 4 == 0) && (ld_dst % (D / 32) == 0) &&
+                      ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+  if (vec_ok) {   // one launch: level 1 everywhere, level 2 on the CTA that finishes last
+    int64_t per_warp;
+    int ctas;
+    srv_level(n, &per_warp, &ctas);
+    unsigned* done = b.take<unsigned>(4);
+    int32_t* ck = b.take<int32_t>(2 * (size_t)ctas);
+    float* cr = b.take<float>(2 * (size_t)ctas * D);
+    if (!b.ok()) return set_error(MTAM_ERR_WORKSPACE, "seg_reduce: workspace %zu < %zu", ws_bytes, b.off);
+    if (ctas > 1) MTAM_CUDA_CHECK(cudaMemsetAsync(done, 0, sizeof(unsigned), st));
+#define SRV_LAUNCH(VEC_)                                                                                              \
+  do {                                                                                                                \
+    const size_t sm_ = SrvGeom<VEC_>::smem;                                                                           \
+    if (accumulate) {                                                                                                 \
+      MTAM_CUDA_CHECK(cudaFuncSetAttribute(seg_reduce_vec_kernel<VEC_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
+      seg_reduce_vec_kernel<VEC_, true><<<ctas, SRV_WARPS * 32, sm_, st>>>(keys_sorted, src, ld_src, perm, n, per_warp, ld_dst, dst, ck, cr, done); \
+    } else {                                                                                                          \
+      MTAM_CUDA_CHECK(cudaFuncSetAttribute(seg_reduce_vec_kernel<VEC_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
+      seg_reduce_vec_kernel<VEC_, false><<<ctas, SRV_WARPS * 32, sm_, st>>>(keys_sorted, src, ld_src, perm, n, per_warp, ld_dst, dst, ck, cr, done); \
+    }                                                                                                                 \
+  } while (0)
+    if (D == 32) SRV_LAUNCH(1);
+    else if (D == 64) SRV_LAUNCH(2);
+    else SRV_LAUNCH(4);
+#undef SRV_LAUNCH
+    MTAM_LAUNCH_CHECK();
+    return 0;
+  }
   const int32_t* k = keys_sorted;
   const int32_t* pm = perm;
   const float* s = src;
   int lds = ld_src;
   int64_t m = n;
+  const int maxv = (D + 31) / 32;
   while (m > 0) {
-    int maxv = (D + 31) / 32;
-    // bulk copies need 16-byte aligned rows; vector stores need aligned destination rows
-    const bool vec_ok = (D == 32 || D == 64 || D == 128) && (lds % 4 == 0) && (ld_dst % (D / 32) == 0) &&
-                        ((uintptr_t)s % 16 == 0) && ((uintptr_t)dst % 16 == 0);
-    int64_t per_warp = 0;
-    int ctas = 0;
-    int64_t nt;                                   // pieces at this level (each leaves 2 carries)
-    if (vec_ok) { srv_level(m, &per_warp, &ctas); nt = ctas; }
-    else nt = (m + SR_CH - 1) / SR_CH;
+    const int64_t nt = (m + SR_CH - 1) / SR_CH;    // pieces at this level (each leaves 2 carries)
     int32_t* ck = nullptr;
     float* cr = nullptr;
     if (nt > 1) {
@@ -521,31 +570,16 @@ int seg_reduce_sorted(const int32_t* keys_sorted, const int32_t* perm, const flo
       cr = b.take<float>(2 * nt * D);
       if (!b.ok()) return set_error(MTAM_ERR_WORKSPACE, "seg_reduce: workspace %zu < %zu", ws_bytes, b.off);
     }
-#define SRV_LAUNCH(VEC_)                                                                                              \
-  do {                                                                                                                \
-    const size_t sm_ = SrvGeom<VEC_>::smem;                                                                           \
-    if (accumulate) {                                                                                                 \
-      MTAM_CUDA_CHECK(cudaFuncSetAttribute(seg_reduce_vec_kernel<VEC_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
-      seg_reduce_vec_kernel<VEC_, true><<<ctas, SRV_WARPS * 32, sm_, st>>>(k, s, lds, pm, m, per_warp, ld_dst, dst, ck, cr); \
-    } else {                                                                                                          \
-      MTAM_CUDA_CHECK(cudaFuncSetAttribute(seg_reduce_vec_kernel<VEC_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
-      seg_reduce_vec_kernel<VEC_, false><<<ctas, SRV_WARPS * 32, sm_, st>>>(k, s, lds, pm, m, per_warp, ld_dst, dst, ck, cr); \
-    }                                                                                                                 \
-  } while (0)
 #define SRL_LAUNCH(MAXV_)                                                                                             \
   do {                                                                                                                \
     const int blocks = cdiv(nt, SR_WARPS);                                                                            \
     if (accumulate) seg_reduce_level_kernel<MAXV_, true><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr); \
     else seg_reduce_level_kernel<MAXV_, false><<<blocks, SR_WARPS * 32, 0, st>>>(k, s, lds, pm, m, D, ld_dst, dst, ck, cr);           \
   } while (0)
-    if (vec_ok && D == 32) SRV_LAUNCH(1);
-    else if (vec_ok && D == 64) SRV_LAUNCH(2);
-    else if (vec_ok && D == 128) SRV_LAUNCH(4);
-    else if (maxv <= 1) SRL_LAUNCH(1);
+    if (maxv <= 1) SRL_LAUNCH(1);
     else if (maxv <= 2) SRL_LAUNCH(2);
     else if (maxv <= 4) SRL_LAUNCH(4);
     else SRL_LAUNCH(8);
-#undef SRV_LAUNCH
 #undef SRL_LAUNCH
     MTAM_LAUNCH_CHECK();
     if (nt <= 1) break;

@@ -74,6 +74,9 @@ struct mtam_model {
   cudaEvent_t ev_ce_done = nullptr;  // caller-owned: recorded once the dense item-table gradient is complete
   bool sort_pending = false;
   const int32_t *sk[4] = {}, *sp[4] = {};   // sorted keys / permutations: item, category, position, user
+  uint32_t drop_seed = 0, drop_calls = 0;   // attention dropout: seed and forward-call counter (device copy: dev_scalars[10])
+  bool drop_prepared = false;        // the device copy already holds the counter of the next forward pass
+  bool drop_explicit = false;        // ... and it was placed there by mtam_set_dropout_state: the next step must use it
   int bpr_neg = -1;                  // injected negative item id (mtam_set_bpr_negative); -1: draw one per step
   int bpr_neg_used = 0;
   uint64_t rng = 1234;
@@ -286,6 +289,9 @@ static int validate(const mtam_config* c) {
     return set_error(MTAM_ERR_INVALID, "table row counts must be positive");
   if (c->gemm_mode != MTAM_GEMM_FP32 && c->gemm_mode != MTAM_GEMM_TF32X3)
     return set_error(MTAM_ERR_INVALID, "unknown gemm_mode %d", c->gemm_mode);
+  if (c->optimizer != MTAM_OPT_ADAM && c->optimizer != MTAM_OPT_SGD)
+    return set_error(MTAM_ERR_UNSUPPORTED, "optimizer %d not built (adam, sgd)", c->optimizer);
+  if (!(c->dropout >= 0.f && c->dropout < 1.f)) return set_error(MTAM_ERR_INVALID, "dropout rate %g outside [0,1)", c->dropout);
   return 0;
 }
 
@@ -508,7 +514,20 @@ static SaCtx sa_ctx(mtam_model* h, const mtam_batch* bt) {
   c.ws = h->ws.sa_ws; c.ws_bytes = h->ws.sa_ws_bytes;
   c.gemm_ws = h->ws.gemm_ws; c.gemm_ws_bytes = h->ws.gemm_ws_bytes;
   c.colsum_ws = h->ws.colsum_ws; c.colsum_ws_bytes = h->ws.colsum_ws_bytes;
+  c.drop_rate = h->cfg.dropout; c.drop_seed = h->drop_seed;
+  c.drop_counter = reinterpret_cast<const uint32_t*>(h->ws.dev_scalars + 10);
   return c;
+}
+
+// every forward pass of a model with attention dropout draws a fresh mask: advance the call counter unless
+// mtam_prepare_step / mtam_set_dropout_state already placed the one this pass is to use on the device
+static int next_dropout_call(mtam_model* h, cudaStream_t st) {
+  const int k = h->cfg.kind;
+  if (h->cfg.dropout <= 0.f || (k != MTAM_KIND_SASREC && k != MTAM_KIND_TISASREC)) return 0;
+  h->drop_explicit = false;
+  if (h->drop_prepared) { h->drop_prepared = false; return 0; }
+  h->drop_calls += 1;
+  return set_scalar_u32(reinterpret_cast<uint32_t*>(h->ws.dev_scalars + 10), h->drop_calls, st);
 }
 
 static int sa_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float* scalars_out, bool with_loss,
@@ -625,7 +644,9 @@ static int fwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* scal
   switch (h->cfg.kind) {
     case MTAM_KIND_MTAM: return mtam_fwd(h, bt, gb, scalars_out, with_loss, st);
     case MTAM_KIND_BPRMF: return bpr_fwd(h, bt, scalars_out, with_loss, st);
-    default: return sa_fwd(h, bt, gb, scalars_out, with_loss, st);
+    default:
+      MTAM_TRY(next_dropout_call(h, st));
+      return sa_fwd(h, bt, gb, scalars_out, with_loss, st);
   }
 }
 static int bwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* nsq, cudaStream_t st) {
@@ -748,11 +769,33 @@ int mtam_prepare_step(mtam_handle h, double lr, void* stream) {
   h->b1_pow *= h->cfg.beta1;
   h->b2_pow *= h->cfg.beta2;
   const float lr32 = (float)lr;  // float64 placeholder cast to fp32 (base_model.py:25)
-  const float lr_t = lr32 * sqrtf(1.f - h->b2_pow) / (1.f - h->b1_pow);
+  const float lr_t = h->cfg.optimizer == MTAM_OPT_SGD ? lr32 : lr32 * sqrtf(1.f - h->b2_pow) / (1.f - h->b1_pow);
   // lr_t travels as a kernel argument (captured by value at launch): no host buffer can be overwritten
   // before the device has read it, however far the host runs ahead.
   MTAM_TRY(set_scalar(h->ws.dev_scalars + 9, lr_t, (cudaStream_t)stream));
+  if (h->cfg.dropout > 0.f && (h->cfg.kind == MTAM_KIND_SASREC || h->cfg.kind == MTAM_KIND_TISASREC)) {
+    // a replayed CUDA graph runs no host code: the mask counter of the NEXT forward pass travels the same way as lr_t.
+    // (In an eager step this call comes after the step's own forward pass and prepares the following one.)
+    if (h->drop_explicit) {
+      h->drop_explicit = false;          // mtam_set_dropout_state chose the counter: keep it
+    } else {
+      h->drop_calls += 1;
+      MTAM_TRY(set_scalar_u32(reinterpret_cast<uint32_t*>(h->ws.dev_scalars + 10), h->drop_calls, (cudaStream_t)stream));
+    }
+    h->drop_prepared = true;
+  }
   h->step_prepared = true;
+  return 0;
+}
+
+int mtam_set_dropout_state(mtam_handle h, uint32_t seed, uint32_t counter) {
+  if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
+  h->drop_seed = seed;
+  h->drop_calls = counter;
+  MTAM_TRY(set_scalar_u32(reinterpret_cast<uint32_t*>(h->ws.dev_scalars + 10), counter, nullptr));
+  MTAM_CUDA_CHECK(cudaStreamSynchronize(nullptr));
+  h->drop_prepared = true;
+  h->drop_explicit = true;
   return 0;
 }
 
@@ -906,8 +949,11 @@ int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_ou
   phase(h, MTAM_PH_ADAM, st);
   if (!h->step_prepared) MTAM_TRY(mtam_prepare_step(h, lr, stream));
   h->step_prepared = false;
-  MTAM_TRY(adam_apply(h->params, h->m, h->v, h->grads, (int64_t)l.total, ds + MTAM_S_CLIP_SCALE, ds + 9, c.beta1, c.beta2,
-                      c.eps, st));
+  if (c.optimizer == MTAM_OPT_SGD)
+    MTAM_TRY(sgd_apply(h->params, h->grads, (int64_t)l.total, ds + MTAM_S_CLIP_SCALE, ds + 9, st));
+  else
+    MTAM_TRY(adam_apply(h->params, h->m, h->v, h->grads, (int64_t)l.total, ds + MTAM_S_CLIP_SCALE, ds + 9, c.beta1, c.beta2,
+                        c.eps, st));
   // restore the invariant "sparse-only table regions of the grads arena are zero"
   MTAM_CUDA_CHECK(cudaMemsetAsync(h->grads + l.cat, 0, (l.dense_begin - l.cat) * sizeof(float), st));
   if (c.kind != MTAM_KIND_PISTREC) MTAM_TRY(zero_rows(h->grads + l.user, h->last_batch.user_id, h->last_B, c.D, st));

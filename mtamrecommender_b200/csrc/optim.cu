@@ -59,6 +59,32 @@ int set_scalar(float* p, float v, cudaStream_t st) {
   return 0;
 }
 
+__global__ void set_scalar_u32_kernel(uint32_t* p, uint32_t v) { p[0] = v; }
+int set_scalar_u32(uint32_t* p, uint32_t v, cudaStream_t st) {
+  set_scalar_u32_kernel<<<1, 1, 0, st>>>(p, v);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
+// tf.train.GradientDescentOptimizer: w -= lr * clipped gradient (rows without a gradient hold 0 in the arena)
+__global__ void __launch_bounds__(256) sgd_kernel(float4* __restrict__ w, const float4* __restrict__ g, int64_t n4,
+                                                  const float* __restrict__ scale_p, const float* __restrict__ lr_p) {
+  const float a = scale_p[0] * lr_p[0];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 gg = __ldg(g + i), ww = w[i];
+    ww.x -= a * gg.x; ww.y -= a * gg.y; ww.z -= a * gg.z; ww.w -= a * gg.w;
+    w[i] = ww;
+  }
+}
+int sgd_apply(float* w, const float* g, int64_t n, const float* scale_p, const float* lr, cudaStream_t st) {
+  int64_t n4 = n / 4;
+  int blocks = std::max(1, (int)std::min<int64_t>(cdiv(n4, 256), kNumSMs * 8));
+  sgd_kernel<<<blocks, 256, 0, st>>>((float4*)w, (const float4*)g, n4, scale_p, lr);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ w, float4* __restrict__ m, float4* __restrict__ v,
                                                    const float4* __restrict__ g, int64_t n4, const float* __restrict__ scale_p,
                                                    const float* __restrict__ lr_t_p, float b1, float b2, float eps) {

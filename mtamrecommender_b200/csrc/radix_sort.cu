@@ -45,29 +45,32 @@ __device__ __forceinline__ unsigned match_digit(int d) {
   return m;
 }
 
-constexpr int OH_ITEMS = 4;             // keys per thread of the histogram kernel: all loads issued up front
+constexpr int OH_ITEMS = 8;             // keys per thread of the histogram kernel: all loads issued up front
 __global__ void __launch_bounds__(OS_THREADS) os_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int passes,
                                                              SortHeader* __restrict__ hdr) {
   __shared__ int h[OS_MAX_PASSES][OS_RADIX];
   for (int i = threadIdx.x; i < OS_MAX_PASSES * OS_RADIX; i += OS_THREADS) (&h[0][0])[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int64_t base = (int64_t)blockIdx.x * (OS_THREADS * OH_ITEMS);
-  int32_t k[OH_ITEMS];
+  // few CTAs (every one ends with passes*256 global atomics), each streaming its share OH_ITEMS loads at a time
+  for (int64_t base = (int64_t)blockIdx.x * (OS_THREADS * OH_ITEMS); base < n;
+       base += (int64_t)gridDim.x * (OS_THREADS * OH_ITEMS)) {
+    int32_t k[OH_ITEMS];
 #pragma unroll
-  for (int i = 0; i < OH_ITEMS; ++i) {
-    const int64_t j = base + i * OS_THREADS + threadIdx.x;
-    k[i] = (j < n) ? __ldg(keys + j) : -1;
-  }
+    for (int i = 0; i < OH_ITEMS; ++i) {
+      const int64_t j = base + i * OS_THREADS + threadIdx.x;
+      k[i] = (j < n) ? __ldg(keys + j) : -1;
+    }
 #pragma unroll
-  for (int i = 0; i < OH_ITEMS; ++i) {
-    const bool valid = k[i] >= 0;
-    // warps filled with one key (the pad id) count it once; otherwise one shared-memory atomic per key and digit
-    const int32_t k0 = __shfl_sync(0xffffffffu, k[i], 0);
-    if (__all_sync(0xffffffffu, k[i] == k0)) {
-      if (valid && lane < passes) atomicAdd(&h[lane][(k[i] >> (8 * lane)) & 255], 32);
-    } else if (valid) {
-      for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(k[i] >> (8 * p)) & 255], 1);
+    for (int i = 0; i < OH_ITEMS; ++i) {
+      const bool valid = k[i] >= 0;
+      // warps filled with one key (the pad id) count it once; otherwise one shared-memory atomic per key and digit
+      const int32_t k0 = __shfl_sync(0xffffffffu, k[i], 0);
+      if (__all_sync(0xffffffffu, k[i] == k0)) {
+        if (valid && lane < passes) atomicAdd(&h[lane][(k[i] >> (8 * lane)) & 255], 32);
+      } else if (valid) {
+        for (int p = 0; p < passes; ++p) atomicAdd(&h[p][(k[i] >> (8 * p)) & 255], 1);
+      }
     }
   }
   __syncthreads();
@@ -278,7 +281,7 @@ int sort_by_row(const int32_t* idx, int64_t n, int key_bound, void* ws, size_t w
   SortHeader* hdr = reinterpret_cast<SortHeader*>(ctl);
   uint32_t* state = reinterpret_cast<uint32_t*>(ctl + sizeof(SortHeader));
   MTAM_CUDA_CHECK(cudaMemsetAsync(ctl, 0, ctl_bytes, st));
-  os_hist_kernel<<<cdiv(n, OS_THREADS * OH_ITEMS), OS_THREADS, 0, st>>>(idx, n, passes, hdr);
+  os_hist_kernel<<<std::min(cdiv(n, OS_THREADS * OH_ITEMS), kNumSMs), OS_THREADS, 0, st>>>(idx, n, passes, hdr);
   MTAM_LAUNCH_CHECK();
   const int32_t* kin = idx;
   const int32_t* vin = nullptr;

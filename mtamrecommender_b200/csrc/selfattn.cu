@@ -8,8 +8,11 @@
 //            time_aware_multihead_attention :215-456, TiSAS_multihead_attention :73-214
 //            Attention.multihead_attention / self_attention  Model/Modules/multihead_attention.py:71-221
 //            PISTRec_model.py:38-74, attention_baseline_models.py:33-84 (gather @ seq_len-1, layer_norm)
-// Attention dropout (multihead_attention.py:179, time_aware_attention.py:198) is not applied: parity
-// runs use rate 0 because TF's Philox stream cannot be reproduced.
+// Attention dropout of the plain and TiSAS variants (multihead_attention.py:179, time_aware_attention.py:198; the
+// reference passes is_training=True unconditionally, so it is active in evaluation too): the softmax weights are
+// multiplied by keep/(1-rate) before the PV product.  TF's Philox stream cannot be reproduced, so the keep mask comes
+// from a counter-based hash of (seed, call counter, block, element) -- sa_keep() below -- which the parity tests
+// restate on the host to hand the oracle the identical mask.
 #include <algorithm>
 
 #include "common.cuh"
@@ -90,8 +93,19 @@ static SaWs sa_plan(const mtam_config& c, void* base, size_t cap) {
 size_t sa_workspace_bytes(const mtam_config& c) { return sa_plan(c, nullptr, 0).total; }
 
 // -------------------------------------------------------------------------------------------------
+// keep decision of attention dropout for element e = ((b*H + h)*L + i)*L + j of block `blk` in forward call `counter`
+__host__ __device__ __forceinline__ bool sa_keep(uint32_t seed, uint32_t counter, uint32_t blk, uint32_t e, uint32_t thr24) {
+  uint32_t x = e * 0x9E3779B1u ^ (seed + 0x85EBCA77u * (counter * 64u + blk));
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;   // murmur3 finaliser
+  return (x >> 8) >= thr24;                                                       // P(keep) = 1 - thr24 / 2^24
+}
+
 struct SaBlockArgs {
   int B, L, D, H, mode;  // mode: 0 plain, 1 time-aware gate, 2 tisas additive interval
+  uint32_t drop_thr24;   // round(rate * 2^24); 0 = no dropout
+  float drop_scale;      // 1 / (1 - rate)
+  uint32_t drop_seed, blk;
+  const uint32_t* drop_counter;
   const int32_t* seq_len;
   const float* time_list;  // [B,L]
   const float* enc;        // [T,D]  block input (raw queries = raw keys)
@@ -151,6 +165,7 @@ __global__ void __launch_bounds__(SA_THREADS) sa_block_fwd_kernel(SaBlockArgs a)
   const float inv = 1.0f;  // scores are divided by sqrt(dh) below, after gating, as the reference does
   (void)inv;
   const float sqrt_dh = sqrtf((float)dh);
+  const uint32_t drop_ctr = a.drop_thr24 ? *a.drop_counter : 0u;
   // ---- gate / interval term, shared by all heads ----
   if (a.mode != 0) {
     const float* w1 = a.gate;
@@ -201,8 +216,11 @@ __global__ void __launch_bounds__(SA_THREADS) sa_block_fwd_kernel(SaBlockArgs a)
       s = warp_sum(s);
       for (int j = lane; j < L; j += 32) {
         float p = (j < len) ? sS[i * SS + j] / s : 0.f;
+        Pg[j] = p;                                       // the softmax weights themselves are kept for the backward pass
+        if (a.drop_thr24)
+          p = sa_keep(a.drop_seed, drop_ctr, a.blk, (uint32_t)((((int64_t)b * H + h) * L + i) * L + j), a.drop_thr24)
+                  ? p * a.drop_scale : 0.f;
         sS[i * SS + j] = p;
-        Pg[j] = p;
       }
     }
     __syncthreads();
@@ -272,14 +290,23 @@ __global__ void __launch_bounds__(SA_THREADS) sa_block_bwd_kernel(SaBlockArgs a)
   }
   __syncthreads();
   const float sqrt_dh = sqrtf((float)dh);
+  const uint32_t drop_ctr = a.drop_thr24 ? *a.drop_counter : 0u;
+  float* sPd = a.drop_thr24 ? sDG : sP;     // dropped weights (the V gradient uses them); sDG is free outside mode 1
   for (int h = 0; h < H; ++h) {
     const int c0 = h * dh;
     const float* Pg = a.P + ((int64_t)b * H + h) * L * L;
     for (int p = tid; p < len * len; p += SA_THREADS) {
       int i = p / len, j = p % len;
-      sP[i * SS + j] = Pg[i * L + j];
+      const float pw = Pg[i * L + j];
+      sP[i * SS + j] = pw;
       float s = 0.f;
       for (int k = 0; k < dh; ++k) s = fmaf(sdO[i * RS + c0 + k], sV[j * RS + c0 + k], s);
+      if (a.drop_thr24) {                   // out = (P * m) V: dP = dPd * m, dV uses P * m
+        const float m = sa_keep(a.drop_seed, drop_ctr, a.blk, (uint32_t)((((int64_t)b * H + h) * L + i) * L + j), a.drop_thr24)
+                            ? a.drop_scale : 0.f;
+        s *= m;
+        sPd[i * SS + j] = pw * m;
+      }
       sdS[i * SS + j] = s;  // dP
     }
     __syncthreads();
@@ -303,7 +330,7 @@ __global__ void __launch_bounds__(SA_THREADS) sa_block_bwd_kernel(SaBlockArgs a)
       int r = p / dh, d = p % dh;
       float dv = 0.f, dq = 0.f, dk = 0.f;
       for (int x = 0; x < len; ++x) {
-        dv = fmaf(sP[x * SS + r], sdO[x * RS + c0 + d], dv);     // dV[j=r] = sum_i P[i,j] dO[i]
+        dv = fmaf(sPd[x * SS + r], sdO[x * RS + c0 + d], dv);    // dV[j=r] = sum_i P[i,j] dO[i]
         dq = fmaf(sdS[r * SS + x], sK[x * RS + c0 + d], dq);     // dQ[i=r] = sum_j dA[i,j] K[j]
         dk = fmaf(sdS[x * SS + r], sQ[x * RS + c0 + d], dk);     // dK[j=r] = sum_i dA[i,j] Q[i]
       }
@@ -397,6 +424,16 @@ static int sa_check_smem(const mtam_config& c, size_t* fwd, size_t* bwd) {
   return 0;
 }
 
+// dropout applies to the plain (0) and TiSAS (2) blocks only: the time-aware block has none (time_aware_attention.py:440)
+static void sa_dropout_args(const SaCtx& c, int mode, int blk, SaBlockArgs& a) {
+  const bool on = mode != 1 && c.drop_rate > 0.f;
+  a.drop_thr24 = on ? (uint32_t)lrintf(c.drop_rate * 16777216.f) : 0u;
+  a.drop_scale = on ? 1.f / (1.f - c.drop_rate) : 1.f;
+  a.drop_seed = c.drop_seed;
+  a.blk = (uint32_t)blk;
+  a.drop_counter = c.drop_counter;
+}
+
 int sa_forward(const SaCtx& c, cudaStream_t st) {
   const mtam_config& g = c.cfg;
   const int B = c.bt->B, L = g.L, D = g.D, N = g.N, H = g.H, mode = sa_mode(g.kind);
@@ -417,6 +454,7 @@ int sa_forward(const SaCtx& c, cudaStream_t st) {
                       c.gemm_ws, c.gemm_ws_bytes, st));
     SaBlockArgs a{};
     a.B = B; a.L = L; a.D = D; a.H = H; a.mode = mode;
+    sa_dropout_args(c, mode, i, a);
     a.seq_len = c.bt->seq_length; a.time_list = c.bt->time_list; a.enc = enc; a.QKV = qkv;
     if (mode == 1) {
       float* et = w.ET + (size_t)i * Tm * D;
@@ -481,6 +519,7 @@ int sa_backward(const SaCtx& c, cudaStream_t st) {
     MTAM_CUDA_CHECK(cudaMemsetAsync(w.dQKV, 0, (size_t)T * 3 * D * sizeof(float), st));
     SaBlockArgs a{};
     a.B = B; a.L = L; a.D = D; a.H = H; a.mode = mode;
+    sa_dropout_args(c, mode, i, a);
     a.seq_len = c.bt->seq_length; a.time_list = c.bt->time_list; a.enc = enc;
     a.QKV = w.QKV + (size_t)i * Tm * 3 * D;
     a.ln_gamma = c.params + c.sl.lng + (size_t)i * D;

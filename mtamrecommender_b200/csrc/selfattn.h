@@ -49,6 +49,9 @@ struct SaCtx {
   size_t ws_bytes;
   void* gemm_ws; size_t gemm_ws_bytes;
   void* colsum_ws; size_t colsum_ws_bytes;
+  float drop_rate = 0.f;                 // attention dropout of SASRec / TiSASRec (0: off)
+  uint32_t drop_seed = 0;
+  const uint32_t* drop_counter = nullptr;   // device: the forward-call counter the mask is keyed on
 };
 int sa_forward(const SaCtx& c, cudaStream_t st);
 int sa_backward(const SaCtx& c, cudaStream_t st);

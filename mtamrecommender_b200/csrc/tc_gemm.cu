@@ -213,9 +213,11 @@ int gemm_tf32x3(int transA, int transB, int M, int N, int K, const float* A, int
                 int ldc, const GemmEpilogue& e, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
   if (K <= 0) return gemm_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ws, ws_bytes, st);
-  static const bool ws_on = !(getenv("MTAM_GEMM_WS") && getenv("MTAM_GEMM_WS")[0] == '0');   // developer switch
-  if (ws_on && gemm_ws_supported(transA, M, N, K, A, lda))   // the pipelined, warp-specialised kernel (tc_gemm_ws.cu)
+  if (gemm_ws_supported(transA, M, N, K, A, lda))   // the pipelined, warp-specialised kernel (tc_gemm_ws.cu)
     return gemm_tf32x3_ws(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ws, ws_bytes, st);
+  // unaligned row-major A (no caller in the model): the simple kernel below keeps one accumulator chain per split, which
+  // is only fp32-class for short K (the tensor core truncates when it accumulates, see tc_gemm_ws.cu)
+  if (K > 1024) return gemm_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ws, ws_bytes, st);
   EpiDev epi{e.bias, e.mask_pos, e.add, e.ld_mask, e.ld_add, e.relu, e.accumulate, e.alpha};
   const int BN = tc_bn(N);
   int S = tc_pick_splits(M, N, K, BN);

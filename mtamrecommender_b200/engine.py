@@ -39,6 +39,9 @@ class ModelConfig:
     beta2: float = 0.999
     eps: float = 1e-8
     gemm_mode: int = _lib.GEMM_FP32
+    optimizer: str = "adam"          # "adam" | "sgd" (base_model.py:71-80)
+    dropout: float = 0.0             # attention dropout of SASREC / TISASREC; ignored by the other kinds, as in the reference
+    dropout_seed: int = 1234
 
     def to_c(self) -> Config:
         c = Config()
@@ -49,6 +52,10 @@ class ModelConfig:
         c.category_rows, c.position_rows = self.category_count + 3, self.L + 3
         c.reg, c.clip, c.beta1, c.beta2, c.eps = self.reg, self.clip, self.beta1, self.beta2, self.eps
         c.gemm_mode = self.gemm_mode
+        if self.optimizer not in _lib.OPTIMIZERS:
+            raise NotImplementedError(f"optimizer {self.optimizer!r}: built are {sorted(_lib.OPTIMIZERS)}")
+        c.optimizer = _lib.OPTIMIZERS[self.optimizer]
+        c.dropout, c.dropout_seed = float(self.dropout), int(self.dropout_seed) & 0xFFFFFFFF
         return c
 
 
@@ -126,6 +133,7 @@ class Engine:
         self._scalars_host = torch.empty(_lib.S_COUNT, dtype=torch.float32).pin_memory()
         self._graph = None
         self._graph_B = -1
+        self.last_scalars = np.zeros(_lib.S_COUNT, np.float32)
         self._h2d_done = None
         if seed is not None:
             self.init_random(seed)
@@ -205,6 +213,11 @@ class Engine:
     def set_bpr_negative(self, item_id: int) -> None:
         """BPR-MF: fix the shared negative item id (BPRMF.py:43 draws it with tf.random_uniform)."""
         check(self.lib.mtam_set_bpr_negative(self.h, int(item_id)), "mtam_set_bpr_negative")
+
+    def set_dropout_state(self, seed: int, counter: int) -> None:
+        """Attention dropout (SASREC / TISASREC): the next forward pass uses the keep mask of call `counter` under `seed`
+        (`dropout_keep_mask` restates it on the host)."""
+        check(self.lib.mtam_set_dropout_state(self.h, int(seed) & 0xFFFFFFFF, int(counter) & 0xFFFFFFFF), "mtam_set_dropout_state")
 
     def set_adam_step(self, t: int) -> None:
         check(self.lib.mtam_set_adam_step(self.h, int(t)), "mtam_set_adam_step")
@@ -293,7 +306,8 @@ class Engine:
             self.train_step_graph(lr)
         else:
             self.train_step_device(batch, lr)
-        return float(self.read_scalars()[_lib.S_LOSS])
+        self.last_scalars = self.read_scalars()
+        return float(self.last_scalars[_lib.S_LOSS])
 
     def forward_device(self, batch: DeviceBatch, want_pred=True):
         B, D = batch.B, self.cfg.D
@@ -402,6 +416,21 @@ class Engine:
         check(self.lib.mtam_hr_ndcg(idx.data_ptr(), idx.shape[0], idx.shape[1], target.data_ptr(), out.data_ptr(),
                                     self._stream()), "mtam_hr_ndcg")
         return out
+
+
+def dropout_keep_mask(seed: int, counter: int, block: int, B: int, H: int, L: int, rate: float) -> np.ndarray:
+    """Host restatement of csrc/selfattn.cu sa_keep(): the multiplicative attention-dropout mask [B,H,L,L]
+    (keep / (1 - rate), else 0) of block `block` in forward call `counter`.  Test / inspection helper."""
+    thr = np.uint32(int(round(np.float32(rate) * np.float32(16777216.0))))
+    e = np.arange(B * H * L * L, dtype=np.uint64).astype(np.uint32)
+    with np.errstate(over="ignore"):
+        key = np.uint32((seed + 0x85EBCA77 * ((counter * 64 + block) & 0xFFFFFFFF)) & 0xFFFFFFFF)
+        x = (e * np.uint32(0x9E3779B1)) ^ key
+        x ^= x >> np.uint32(16); x *= np.uint32(0x85EBCA6B); x ^= x >> np.uint32(13); x *= np.uint32(0xC2B2AE35)
+        x ^= x >> np.uint32(16)
+    keep = (x >> np.uint32(8)) >= thr
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(rate))
+    return (keep.astype(np.float32) * scale).reshape(B, H, L, L)
 
 
 # ---- stand-alone kernels --------------------------------------------------------------------

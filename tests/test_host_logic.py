@@ -2,7 +2,12 @@
 presets, synthetic generator invariants."""
 import math
 
+import os
+
+import os
+
 import numpy as np
+import pytest
 
 from oracle import mtam_oracle as O
 from mtamrecommender_b200.DataHandle.get_input_data import DataInput
@@ -108,3 +113,50 @@ def test_bench_stdout_carries_only_the_json_line(tmp_path):
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip() == '{"ok": 1}'
     assert "banner from a C library" in r.stderr and "python-level noise" in r.stderr
+
+
+def test_lr_schedule_matches_the_reference_rule():
+    """train_process.py:154-159, 324-336: lr1 = FLAGS.lr * 0.99^floor(gs/100) while the CURRENT rate is above 0.001,
+    else lr2 = 0.001 * FLAGS.decay_rate^floor(gs/100); the oracle restates the same rule independently."""
+    from oracle import mtam_oracle as O
+    from mtamrecommender_b200.train_process import exponential_decay, lr_schedule
+    assert exponential_decay(0.1, 250, 100, 0.5, True) == pytest.approx(0.025)
+    assert exponential_decay(0.1, 250, 100, 0.5, False) == pytest.approx(0.1 * 0.5 ** 2.5, rel=1e-6)
+    for flags_lr, decay in ((0.001, 0.995), (0.01, 0.995), (0.001, 0.001), (0.0005, 0.9)):
+        cur = flags_lr
+        for gs in range(0, 1200, 7):
+            want = O.lr_schedule(flags_lr, decay, gs, cur)
+            got = lr_schedule(cur, gs, flags_lr, decay)
+            assert got == pytest.approx(want, rel=2e-6), (flags_lr, decay, gs)
+            cur = got
+    # the flag default decay_rate = 0.001 collapses the rate by 1000x every 100 steps (SURVEY a17)
+    assert lr_schedule(0.001, 100, 0.001, 0.001) == pytest.approx(1e-6, rel=1e-5)
+    # a rate above 0.001 follows lr1 until lr1 itself has decayed to 0.001 or below, then switches to lr2 for good
+    cur, seen_lr2 = 0.0011, False
+    for gs in range(0, 2000, 50):
+        cur = lr_schedule(cur, gs, 0.0011, 0.995)
+        seen_lr2 |= cur <= 0.001
+    assert seen_lr2
+
+
+def test_checkpoint_layout_and_summary_writer(tmp_path):
+    from mtamrecommender_b200.util import checkpoint as ck, summary as tb
+    d = str(tmp_path / "m")
+    t1 = {"a/kernel": np.arange(6, dtype=np.float32).reshape(2, 3), "a/kernel/Adam": np.ones((2, 3), np.float32),
+          "beta1_power": np.asarray(0.9, np.float32)}
+    for step in range(1, 8):
+        ck.save(os.path.join(d, f"model.ckpt-{step}"), t1, {"adam_step": step})
+    assert ck.latest_checkpoint(d).endswith("model.ckpt-7")
+    state = open(os.path.join(d, "checkpoint")).read().splitlines()
+    assert state[0] == 'model_checkpoint_path: "model.ckpt-7"' and len(state) == 6          # max_to_keep = 5
+    assert not os.path.exists(os.path.join(d, "model.ckpt-2.index")) and os.path.exists(os.path.join(d, "model.ckpt-3.index"))
+    back = ck.load(ck.latest_checkpoint(d))
+    assert set(back) == set(t1) and all(np.array_equal(back[k], t1[k]) for k in t1)
+    assert ck.latest_checkpoint(str(tmp_path / "none")) is None
+    w = tb.FileWriter(str(tmp_path / "tb"))
+    w.add_summary(tb.scalars([("Training Loss", 1.5), ("l2_norm", 2.0)]), 3)
+    w.add_summary(None, 4)
+    w.close()
+    import json
+    lines = [json.loads(x) for x in open(tmp_path / "tb" / "events.jsonl")]
+    assert [(x["step"], x["tag"], x["value"]) for x in lines] == [(3, "Training Loss", 1.5), (3, "l2_norm", 2.0)]

@@ -13,6 +13,7 @@ def _flags(**kw):
     F.type, F.experiment_type, F.version = "synthetic", "MTAM", "t"
     F.num_units, F.num_blocks, F.num_heads, F.length_of_user_history = 64, 2, 1, 12
     F.train_batch_size, F.test_batch_size, F.dropout = 16, 16, 0.0
+    F.summary_dir = ""          # scalars stay in memory unless a test asks for files
     for k, v in kw.items():
         setattr(F, k, v)
     return F
@@ -55,3 +56,48 @@ def test_train_and_eval_from_tuples_and_from_record_store(gemm_mode):
     assert a == b and len(a) == 10
     ref, _, _ = O.metrics_topk(cfg, tr.params, O.make_feed(cfg, recs[:16]))
     assert np.allclose(np.array(a), np.array(ref), atol=1e-6)
+
+
+def test_train_process_driver_schedule_summaries_and_checkpoint(tmp_path):
+    """The `train_process.py` drop-in (Train_main_process.train): the learning rate of every step follows
+    train_process.py:154-159/324-336, the training scalars and recall@k / ndgc@k reach the train writer under the
+    reference's tag names, and the final checkpoint -- TF-Saver file naming -- restores into a fresh model that then
+    continues bit-identically."""
+    import os
+    from oracle import mtam_oracle as O
+    from mtamrecommender_b200.train_process import Train_main_process
+    users, items, cats = 30, 400, 7
+    cfg = O.OracleConfig(kind=O.MTAM, L=12, D=64, H=1, N=2, user_count=users, item_count=items, category_count=cats)
+    train, test = O.synth_records(cfg, 70, 3), O.synth_records(cfg, 20, 4)
+    ck = str(tmp_path / "ck")
+    F = _flags(max_epochs=2, eval_freq=3, learning_rate=0.002, decay_rate=0.5, checkpoint_path_dir=ck,
+               summary_dir=str(tmp_path / "tb"))
+    drv = Train_main_process(FLAGS=F, train_set=train, test_set=test, user_count=users, item_count=items, category_count=cats)
+    drv.train()
+    steps = drv.global_step
+    assert steps == 2 * 5                                              # 70 records / 16 = 5 batches per epoch
+    # oracle's restatement of the rule, driven the same way (reset at each epoch start, global step never reset)
+    want, gs = [], 0
+    for epoch in range(2):
+        cur = F.learning_rate
+        for _ in range(5):
+            cur = O.lr_schedule(F.learning_rate, F.decay_rate, gs, cur)
+            want.append(cur); gs += 1
+    assert np.allclose(drv.learning_rates, want, rtol=1e-6)
+    tags = {t for _, t, _ in drv.model.train_writer.events}
+    assert {"Training Loss", "normalized Training Loss", "l2_norm", "Learning_rate", "recall@1", "ndgc@50"} <= tags
+    assert os.path.exists(os.path.join(drv.model.train_writer.get_logdir(), "events.jsonl"))
+    # TF-Saver layout
+    assert sorted(os.listdir(ck)) == ["checkpoint", f"model.ckpt-{steps}.data-00000-of-00001", f"model.ckpt-{steps}.index",
+                                      f"model.ckpt-{steps}.meta"]
+    assert open(os.path.join(ck, "checkpoint")).read().startswith(f'model_checkpoint_path: "model.ckpt-{steps}"')
+    F2 = _flags(load_type="full", checkpoint_path_dir=ck)
+    m2, s2 = _model(F2, users, items, cats)
+    assert bool((m2.engine.params == drv.model.engine.params).all()) and m2.engine.adam_step() == steps
+    l1, _ = drv.model.train(drv.sess, train[:16], 1e-3)
+    l2, _ = m2.train(s2, train[:16], 1e-3)
+    assert l1 == l2 and bool((m2.engine.params == drv.model.engine.params).all())
+    with pytest.raises(ValueError):
+        _model(_flags(load_type="sideways"), users, items, cats)
+    with pytest.raises(NotImplementedError):
+        _model(_flags(optimizer="rmsprop"), users, items, cats)

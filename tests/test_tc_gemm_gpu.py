@@ -40,3 +40,26 @@ def test_gemm_matches_fp64(mode, ta, tb, M, N, K):
     ref2 = ref + (A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double())
     err = (Cd.double().cpu() - ref2).abs()
     assert bool((err <= 4e-6 * bound + 2e-6).all())
+
+
+@pytest.mark.parametrize("ta,tb,M,N,K", [(1, 0, 64, 768, 51200), (1, 0, 128, 64, 51200), (0, 1, 256, 64, 4096),
+                                         (1, 0, 64, 192, 20000)])
+def test_long_accumulations_do_not_drift(ta, tb, M, N, K):
+    """One-signed operands make the accumulator grow with every MMA, which exposes the tensor core's truncating fp32
+    accumulation (a chain of n MMAs loses about n * 2^-24 of the sum: 1e-3 at K = 51 200, the weight-gradient shape of
+    the cfg3 step).  The kernel cuts K into sub-units of 192 MMAs and sums them with ordinary fp32 adds: the result must
+    be fp32-class relative to the RESULT, not merely to sum |a||b|."""
+    import torch
+    from mtamrecommender_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(K + M)
+    A = torch.rand((K, M) if ta else (M, K), generator=g) + 0.5
+    B = torch.rand((N, K) if tb else (K, N), generator=g) + 0.5
+    ref = (A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double())
+    Ad, Bd = A.cuda(), B.cuda()
+    Cd = torch.empty((M, N), device="cuda")
+    ws = torch.empty(max(int(lib.mtam_gemm_workspace(M, N, K)), 16), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mtam_gemm(1, ta, tb, M, N, K, Ad.data_ptr(), Ad.stride(0), Bd.data_ptr(), Bd.stride(0), Cd.data_ptr(), N,
+                             None, 0, 0, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream), "mtam_gemm")
+    relerr = ((Cd.double().cpu() - ref).abs() / ref).max().item()
+    assert relerr < 1.5e-5, relerr            # 192 truncating adds per sub-unit: <= 192 * 2^-24 = 1.1e-5
