@@ -44,7 +44,7 @@ struct Workspace {
   float *l2_partial, *sq_partial, *ce_partial, *norm_partial, *dev_scalars;  // dev_scalars: [16]
   float *bU, *bIP, *bdot, *bbpos, *browsum, *bcolsum, *bloss, *bdU, *bdIP, *bdINp, *bdIN, *bdbneg, *bl2, *bsq;  // BPRMF
   int32_t* bneg_idx;
-  void *ce_ws, *gemm_ws, *colsum_ws, *scatter_ws, *sa_ws, *topk_ws, *sort_ws[4], *seg_ws;
+  void *ce_ws, *gemm_ws, *colsum_ws, *gemm_ws2, *colsum_ws2, *scatter_ws, *sa_ws, *topk_ws, *sort_ws[4], *seg_ws;
   size_t ce_ws_bytes, gemm_ws_bytes, colsum_ws_bytes, scatter_ws_bytes, sa_ws_bytes, topk_ws_bytes, sort_ws_bytes[4],
       seg_ws_bytes;
   size_t total_bytes;
@@ -71,6 +71,8 @@ struct mtam_model {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t side2 = nullptr;      // tensor-core CE: the dense item-table gradient runs here, beside the backward chain
   cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+  cudaStream_t side3 = nullptr;      // parameter gradients (weight-gradient GEMMs, column sums): nothing downstream of the
+  cudaEvent_t ev_pg[3] = {}, ev_join3 = nullptr;   // backward chain reads them, so they run beside it
   cudaEvent_t ev_ce_done = nullptr;  // caller-owned: recorded once the dense item-table gradient is complete
   bool sort_pending = false;
   const int32_t *sk[4] = {}, *sp[4] = {};   // sorted keys / permutations: item, category, position, user
@@ -251,6 +253,9 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
   w.gemm_ws = b.take<char>(w.gemm_ws_bytes);
   w.colsum_ws_bytes = colsum_ws + 256;
   w.colsum_ws = b.take<char>(w.colsum_ws_bytes);
+  // the parameter-gradient products run on a side stream beside the backward chain: their own split-K / partial scratch
+  w.gemm_ws2 = b.take<char>(w.gemm_ws_bytes);
+  w.colsum_ws2 = b.take<char>(w.colsum_ws_bytes);
   size_t sc = 0;
   sc = std::max(sc, scatter_add_workspace_bytes(T, c.item_rows, D));
   sc = std::max(sc, scatter_add_workspace_bytes(T, c.category_rows, D));
@@ -305,6 +310,16 @@ static int gemm(mtam_model* h, int tA, int tB, int M, int N, int K, const float*
 static int colsum(mtam_model* h, const float* A, int lda, const float* Bm, int ldb, int M, int N, float* out,
                   cudaStream_t st) {
   return colsum_f32(A, lda, Bm, ldb, M, N, out, 0, h->ws.colsum_ws, h->ws.colsum_ws_bytes, st);
+}
+
+// the same on the parameter-gradient side stream (own scratch)
+static int gemm2(mtam_model* h, int tA, int tB, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb,
+                 float* C, int ldc, const GemmEpilogue& e, cudaStream_t st) {
+  return gemm_any(h->cfg.gemm_mode, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, e, h->ws.gemm_ws2, h->ws.gemm_ws_bytes, st);
+}
+static int colsum2(mtam_model* h, const float* A, int lda, const float* Bm, int ldb, int M, int N, float* out,
+                   cudaStream_t st) {
+  return colsum_f32(A, lda, Bm, ldb, M, N, out, 0, h->ws.colsum_ws2, h->ws.colsum_ws_bytes, st);
 }
 
 static HopArgs hop_args(mtam_model* h, const mtam_batch* bt) {
@@ -397,7 +412,7 @@ static int mtam_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
 // shared: embedding-layer backward from dX; leaves the IndexedSlices values in dE2/dEp/dEu and
 // adds their squared norm to *norm_sq_sparse.
 static int embed_backward(mtam_model* h, const mtam_batch* bt, int include_user, float* norm_sq_sparse,
-                          cudaStream_t st) {
+                          cudaStream_t st, cudaStream_t pg = nullptr, cudaEvent_t ev_pg = nullptr) {
   const mtam_config& c = h->cfg;
   const Layout& l = h->lay;
   Workspace& w = h->ws;
@@ -407,7 +422,13 @@ static int embed_backward(mtam_model* h, const mtam_batch* bt, int include_user,
   float* G = h->grads;
   MTAM_TRY(relu_mask(w.dX, w.R, T * D, w.dR, st));
   GemmEpilogue e;
-  MTAM_TRY(gemm(h, 1, 0, 2 * D, D, (int)T, w.E2, 2 * D, w.dR, D, G + l.Wemb, D, e, st));     // dW = E2^T dR
+  if (pg) {   // the weight gradient runs beside the rest of the chain (the caller joins `pg` afterwards)
+    MTAM_CUDA_CHECK(cudaEventRecord(ev_pg, st));
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(pg, ev_pg, 0));
+    MTAM_TRY(gemm2(h, 1, 0, 2 * D, D, (int)T, w.E2, 2 * D, w.dR, D, G + l.Wemb, D, e, pg));
+  } else {
+    MTAM_TRY(gemm(h, 1, 0, 2 * D, D, (int)T, w.E2, 2 * D, w.dR, D, G + l.Wemb, D, e, st));     // dW = E2^T dR
+  }
   MTAM_TRY(gemm(h, 0, 1, (int)T, 2 * D, D, w.dR, D, P + l.Wemb, D, w.dE2, 2 * D, e, st));    // dE2 = dR W^T
   int n_sq = 0;
   MTAM_TRY(embed_bwd_tail(w.E2, w.dX, P + l.pos, P + l.user, bt->position_list, bt->user_id, B, c.L, D, c.reg,
@@ -460,8 +481,20 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   g.dpred = w.dpred; g.WqT = w.WqT; g.WtT = w.WtT; g.dX = w.dX; g.dKV = w.dKV; g.DOUT = w.DOUT; g.DQP = w.DQP; g.BKV = w.BKV;
   g.DQT = w.DQT; g.GB = w.GB; g.dq0 = w.dq0;
   MTAM_TRY(hop_backward(a, g, st));
+  // Parameter gradients (weight-gradient GEMMs with K = B*L, column sums) feed nothing but the norm and the optimizer, so
+  // they run on a side stream (`pg`) beside the chain dX -> T-GRU backward -> embedding backward, joining before the
+  // norm.  (Not while profiling: the per-phase times would no longer add up.)
+  const bool pg_aside = !h->prof;
+  cudaStream_t pg = pg_aside ? h->side3 : st;
+  auto pg_after_main = [&](int i) -> int {   // pg continues once the main stream has reached this point
+    if (!pg_aside) return 0;
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_pg[i], st));
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(pg, h->ev_pg[i], 0));
+    return 0;
+  };
   // hop parameter gradients
   phase(h, MTAM_PH_HOP_PARAM_GRADS, st);
+  MTAM_TRY(pg_after_main(0));
   {  // the six per-sequence column sums (LN gains / biases, query bias, gate vectors) in one launch
     ColsumBatch cb{};
     cb.job[0] = ColsumJob{w.dpred, D, nullptr, 0, D, G + l.lnfb};
@@ -474,15 +507,15 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
     // the K,V bias gradient: the CTA-per-sequence backward leaves per-sequence column sums of dKV ([B, 2ND] instead of
     // a second pass over the [B*L, 2ND] rows)
     if (kv_bias_fused) cb.job[cb.n_jobs++] = ColsumJob{w.BKV, 2 * N * D, nullptr, 0, 2 * N * D, G + l.bkv};
-    MTAM_TRY(colsum_multi_f32(cb, B, st));
+    MTAM_TRY(colsum_multi_f32(cb, B, pg));
   }
   // dWq_i = Qin_i^T dQpre_i, dWt_i = Qin_i^T dQt_i: the N hops of each in one batched split-K launch
   MTAM_TRY(gemm_atb_batched_f32(N, D, D, B, w.Qin, D, (int64_t)B * D, w.DQP, N * D, D, G + l.Wq, D, (int64_t)D * D,
-                                w.gemm_ws, w.gemm_ws_bytes, st));
+                                w.gemm_ws2, w.gemm_ws_bytes, pg));
   MTAM_TRY(gemm_atb_batched_f32(N, D, D, B, w.Qin, D, (int64_t)B * D, w.DQT, N * D, D, G + l.Wt, D, (int64_t)D * D,
-                                w.gemm_ws, w.gemm_ws_bytes, st));
-  if (!kv_bias_fused) MTAM_TRY(colsum(h, w.dKV, 2 * N * D, nullptr, 0, (int)T, 2 * N * D, G + l.bkv, st));
-  MTAM_TRY(gemm(h, 1, 0, D, 2 * N * D, (int)T, w.X, D, w.dKV, 2 * N * D, G + l.Wkv, 2 * N * D, e0, st));
+                                w.gemm_ws2, w.gemm_ws_bytes, pg));
+  if (!kv_bias_fused) MTAM_TRY(colsum2(h, w.dKV, 2 * N * D, nullptr, 0, (int)T, 2 * N * D, G + l.bkv, pg));
+  MTAM_TRY(gemm2(h, 1, 0, D, 2 * N * D, (int)T, w.X, D, w.dKV, 2 * N * D, G + l.Wkv, 2 * N * D, e0, pg));
   MTAM_TRY(gemm(h, 0, 1, (int)T, D, 2 * N * D, w.dKV, 2 * N * D, P + l.Wkv, 2 * N * D, w.dX, D, eacc, st));
   // T-GRU
   phase(h, MTAM_PH_GRU_BWD, st);
@@ -490,15 +523,20 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   MTAM_TRY(gru_backward(D, w.X, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, w.Hs, w.RUCT, w.dq0, B, L,
                         w.dGX, w.dX, w.vec_partial, st));
   phase(h, MTAM_PH_GRU_PARAM_GRADS, st);
-  MTAM_TRY(colsum(h, w.vec_partial, 8 * D, nullptr, 0, gru_num_blocks(B), 8 * D, G + l.gruvec, st));
-  MTAM_TRY(colsum(h, w.dGX, 3 * D, nullptr, 0, (int)T, 3 * D, G + l.bgru, st));
-  MTAM_TRY(gemm(h, 1, 0, D, 3 * D, (int)T, w.X, D, w.dGX, 3 * D, G + l.Wgru, 3 * D, e0, st));
+  MTAM_TRY(pg_after_main(1));
+  MTAM_TRY(colsum2(h, w.vec_partial, 8 * D, nullptr, 0, gru_num_blocks(B), 8 * D, G + l.gruvec, pg));
+  MTAM_TRY(colsum2(h, w.dGX, 3 * D, nullptr, 0, (int)T, 3 * D, G + l.bgru, pg));
+  MTAM_TRY(gemm2(h, 1, 0, D, 3 * D, (int)T, w.X, D, w.dGX, 3 * D, G + l.Wgru, 3 * D, e0, pg));
   // h-side: h_{t-1} = Hs shifted by one row (leading zero row), r*h_{t-1} = RH
-  MTAM_TRY(gemm(h, 1, 0, D, 2 * D, (int)T, w.Hs, D, w.dGX, 3 * D, G + l.Wgru + (size_t)D * 3 * D, 3 * D, e0, st));
-  MTAM_TRY(gemm(h, 1, 0, D, D, (int)T, w.RH, D, w.dGX + 2 * D, 3 * D, G + l.Wgru + (size_t)D * 3 * D + 2 * D, 3 * D, e0, st));
+  MTAM_TRY(gemm2(h, 1, 0, D, 2 * D, (int)T, w.Hs, D, w.dGX, 3 * D, G + l.Wgru + (size_t)D * 3 * D, 3 * D, e0, pg));
+  MTAM_TRY(gemm2(h, 1, 0, D, D, (int)T, w.RH, D, w.dGX + 2 * D, 3 * D, G + l.Wgru + (size_t)D * 3 * D + 2 * D, 3 * D, e0, pg));
   MTAM_TRY(gemm(h, 0, 1, (int)T, D, 3 * D, w.dGX, 3 * D, P + l.Wgru, 3 * D, w.dX, D, eacc, st));
   phase(h, MTAM_PH_EMBED_BWD, st);
-  MTAM_TRY(embed_backward(h, bt, 1, norm_sq_sparse, st));
+  MTAM_TRY(embed_backward(h, bt, 1, norm_sq_sparse, st, pg_aside ? pg : nullptr, pg_aside ? h->ev_pg[2] : nullptr));
+  if (pg_aside) {
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_join3, pg));
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join3, 0));
+  }
   if (dt_aside) MTAM_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join2, 0));
   phase(h, MTAM_PH_DENSE_NORM, st);
   return 0;
@@ -707,7 +745,12 @@ int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, 0) != cudaSuccess ||   /* lowest priority */
       cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->side3, cudaStreamNonBlocking, 0) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_pg[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_pg[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_pg[2], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming) != cudaSuccess) {
     int e = set_error(MTAM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     mtam_destroy(h);
     return e;
@@ -725,6 +768,10 @@ int mtam_destroy(mtam_handle h) {
     if (h->side2) cudaStreamDestroy(h->side2);
     if (h->ev_fork2) cudaEventDestroy(h->ev_fork2);
     if (h->ev_join2) cudaEventDestroy(h->ev_join2);
+    if (h->side3) cudaStreamDestroy(h->side3);
+    for (int i = 0; i < 3; ++i)
+      if (h->ev_pg[i]) cudaEventDestroy(h->ev_pg[i]);
+    if (h->ev_join3) cudaEventDestroy(h->ev_join3);
     for (int i = 0; i <= MTAM_PHASE_COUNT; ++i)
       if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   }
