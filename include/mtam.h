@@ -250,6 +250,30 @@ int mtam_scatter_sparse_into(mtam_handle h, float* item_dst, float* category_dst
 
 /* BPR-MF only: fixes the negative item id that `tf.random_uniform([1], 0, item_count)` (BPRMF.py:43) would
  * draw, so a run can be reproduced; item_id < 0 restores the per-step draw from the handle's own generator. */
+/* ---- row-sharded item table: the scalable training variant -----------------------------------------------
+ * The reference keeps the whole item table on one device and both looks it up (Behavior_...py:68-75) and scores against
+ * it (base_model.py:316).  With the table row-sharded over the ranks, a handle is created with item_rows = the rows of
+ * THIS rank's shard (they live in the arenas under embedding_layer/item) and the caller owns the exchanges:
+ *   item rows of the batch  <- all-to-all lookup from the owning ranks              (parallel.ShardedCatalogue.lookup)
+ *   mtam_forward_rows       : forward pass up to pred with those rows in place of the table lookup (item_rows [B*L, D],
+ *                             row t = table[item_list[t]]; the batch's item_list itself is not read); no softmax.
+ *                             scalars_out[MTAM_S_L2_NORM] = the L2 term over this rank's rows.
+ *   softmax cross-entropy   <- mtam_softmax_ce_forward / _backward on the shard + the combination of the per-shard
+ *                             log-sum-exps; the shard's dense table gradient is purely local
+ *   mtam_backward_rows      : backward pass from dpred (gradient of the loss mean over global_batch).  Dense parameter
+ *                             gradients go to the grads arena (its item-table region is not touched); the IndexedSlices
+ *                             values stay in the workspace (mtam_sparse_pieces: the first D columns of item_cat_rows are
+ *                             d loss / d item_rows, to be sent back to the owners and scatter-added there); their squared
+ *                             norm is added to *norm_sq_sparse.
+ *   then mtam_scatter_sparse_into (category / position / user), mtam_sumsq for the dense pieces, mtam_apply. */
+int mtam_forward_rows(mtam_handle h, const mtam_batch* batch, const float* item_rows, float* pred_out, float* scalars_out,
+                      void* stream);
+int mtam_backward_rows(mtam_handle h, const mtam_batch* batch, const float* item_rows, const float* dpred,
+                       int32_t global_batch, float* norm_sq_sparse, void* stream);
+/* out_accumulate[0] += sum x[i]^2 (a dense piece of tf.clip_by_global_norm's norm, base_model.py:294); x 16-byte aligned */
+size_t mtam_sumsq_workspace(int64_t n);
+int mtam_sumsq(const float* x, int64_t n, float* out_accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Attention dropout state: the keep mask of forward call number `counter` is a pure function of (seed, counter, block,
  * element) -- csrc/selfattn.cu sa_keep(); tests restate it to give the oracle the same mask.  The next forward pass
  * (train or eval) uses exactly `counter`, later ones count up from it. */

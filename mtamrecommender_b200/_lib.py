@@ -88,6 +88,10 @@ SIGNATURES = {
     "mtam_finish_grads": (C.c_int, [_VP, _VP, _I32, _VP]),
     "mtam_apply": (C.c_int, [_VP, C.c_double, _VP, _VP, _VP]),
     "mtam_set_bpr_negative": (C.c_int, [_VP, _I32]),
+    "mtam_forward_rows": (C.c_int, [_VP, C.POINTER(Batch), _VP, _VP, _VP, _VP]),
+    "mtam_backward_rows": (C.c_int, [_VP, C.POINTER(Batch), _VP, _VP, _I32, _VP, _VP]),
+    "mtam_sumsq_workspace": (_SZ, [_I64]),
+    "mtam_sumsq": (C.c_int, [_VP, _I64, _VP, _VP, _SZ, _VP]),
     "mtam_set_dropout_state": (C.c_int, [_VP, C.c_uint32, C.c_uint32]),
     "mtam_set_item_grad_event": (C.c_int, [_VP, _VP]),
     "mtam_scatter_sparse_into": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),

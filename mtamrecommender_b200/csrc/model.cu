@@ -44,6 +44,7 @@ struct Workspace {
   float *l2_partial, *sq_partial, *ce_partial, *norm_partial, *dev_scalars;  // dev_scalars: [16]
   float *bU, *bIP, *bdot, *bbpos, *browsum, *bcolsum, *bloss, *bdU, *bdIP, *bdINp, *bdIN, *bdbneg, *bl2, *bsq;  // BPRMF
   int32_t* bneg_idx;
+  int32_t* iota;     // 0..max_batch*L-1: token numbers as row ids of a caller-supplied [B*L, D] item-row array
   void *ce_ws, *gemm_ws, *colsum_ws, *gemm_ws2, *colsum_ws2, *scatter_ws, *sa_ws, *topk_ws, *sort_ws[4], *seg_ws;
   size_t ce_ws_bytes, gemm_ws_bytes, colsum_ws_bytes, scatter_ws_bytes, sa_ws_bytes, topk_ws_bytes, sort_ws_bytes[4],
       seg_ws_bytes;
@@ -74,6 +75,8 @@ struct mtam_model {
   cudaStream_t side3 = nullptr;      // parameter gradients (weight-gradient GEMMs, column sums): nothing downstream of the
   cudaEvent_t ev_pg[3] = {}, ev_join3 = nullptr;   // backward chain reads them, so they run beside it
   cudaEvent_t ev_ce_done = nullptr;  // caller-owned: recorded once the dense item-table gradient is complete
+  const float* item_rows_ext = nullptr;   // row-sharded item table: the batch's item rows, fetched by the caller
+  bool rows_mode = false;                 // ... and the softmax is the caller's too (mtam_forward_rows / mtam_backward_rows)
   bool sort_pending = false;
   const int32_t *sk[4] = {}, *sp[4] = {};   // sorted keys / permutations: item, category, position, user
   uint32_t drop_seed = 0, drop_calls = 0;   // attention dropout: seed and forward-call counter (device copy: dev_scalars[10])
@@ -201,6 +204,7 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
   w.ce_partial = b.take<float>(cdiv(B, 32) + 1);
   w.norm_partial = b.take<float>(kNumSMs * 4 + 4);
   w.dev_scalars = b.take<float>(16);
+  w.iota = b.take<int32_t>(T);
   size_t gemm_ws = 0, colsum_ws = 0;
   auto G = [&](int M, int Nn, int K) { gemm_ws = std::max(gemm_ws, gemm_any_workspace_bytes(M, Nn, K)); };
   auto CS = [&](int M, int Nn) { colsum_ws = std::max(colsum_ws, colsum_workspace_bytes(M, Nn)); };
@@ -346,7 +350,9 @@ static int embed_forward(mtam_model* h, const mtam_batch* bt, int include_user, 
   const int B = bt->B, D = c.D;
   const int64_t T = (int64_t)B * c.L;
   float* P = h->params;
-  MTAM_TRY(embed_gather(P + l.item, P + l.cat, P + l.pos, P + l.user, bt->item_list, bt->category_list,
+  // (row-sharded item table: the rows were fetched by the caller; token t reads row t of that array)
+  const float* item_tab = h->item_rows_ext ? h->item_rows_ext : P + l.item;
+  MTAM_TRY(embed_gather(item_tab, P + l.cat, P + l.pos, P + l.user, bt->item_list, bt->category_list,
                         bt->position_list, bt->user_id, B, c.L, D, include_user, w.E2, w.l2_partial, n_l2, st));
   GemmEpilogue e;
   e.relu = 1;
@@ -401,6 +407,13 @@ static int mtam_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   HopArgs a = hop_args(h, bt);
   MTAM_TRY(hop_forward(a, st));
   phase(h, MTAM_PH_CE_FWD, st);
+  if (h->rows_mode) {   // the softmax against the sharded table is the caller's: leave the L2 term of this rank's rows
+    MTAM_TRY(finalize_sum(w.l2_partial, n_l2, 0.5f, w.dev_scalars + MTAM_S_L2_NORM, 0, st));
+    if (scalars_out)
+      MTAM_CUDA_CHECK(cudaMemcpyAsync(scalars_out + MTAM_S_L2_NORM, w.dev_scalars + MTAM_S_L2_NORM, sizeof(float),
+                                      cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
   if (!with_loss) return 0;
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.tlogit, 0, (size_t)B * sizeof(float), st));
   MTAM_TRY(ce_forward(c.gemm_mode, D, w.pred, P + l.item, bt->target_item_id, B, c.item_rows, w.ce_ws, w.tlogit, w.lse,
@@ -452,8 +465,10 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   // The dense item-table gradient (dT = G^T pred, a full-machine tensor-core pass) feeds only the norm and Adam; the
   // chain behind dpred (hops, T-GRU, embedding) is latency-bound kernels on a fraction of the SMs.  Run dT beside it.
   // (Not while profiling: the per-phase times would no longer add up.)
-  const bool dt_aside = c.gemm_mode == MTAM_GEMM_TF32X3 && ce_tc_supported(D) && !h->prof;
-  if (dt_aside) {
+  const bool dt_aside = c.gemm_mode == MTAM_GEMM_TF32X3 && ce_tc_supported(D) && !h->prof && !h->rows_mode;
+  if (h->rows_mode) {
+    // dpred was placed in the workspace by mtam_backward_rows (softmax against the sharded table: the caller's)
+  } else if (dt_aside) {
     MTAM_CUDA_CHECK(cudaEventRecord(h->ev_fork2, st));
     MTAM_CUDA_CHECK(cudaStreamWaitEvent(h->side2, h->ev_fork2, 0));
     MTAM_TRY(ce_backward_tc(D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
@@ -740,6 +755,10 @@ int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam
     return set_error(MTAM_ERR_CUDA, "cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   memset(&h->last_batch, 0, sizeof(h->last_batch));
+  if (fill_iota(h->ws.iota, (int64_t)cfg->max_batch * cfg->L, nullptr) != 0 || cudaStreamSynchronize(nullptr) != cudaSuccess) {
+    delete h;
+    return set_error(MTAM_ERR_CUDA, "workspace initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
@@ -892,6 +911,75 @@ int mtam_forward(mtam_handle h, const mtam_batch* batch, float* scalars_out, flo
                                     cudaMemcpyDeviceToDevice, st));
   return 0;
 }
+
+// ---- row-sharded item table ("scalable training variant") ----------------------------------------------
+static int rows_batch(mtam_handle h, const mtam_batch* batch, const float* item_rows, mtam_batch* out) {
+  MTAM_TRY(check_batch(h, batch));
+  if (h->cfg.kind != MTAM_KIND_MTAM) return set_error(MTAM_ERR_UNSUPPORTED, "sharded item table: MTAM only");
+  if (!item_rows) return set_error(MTAM_ERR_INVALID, "item_rows is null");
+  *out = *batch;
+  out->item_list = h->ws.iota;
+  return 0;
+}
+
+int mtam_forward_rows(mtam_handle h, const mtam_batch* batch, const float* item_rows, float* pred_out, float* scalars_out,
+                      void* stream) {
+  mtam_batch bt;
+  MTAM_TRY(rows_batch(h, batch, item_rows, &bt));
+  cudaStream_t st = (cudaStream_t)stream;
+  const mtam_config& c = h->cfg;
+  Workspace& w = h->ws;
+  const int64_t T = (int64_t)batch->B * c.L;
+  // the sorts of the replicated tables' ids run beside the forward pass, as in mtam_forward_backward
+  MTAM_CUDA_CHECK(cudaEventRecord(h->ev_fork, st));
+  MTAM_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  MTAM_TRY(sort_by_row(batch->category_list, T, c.category_rows, w.sort_ws[1], w.sort_ws_bytes[1], &h->sk[1], &h->sp[1], h->side));
+  MTAM_TRY(sort_by_row(batch->position_list, T, c.position_rows, w.sort_ws[2], w.sort_ws_bytes[2], &h->sk[2], &h->sp[2], h->side));
+  MTAM_TRY(sort_by_row(batch->user_id, batch->B, c.user_rows, w.sort_ws[3], w.sort_ws_bytes[3], &h->sk[3], &h->sp[3], h->side));
+  MTAM_CUDA_CHECK(cudaEventRecord(h->ev_join, h->side));
+  h->sort_pending = true;
+  h->item_rows_ext = item_rows;
+  h->rows_mode = true;
+  const int r = fwd_dispatch(h, &bt, batch->B, scalars_out, false, st);
+  h->item_rows_ext = nullptr;
+  h->rows_mode = false;
+  MTAM_TRY(r);
+  if (pred_out)
+    MTAM_CUDA_CHECK(cudaMemcpyAsync(pred_out, w.pred, (size_t)batch->B * c.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int mtam_backward_rows(mtam_handle h, const mtam_batch* batch, const float* item_rows, const float* dpred,
+                       int32_t global_batch, float* norm_sq_sparse, void* stream) {
+  mtam_batch bt;
+  MTAM_TRY(rows_batch(h, batch, item_rows, &bt));
+  if (!dpred || !norm_sq_sparse) return set_error(MTAM_ERR_INVALID, "dpred / norm_sq_sparse is null");
+  cudaStream_t st = (cudaStream_t)stream;
+  MTAM_CUDA_CHECK(cudaMemcpyAsync(h->ws.dpred, dpred, (size_t)batch->B * h->cfg.D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  h->item_rows_ext = item_rows;
+  h->rows_mode = true;
+  const int r = bwd_dispatch(h, &bt, global_batch, norm_sq_sparse, st);
+  h->item_rows_ext = nullptr;
+  h->rows_mode = false;
+  MTAM_TRY(r);
+  h->last_batch = *batch;
+  h->last_B = batch->B;
+  h->grads_pending = true;
+  return 0;
+}
+
+// out[0] += sum of x[i]^2 (the dense pieces of tf.clip_by_global_norm's norm, base_model.py:294)
+int mtam_sumsq(const float* x, int64_t n, float* out_accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !out_accumulate || n < 0) return set_error(MTAM_ERR_INVALID, "mtam_sumsq: bad argument");
+  if (n == 0) return 0;
+  if ((uintptr_t)x % 16) return set_error(MTAM_ERR_INVALID, "mtam_sumsq: x must be 16-byte aligned");
+  const int np = sumsq_num_partials(n);
+  if (!workspace || workspace_bytes < (size_t)np * sizeof(float)) return set_error(MTAM_ERR_WORKSPACE, "mtam_sumsq: workspace too small");
+  int got = 0;
+  MTAM_TRY(sumsq_partials(x, n, (float*)workspace, &got, (cudaStream_t)stream));
+  return finalize_sum((float*)workspace, got, 1.0f, out_accumulate, 1, (cudaStream_t)stream);
+}
+size_t mtam_sumsq_workspace(int64_t n) { return (size_t)sumsq_num_partials(n) * sizeof(float) + 256; }
 
 int mtam_forward_backward(mtam_handle h, const mtam_batch* batch, int32_t global_batch, float* scalars_out,
                           float* norm_sq_sparse, void* stream) {

@@ -124,6 +124,7 @@ int sumsq_partials(const float* x, int64_t n, float* partial, int* n_partial, cu
 int clip_scale(const float* norm_sq, float clip, float* gn_out, float* scale_out, cudaStream_t st);
 int set_scalar(float* p, float v, cudaStream_t st);
 int set_scalar_u32(uint32_t* p, uint32_t v, cudaStream_t st);
+int fill_iota(int32_t* p, int64_t n, cudaStream_t st);
 int sgd_apply(float* w, const float* g, int64_t n, const float* scale_p, const float* lr, cudaStream_t st);
 int adam_apply(float* w, float* m, float* v, const float* g, int64_t n, const float* scale_p, const float* lr_t, float b1,
                float b2, float eps, cudaStream_t st);

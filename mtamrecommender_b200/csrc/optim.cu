@@ -59,6 +59,17 @@ int set_scalar(float* p, float v, cudaStream_t st) {
   return 0;
 }
 
+__global__ void iota_kernel(int32_t* p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
+}
+int fill_iota(int32_t* p, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  iota_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, n);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void set_scalar_u32_kernel(uint32_t* p, uint32_t v) { p[0] = v; }
 int set_scalar_u32(uint32_t* p, uint32_t v, cudaStream_t st) {
   set_scalar_u32_kernel<<<1, 1, 0, st>>>(p, v);

@@ -134,6 +134,7 @@ class Engine:
         self._graph = None
         self._graph_B = -1
         self.last_scalars = np.zeros(_lib.S_COUNT, np.float32)
+        self.item_id_bound = None        # set by parallel.ShardedItemTableTrainer: the catalogue's row count
         self._h2d_done = None
         if seed is not None:
             self.init_random(seed)
@@ -243,7 +244,8 @@ class Engine:
         """The gather / scatter kernels index the tables unchecked (as tf.gather does on the GPU): reject feeds whose
         ids fall outside the tables, or whose lengths fall outside [2, L], on the host."""
         c = self.cfg
-        bounds = (("user_id", c.user_count + 3), ("item_list", c.item_count + 3), ("target_item_id", c.item_count + 3),
+        items = self.item_id_bound or c.item_count + 3      # (row-sharded item table: ids are global)
+        bounds = (("user_id", c.user_count + 3), ("item_list", items), ("target_item_id", items),
                   ("category_list", c.category_count + 3), ("position_list", c.L + 3))
         for k, hi in bounds:
             a = np.asarray(feed[k])

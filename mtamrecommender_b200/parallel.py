@@ -17,7 +17,7 @@ The reference has no data parallelism (one tf.Session on one device)
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict
+from typing import Dict, Optional
 
 import numpy as np
 import torch
@@ -208,28 +208,49 @@ class ShardedCatalogue:
         S = shard_rows(table.shape[0], world)
         return ShardedCatalogue(table[rank * S: min(table.shape[0], (rank + 1) * S)].clone(), table.shape[0], group)
 
-    def lookup(self, ids: torch.Tensor) -> torch.Tensor:
-        """rows[i] = table[ids[i]] for ids anywhere in the catalogue (int32, any shape) -> [..., D]."""
+    def route(self, ids: torch.Tensor) -> dict:
+        """The exchange plan of a lookup: ids bucketed by owner (stable), split sizes, and the ids each owner receives.
+        One host synchronisation (the split sizes of the all-to-all); reused by `scatter_back`."""
         flat = ids.reshape(-1).contiguous()
-        n, W, dev = flat.numel(), self.world, flat.device
+        W, dev = self.world, flat.device
         owner = torch.div(flat, self.rows_per_shard, rounding_mode="floor").to(torch.int32)
         srt = sort_indices(owner, W)                              # stable: ids of one owner stay in request order
-        send_ids = flat[srt.perm.long()]
+        perm = srt.perm.long()
+        send_ids = flat[perm]
         send_counts = torch.bincount(srt.keys_sorted.long(), minlength=W)
         recv_counts = torch.empty_like(send_counts)
         dist.all_to_all_single(recv_counts, send_counts, group=self.group)
-        sc, rc = send_counts.tolist(), recv_counts.tolist()        # host sync: split sizes of the exchange
+        both = torch.stack([send_counts, recv_counts]).to("cpu", non_blocking=False)     # the one host sync
+        sc, rc = both[0].tolist(), both[1].tolist()
         recv_ids = torch.empty(sum(rc), dtype=torch.int32, device=dev)
         dist.all_to_all_single(recv_ids, send_ids, rc, sc, group=self.group)
-        local = gather(self.shard, recv_ids - self.row_begin) if recv_ids.numel() else \
-            torch.empty((0, self.D), dtype=torch.float32, device=dev)
-        back = torch.empty((n, self.D), dtype=torch.float32, device=dev)
-        dist.all_to_all_single(back, local, sc, rc, group=self.group)
-        out = torch.empty_like(back)
-        out[srt.perm.long()] = back
-        return out.reshape(*ids.shape, self.D)
+        return dict(n=flat.numel(), shape=tuple(ids.shape), perm=perm, sc=sc, rc=rc, recv_local=recv_ids - self.row_begin)
 
-    def softmax_ce(self, pred: torch.Tensor, target: torch.Tensor, gemm_mode: int = _lib.GEMM_TF32X3):
+    def lookup(self, ids: torch.Tensor, plan: Optional[dict] = None) -> torch.Tensor:
+        """rows[i] = table[ids[i]] for ids anywhere in the catalogue (int32, any shape) -> [..., D]."""
+        plan = plan or self.route(ids)
+        dev = self.shard.device
+        local = gather(self.shard, plan["recv_local"]) if plan["recv_local"].numel() else \
+            torch.empty((0, self.D), dtype=torch.float32, device=dev)
+        back = torch.empty((plan["n"], self.D), dtype=torch.float32, device=dev)
+        dist.all_to_all_single(back, local, plan["sc"], plan["rc"], group=self.group)
+        out = torch.empty_like(back)
+        out[plan["perm"]] = back
+        return out.reshape(*plan["shape"], self.D)
+
+    def scatter_back(self, plan: dict, grad_rows: torch.Tensor, dshard: torch.Tensor, workspace=None) -> None:
+        """The transpose of `lookup`: dshard[id - row_begin] += grad_rows[i] for every looked-up id, on the owning rank
+        (all-to-all of the gradient rows to the owners, then the deterministic scatter-add).  grad_rows [n, D] may be a
+        strided view."""
+        dev = self.shard.device
+        send = grad_rows.reshape(plan["n"], -1)[plan["perm"]].contiguous()
+        recv = torch.empty((sum(plan["rc"]), self.D), dtype=torch.float32, device=dev)
+        dist.all_to_all_single(recv, send, plan["rc"], plan["sc"], group=self.group)
+        if recv.shape[0]:
+            scatter_add(dshard, plan["recv_local"], recv, workspace)
+
+    def softmax_ce(self, pred: torch.Tensor, target: torch.Tensor, gemm_mode: int = _lib.GEMM_TF32X3,
+                   dshard_out: Optional[torch.Tensor] = None):
         """pred [B_local, D], target [B_local] int32 global item ids -> (loss_origin [B_local] = -log softmax at the
         target, dpred [B_local, D] and dshard [shard rows, D] for the MEAN loss over the global batch)."""
         W, Bl = self.world, pred.shape[0]
@@ -244,7 +265,7 @@ class ShardedCatalogue:
         dist.all_gather_into_tensor(all_lse, lse_r, group=self.group)
         dist.all_reduce(tl, group=self.group)
         lse = combine_lse(all_lse)
-        dshard, dp = softmax_ce_backward(allp, self.shard, rel, lse, 1.0 / (W * Bl), gemm_mode)
+        dshard, dp = softmax_ce_backward(allp, self.shard, rel, lse, 1.0 / (W * Bl), gemm_mode, dtable=dshard_out)
         dpred = torch.empty((Bl, self.D), dtype=torch.float32, device=dev)
         dist.reduce_scatter_tensor(dpred, dp, group=self.group)
         mine = slice(self.rank * Bl, (self.rank + 1) * Bl)
@@ -265,3 +286,134 @@ class ShardedCatalogue:
         dist.all_gather_into_tensor(g_sc, sc, group=self.group)
         mine = slice(self.rank * Bl, (self.rank + 1) * Bl)
         return merge_topk(g_idx[:, mine].contiguous(), g_sc[:, mine].contiguous())
+
+
+class ShardedItemTableTrainer:
+    """MTAM train step with the item table row-sharded over the ranks -- the scalable training variant of SURVEY 8e
+    (BASELINE configs[3]: 10 M items).  The data-parallel step above all-reduces the dense [V, D] item-table gradient
+    (2.56 GB at 10 M items) and all-gathers the sparse rows; here every rank owns V/N rows of the table, its Adam slots
+    and its gradient, and per step
+      1. the item rows of the rank's tokens come from their owners (all-to-all, `ShardedCatalogue.lookup`);
+      2. mtam_forward_rows runs the model on them up to pred;
+      3. the softmax cross-entropy runs against the shard (all-gather of pred, per-shard log-sum-exp, combination,
+         per-shard backward): the shard's dense table gradient is complete and local, dpred is reduce-scattered;
+      4. mtam_backward_rows runs the backward chain from dpred;
+      5. the gradient rows of the looked-up items go back to their owners (all-to-all) and are scatter-added there;
+      6. ONE all-reduce carries the dense parameter gradients, the loss scalars and the squared norm of the
+         rank-local pieces (shard gradient + un-deduplicated sparse pieces, trap T1); category / position pieces are
+         densified locally and all-reduced, the user rows all-gathered (as in DataParallel);
+      7. identical clip on every rank, Adam on the shard and on the replicated parameters (mtam_apply).
+    The engine is built with item_count + 3 == rows per shard; `total_item_rows` is the catalogue's V.
+    Contract: equal to the single-GPU step on the concatenated batch within the fp32 tolerances of the tests (the
+    log-sum-exp is combined across shards in another order)."""
+
+    def __init__(self, engine: Engine, total_item_rows: int, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        if engine.cfg.kind != "MTAM":
+            raise NotImplementedError("ShardedItemTableTrainer: MTAM only")
+        self.eng, self.group = engine, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        c = engine.c_cfg
+        S = shard_rows(total_item_rows, self.world)
+        if c.item_rows != S:
+            raise ValueError(f"engine has {c.item_rows} item rows, a shard of {total_item_rows} over {self.world} ranks has {S}")
+        self.total_rows = int(total_item_rows)
+        lo, hi = self.rank * S, min(self.total_rows, (self.rank + 1) * S)
+        self.local_rows = max(hi - lo, 0)
+        self.cat = ShardedCatalogue(engine.param_view("embedding_layer/item")[: self.local_rows], self.total_rows, group)
+        dev, D, B, L, W = engine.device, engine.cfg.D, engine.cfg.max_batch, engine.cfg.L, self.world
+        self.sp = torch.zeros((c.category_rows + c.position_rows, D), dtype=torch.float32, device=dev)   # [category | position]
+        self.g_user = torch.empty(W * B, dtype=torch.int32, device=dev)
+        self.g_dEu = torch.empty((W * B, D), dtype=torch.float32, device=dev)
+        need = max(scatter_add_workspace(W * B, c.user_rows, D), scatter_add_workspace(W * B * L, c.item_rows, D))
+        self.scatter_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        self.sumsq_ws = torch.empty(int(engine.lib.mtam_sumsq_workspace(engine.n_floats)), dtype=torch.uint8, device=dev)
+        self.loss_origin = None
+        engine.item_id_bound = self.total_rows
+
+    def init_shard_from_full(self, full_table: torch.Tensor) -> None:
+        """Copies this rank's rows of a full [V, D] table into the engine (tests / imports)."""
+        S = self.cat.rows_per_shard
+        v = self.eng.param_view("embedding_layer/item")
+        v.zero_()
+        v[: self.local_rows].copy_(full_table[self.rank * S: self.rank * S + self.local_rows])
+
+    def _sumsq_into_norm(self, x: torch.Tensor) -> None:
+        eng = self.eng
+        check(eng.lib.mtam_sumsq(x.data_ptr(), x.numel(), eng.norm_sq.data_ptr(), self.sumsq_ws.data_ptr(), self.sumsq_ws.numel(),
+                                 torch.cuda.current_stream(eng.device).cuda_stream), "mtam_sumsq")
+
+    def train_step_device(self, batch: DeviceBatch, lr: float) -> None:
+        eng, W = self.eng, self.world
+        B, L, D = batch.B, eng.cfg.L, eng.cfg.D
+        T = B * L
+        c = eng.c_cfg
+        st = torch.cuda.current_stream(eng.device).cuda_stream
+        # 1. item rows from their owners
+        plan = self.cat.route(batch.t["item_list"])
+        rows = self.cat.lookup(batch.t["item_list"], plan).reshape(T, D)
+        # 2. forward up to pred
+        pred = torch.empty((B, D), dtype=torch.float32, device=eng.device)
+        eng.norm_sq.zero_()
+        eng.scalars.zero_()
+        check(eng.lib.mtam_forward_rows(eng.h, C.byref(batch.c), rows.data_ptr(), pred.data_ptr(), eng.scalars.data_ptr(), st),
+              "mtam_forward_rows")
+        # 3. softmax cross-entropy against the sharded table; the shard's dense gradient lands in the grads arena
+        sv = _lib.SparseView()
+        check(eng.lib.mtam_sparse_pieces(eng.h, C.byref(sv)), "mtam_sparse_pieces")
+        item_lo = int(sv.item_offset)
+        item_hi = item_lo + c.item_rows * D
+        g_item = eng.grads[item_lo:item_hi].view(c.item_rows, D)
+        if self.local_rows < c.item_rows:
+            g_item[self.local_rows:].zero_()
+        loss_origin, dpred, _ = self.cat.softmax_ce(pred, batch.t["target_item_id"], eng.cfg.gemm_mode,
+                                                    dshard_out=g_item[: self.local_rows])
+        self.loss_origin = loss_origin
+        # 4. backward chain from dpred
+        check(eng.lib.mtam_backward_rows(eng.h, C.byref(batch.c), rows.data_ptr(), dpred.contiguous().data_ptr(), B * W,
+                                         eng.norm_sq.data_ptr(), st), "mtam_backward_rows")
+        # rank-local pieces of the global norm: the shard's dense gradient (the un-deduplicated sparse pieces were added
+        # by the backward pass); loss scalars of the rank's rows
+        self._sumsq_into_norm(g_item[: self.local_rows])
+        eng.scalars[_lib.S_LOSS_ORIGIN] = loss_origin.sum() / float(B * W)
+        # 6. one all-reduce: [dense parameter gradients | scalars | norm^2]
+        dist.all_reduce(eng._grads_all[item_hi: eng.n_floats + _lib.S_COUNT + 1], group=self.group)
+        self._sumsq_into_norm(eng.grads[item_hi: eng.n_floats])          # replicated pieces: counted once
+        eng.scalars[_lib.S_LOSS] = eng.scalars[_lib.S_LOSS_ORIGIN] + eng.cfg.reg * eng.scalars[_lib.S_L2_NORM]
+        # 5. item gradient rows back to their owners, added to the shard's gradient
+        off = int(sv.item_cat_rows) - eng.workspace.data_ptr()
+        dE2 = eng.workspace[off: off + T * 2 * D * 4].view(torch.float32).view(T, 2 * D)
+        self.cat.scatter_back(plan, dE2[:, :D], g_item[: max(self.local_rows, 1)], self.scatter_ws)
+        # category / position: densified locally, all-reduced; user rows: all-gathered
+        self.sp.zero_()
+        sp_cat, sp_pos = self.sp[: c.category_rows], self.sp[c.category_rows:]
+        check(eng.lib.mtam_scatter_sparse_into(eng.h, None, sp_cat.data_ptr(), sp_pos.data_ptr(), None, st), "mtam_scatter_sparse_into")
+        dist.all_reduce(self.sp, group=self.group)
+        eng.grads[int(sv.category_offset): int(sv.category_offset) + c.category_rows * D].view(c.category_rows, D).copy_(sp_cat)
+        eng.grads[int(sv.position_offset): int(sv.position_offset) + c.position_rows * D].view(c.position_rows, D).copy_(sp_pos)
+        g_user = self.g_user[: W * B]
+        dist.all_gather_into_tensor(g_user, batch.t["user_id"].contiguous(), group=self.group)
+        g_dEu = self.g_dEu[: W * B]
+        offu = int(sv.user_rows) - eng.workspace.data_ptr()
+        dEu = eng.workspace[offu: offu + B * D * 4].view(torch.float32).view(B, D)
+        dist.all_gather_into_tensor(g_dEu, dEu, group=self.group)
+        g_usr = eng.grads[int(sv.user_offset): int(sv.user_offset) + c.user_rows * D].view(c.user_rows, D)
+        scatter_add(g_usr, g_user, g_dEu, self.scatter_ws)
+        # 7. clip + Adam (shard + replicated parameters)
+        eng.apply(lr)
+        g_usr.index_fill_(0, g_user.long(), 0.0)     # apply() re-zeroes only the local users' rows
+
+    def train_step(self, feed: Dict[str, np.ndarray], lr: float) -> float:
+        self.train_step_device(self.eng.upload(feed), lr)
+        return float(self.eng.read_scalars()[_lib.S_LOSS])
+
+    def eval_topk(self, batch: DeviceBatch, k: int = 50):
+        """metrics_topK over the sharded table: forward on looked-up rows, sharded score + top-k, all-gather merge."""
+        eng = self.eng
+        plan = self.cat.route(batch.t["item_list"])
+        rows = self.cat.lookup(batch.t["item_list"], plan).reshape(batch.B * eng.cfg.L, eng.cfg.D)
+        pred = torch.empty((batch.B, eng.cfg.D), dtype=torch.float32, device=eng.device)
+        check(eng.lib.mtam_forward_rows(eng.h, C.byref(batch.c), rows.data_ptr(), pred.data_ptr(), None,
+                                        torch.cuda.current_stream(eng.device).cuda_stream), "mtam_forward_rows")
+        return self.cat.topk(pred, k)

@@ -27,7 +27,7 @@ def _rank_main(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     from oracle import mtam_oracle as O
     from mtamrecommender_b200 import engine as E
-    from mtamrecommender_b200.parallel import DataParallel, ShardedCatalogue
+    from mtamrecommender_b200.parallel import DataParallel, ShardedCatalogue, ShardedItemTableTrainer, shard_rows
     dev = f"cuda:{rank}"
     out = {}
     # ---- data-parallel step --------------------------------------------------------------------
@@ -58,6 +58,38 @@ def _rank_main(rank, world, port, q):
             out[f"param_err_{mode}"] = max(float(np.linalg.norm(got[k] - want[k]) / max(np.linalg.norm(want[k]), 1e-30))
                                            for k in want)
         del dp, eng
+    # ---- train step over the row-sharded item table == the one-GPU step on the concatenated batch ----
+    S = shard_rows(903, world)
+    for gm in (0, 1):
+        if rank == 0:
+            ref = E.Engine(E.ModelConfig(max_batch=48, gemm_mode=gm, **mc), device=dev)
+            ref.set_params(P)
+            rl = [ref.train_step(full, 1e-3) for _ in range(3)]
+            want = ref.get_params()
+            ridx, _ = ref.eval_topk_device(ref.upload(full), 50)
+        mcs = dict(mc, item_count=S - 3)
+        eng = E.Engine(E.ModelConfig(max_batch=Bl, gemm_mode=gm, **mcs), device=dev)
+        eng.set_params({k: (v if k != "embedding_layer/item" else np.zeros((S, 64), np.float32)) for k, v in P.items()})
+        tr = ShardedItemTableTrainer(eng, 903)
+        tr.init_shard_from_full(torch.from_numpy(P["embedding_layer/item"]).to(dev))
+        losses = [tr.train_step(local, 1e-3) for _ in range(3)]
+        got = eng.get_params()
+        shards = [torch.empty((S, 64), device=dev) for _ in range(world)]
+        dist.all_gather(shards, eng.param_view("embedding_layer/item").contiguous())
+        sidx, _ = tr.eval_topk(eng.upload(local), 50)
+        allidx = [torch.empty_like(sidx) for _ in range(world)]
+        dist.all_gather(allidx, sidx)
+        if rank == 0:
+            table = torch.cat(shards)[:903].cpu().numpy()
+            out[f"sharded_loss_err_{gm}"] = max(abs(a - b) / abs(b) for a, b in zip(losses, rl))
+            errs = {k: float(np.linalg.norm(got[k] - want[k]) / max(np.linalg.norm(want[k]), 1e-30)) for k in want
+                    if k != "embedding_layer/item"}
+            errs["embedding_layer/item"] = float(np.linalg.norm(table - want["embedding_layer/item"]) /
+                                                 np.linalg.norm(want["embedding_layer/item"]))
+            out[f"sharded_param_err_{gm}"] = max(errs.values())
+            out[f"sharded_topk_overlap_{gm}"] = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / 50.0
+                                                                 for a, b in zip(torch.cat(allidx).cpu(), ridx.cpu())]))
+        del tr, eng
     # ---- row-sharded catalogue -----------------------------------------------------------------
     V, D, k = 20011, 64, 50
     g = torch.Generator().manual_seed(11)
@@ -122,3 +154,7 @@ def test_two_gpu_dp_and_sharded_catalogue():
     for mode in ("dense", "gather"):
         assert res[0][f"loss_err_{mode}"] < 2e-5, res[0]
         assert res[0][f"param_err_{mode}"] < 1e-4, res[0]
+    for gm in (0, 1):      # the sharded-table step: same losses, same weights (item table gathered back from the shards)
+        assert res[0][f"sharded_loss_err_{gm}"] < 2e-5, res[0]
+        assert res[0][f"sharded_param_err_{gm}"] < 1e-4, res[0]
+        assert res[0][f"sharded_topk_overlap_{gm}"] > 0.99, res[0]
