@@ -385,10 +385,73 @@ def _run_cuda(args, w):
                "rooflines_top_phases": roofs, "bandwidth_kernels": bw, "eval_topk": ev}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(w)
+    # BASELINE configs[3] in the same run (every rank takes part; rank 0 reports)
+    if args.workload == "cfg3" and not args.no_cfg4:
+        del eng, dp, batches
+        torch.cuda.empty_cache()
+        c4 = cfg4_section(args, rank, world, local, dev, timed)
+        if out is not None:
+            out["cfg4"] = c4
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return json.dumps(out) if out is not None else None
+
+
+def cfg4_section(args, rank, world, local, dev, timed_fn):
+    """BASELINE configs[3]: synthetic MTAMRec, 10 M items, seq len 200, GLOBAL batch 8192 (strong scaling: 8192 / N
+    sequences per GPU).  N = 1: the plain engine.  N > 1: the item table row-sharded over the ranks
+    (parallel.ShardedItemTableTrainer: all-to-all lookup, sharded softmax CE with a rank-local table gradient, one
+    all-reduce for the replicated parameters) -- the dense [10 M, 64] table gradient is never all-reduced."""
+    import torch
+    import torch.distributed as dist
+    from mtamrecommender_b200 import _lib, engine as E
+    from mtamrecommender_b200.synth import ZipfSampler, synth_feed
+    w = dict(WORKLOADS["cfg4"])
+    GB = 8192
+    B = GB // world
+    gm = _lib.GEMM_TF32X3 if args.gemm_mode == "tf32x3" else _lib.GEMM_FP32
+    V = w["items"] + 3
+    try:
+        if world > 1:
+            from mtamrecommender_b200.parallel import ShardedItemTableTrainer, shard_rows
+            S = shard_rows(V, world)
+            eng = E.Engine(E.ModelConfig(kind="MTAM", max_batch=B, L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
+                                         item_count=S - 3, category_count=w["cats"], gemm_mode=gm), device=dev, seed=1234 + rank)
+            # replicated parameters must start identical: broadcast everything but the item shard from rank 0
+            sv_lo = int(eng.info["embedding_layer/item"].offset)
+            sv_hi = sv_lo + S * w["D"]
+            dist.broadcast(eng.params[:sv_lo], 0)
+            dist.broadcast(eng.params[sv_hi:], 0)
+            tr = ShardedItemTableTrainer(eng, V)
+            step = lambda b: tr.train_step_device(b, LR)
+            par = f"item table row-sharded over {world} ranks + data parallel (global batch {GB})"
+        else:
+            eng = E.Engine(E.ModelConfig(kind="MTAM", max_batch=B, L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
+                                         item_count=w["items"], category_count=w["cats"], gemm_mode=gm), device=dev, seed=1234)
+            step = lambda b: eng.train_step_device(b, LR)
+            par = "one GPU"
+        samp = ZipfSampler(w["items"], 1.05)
+        feeds = [synth_feed(B, w["L"], w["items"], w["cats"], w["users"], 777 + 10 * rank + i, samp) for i in range(2)]
+        batches = [eng.device_batch({k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in f.items()}) for f in feeds]
+        for i in range(3):
+            step(batches[i % 2])
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        steps = max(3, min(args.steps, 8))
+        ms = timed_fn(lambda i: step(batches[i % 2]), steps)
+        clk = clocks.stop() if rank == 0 else {}
+        loss = float(eng.read_scalars()[_lib.S_LOSS])
+        out = {"workload": "cfg4 (BASELINE configs[3])", "items": w["items"], "seq_len": w["L"], "global_batch": GB,
+               "batch_per_gpu": B, "n_gpus": world, "parallelism": par, "steps": steps, "ms_per_step": ms / steps,
+               "seq_per_s": GB * steps / (ms / 1e3), "scaling": "strong", "loss": loss, "clocks": clk,
+               "gemm_mode": args.gemm_mode}
+        del eng
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:   # report, never hide
+        return {"workload": "cfg4", "error": repr(e)}
 
 
 def eval_topk_bench(eng, batches, w, pk, k=50, reps=10):
@@ -519,6 +582,7 @@ def main():
     ap.add_argument("--gemm-mode", default="tf32x3", choices=["tf32x3", "fp32"],
                     help="dense contractions: tcgen05 3-term-split TF32 (fp32-class accuracy) or exact fp32 FFMA")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the cfg4 (10 M items, global batch 8192) section")
     ap.add_argument("--cpu-batch", type=int, default=0,
                     help="sequences per step of the CPU arm; 0 = the workload's own batch size (the default)")
     args = ap.parse_args()

@@ -191,3 +191,46 @@ def test_mtam_via_t_gru_restatement_structure():
     Pa = {k: v for k, v in P.items() if k in O.param_shapes(a)}
     assert np.array_equal(O.forward(b, P, f2)["pred"].numpy(), out["pred"].numpy())
     assert not np.array_equal(O.forward(a, Pa, f2)["pred"].numpy(), O.forward(a, Pa, feed)["pred"].numpy())
+
+
+@pytest.mark.parametrize("case", [dict(L=9, D=32, H=4, N=2, B=11, users=20, items=120, cats=6),
+                                  dict(L=14, D=64, H=1, N=3, B=7, users=9, items=60, cats=4)])
+def test_two_independent_restatements_agree(case):
+    """oracle/mtam_oracle.py (torch fp64 + autograd) against oracle/mtam_oracle_np.py (NumPy fp64, backward derived by
+    hand, written separately from the same reference files): loss, pred, every gradient, the un-deduplicated global norm
+    (trap T1) and the weights after three TF-style Adam steps (trap T2) agree to fp64 rounding.  The oracle stays
+    unpinned against TensorFlow itself, but a transcription slip would have to be made twice, identically."""
+    from oracle import mtam_oracle_np as N2
+    cfg = O.OracleConfig(kind=O.MTAM, L=case["L"], D=case["D"], H=case["H"], N=case["N"], user_count=case["users"],
+                         item_count=case["items"], category_count=case["cats"])
+    P = O.init_params(cfg, 21)
+    rng = np.random.default_rng(22)
+    for k in P:
+        if k.endswith("/bias") or k.endswith("/beta"):
+            P[k] = (P[k] + 0.1 * rng.standard_normal(P[k].shape)).astype(np.float32)
+    feed = O.synth_batch(cfg, case["B"], 23)
+    fwd, grads, pieces = O.loss_and_grads(cfg, P, feed)
+    out2, grads2, pieces2 = N2.forward_backward(P, feed, cfg.L, cfg.D, cfg.H, cfg.N, cfg.reg)
+    assert abs(out2["loss"] - float(fwd["loss"].detach())) < 1e-12 * abs(out2["loss"])
+    assert np.allclose(out2["pred"], fwd["pred"].detach().numpy(), rtol=1e-11, atol=1e-13)
+    assert np.allclose(out2["loss_origin"], fwd["loss_origin"].detach().numpy(), rtol=1e-11)
+    assert set(grads) == set(grads2)
+    for k, v in grads.items():
+        if v is None:
+            assert grads2[k] is None, k
+        else:
+            err = np.linalg.norm(grads2[k] - v) / max(np.linalg.norm(v), 1e-300)
+            assert err < 1e-9, (k, err)
+    assert abs(N2.global_norm(pieces2) - O.global_norm(pieces)) < 1e-11 * O.global_norm(pieces)
+    tr = O.OracleTrainer(cfg, P)
+    p2 = {k: v.astype(np.float64) for k, v in P.items()}
+    m2 = {k: np.zeros_like(v) for k, v in p2.items()}
+    v2 = {k: np.zeros_like(v) for k, v in p2.items()}
+    for t in range(1, 4):
+        l1 = tr.train_step(feed, 2e-3)
+        o, g2, pc2 = N2.forward_backward(p2, feed, cfg.L, cfg.D, cfg.H, cfg.N, cfg.reg)
+        N2.clip_and_adam(p2, g2, pc2, m2, v2, t, 2e-3, cfg.clip, cfg.beta1, cfg.beta2, cfg.eps)
+        assert abs(o["loss"] - l1) < 1e-10 * abs(l1), t
+    for k in p2:
+        err = np.linalg.norm(p2[k] - tr.params[k]) / max(np.linalg.norm(tr.params[k]), 1e-300)
+        assert err < 1e-9, (k, err)
