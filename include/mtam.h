@@ -45,7 +45,9 @@ typedef enum {
   MTAM_KIND_SASREC = 2,     /* 'SASrec'                            Model/attention_baseline_models.py:33-46 */
   MTAM_KIND_TA_SASREC = 3,  /* 'Time_Aware_Self_Attention_Model'   Model/attention_baseline_models.py:47-65 */
   MTAM_KIND_TISASREC = 4,   /* 'Ti_Self_Attention_Model'           Model/attention_baseline_models.py:66-84 */
-  MTAM_KIND_BPRMF = 5       /* 'bpr'                               Model/BPRMF.py:10-59 */
+  MTAM_KIND_BPRMF = 5,      /* 'bpr'                               Model/BPRMF.py:10-59 */
+  MTAM_KIND_MTAM_VIA_T_GRU = 6  /* 'MTAM_via_T_GRU'                Model/MTAMRec_model.py:167-204: the hops read the
+                               T-GRU's OUTPUT SEQUENCE as their memory, and the query is layer-normed first */
 } mtam_kind;
 
 /* How the dense contractions are computed. */

@@ -1,4 +1,5 @@
-"""MTAM: T-GRU short-term intent + N-hop time-aware attentive memory (Model/MTAMRec_model.py:14-92)."""
+"""MTAM: T-GRU short-term intent + N-hop time-aware attentive memory (Model/MTAMRec_model.py:14-92), and the sibling
+MTAM_via_T_GRU (:167-204), whose hops read the T-GRU's output sequence as their memory."""
 from .base_model import base_model
 
 
@@ -13,3 +14,8 @@ class MTAMRec_model(base_model):
 
 class MTAM(MTAMRec_model):
     pass
+
+
+class MTAM_via_T_GRU(MTAMRec_model):
+    """Model/MTAMRec_model.py:167-204: user_history = the T-GRU output sequence, query = layer_norm(short-term intent)."""
+    KIND = "MTAM_VIA_T_GRU"

@@ -156,13 +156,14 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
 
 // Reverse-time pass.  dGX[t] = [d r_pre | d u_pre | d c_pre] (zero past length; caller memsets),
 // dX[t] += element-wise path, vec_partial[block][8][D] = per-CTA sums of the 8 vector-parameter
-// gradients.  dq0[b] is d loss / d short_term_intent (state after the last real item).
+// gradients.  dq0[b] is d loss / d short_term_intent (state after the last real item); dOut (may be null) is
+// d loss / d output[t] for every step (outputs past seq_len-1 are zeros and carry no gradient).
 template <int D>
 __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
     const float* __restrict__ X, const float* __restrict__ timelast, const int32_t* __restrict__ seq_len,
     const float* __restrict__ Wgru, const float* __restrict__ vecs, const float* __restrict__ Hs,
-    const float* __restrict__ RUCT, const float* __restrict__ dq0, int B, int L, float* __restrict__ dGX,
-    float* __restrict__ dX, float* __restrict__ vec_partial) {
+    const float* __restrict__ RUCT, const float* __restrict__ dq0, const float* __restrict__ dOut, int B, int L,
+    float* __restrict__ dGX, float* __restrict__ dX, float* __restrict__ vec_partial) {
   extern __shared__ __align__(16) float sm[];
   float* WhT = sm;                 // [3D][D]   WhT[n][k] = W_gru[D+k][n]
   float* dpcS = WhT + 3 * D * D;   // [D][RB]
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
 
   // the step's saved activations are independent of the recurrence: the loads of step t-1 are issued at the top of
   // step t and land while its two matrix-vector loops run
-  struct StepIn { float r, u, c, Tg, hold, x, dl, dx; };
+  struct StepIn { float r, u, c, Tg, hold, x, dl, dx, dout; };
   auto fetch = [&](int t, StepIn (&v)[2]) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -202,6 +203,8 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
       v[i].x = ld_nc_pred(X + tok * D + n, live);
       v[i].dl = ld_nc_pred(timelast + tok, live);
       v[i].dx = ld_cg_pred(dX + tok * D + n, live);         // dX[t] is updated in place: read it a step ahead too
+      // d loss / d output[t] when the whole output sequence is consumed (MTAM_via_T_GRU: it is the hops' memory)
+      v[i].dout = dOut ? ld_nc_pred(dOut + tok * D + n, live) : 0.f;
     }
   };
   // part of this thread's weight column lives in registers for all L steps (D <= 64): the candidate path
@@ -229,6 +232,7 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
         int64_t b = b0 + row;
         int64_t tok = b * L + t;
         if (t == steps[row] - 1) dh[i] += __ldg(dq0 + b * D + n);
+        dh[i] += cur[i].dout;
         const float r = cur[i].r, u = cur[i].u, c = cur[i].c, Tg = cur[i].Tg, hold = cur[i].hold, x = cur[i].x,
                     dl = cur[i].dl;
         float d = dh[i];
@@ -335,11 +339,11 @@ static int gru_fwd_launch(const float* X, const float* GX, const float* timelast
 }
 template <int D>
 static int gru_bwd_launch(const float* X, const float* timelast, const int32_t* seq_len, const float* Wgru,
-                          const float* vecs, const float* Hs, const float* RUCT, const float* dq0, int B, int L,
+                          const float* vecs, const float* Hs, const float* RUCT, const float* dq0, const float* dOut, int B, int L,
                           float* dGX, float* dX, float* vec_partial, cudaStream_t st) {
   size_t smem = gru_smem_bytes(D);
   MTAM_CUDA_CHECK(cudaFuncSetAttribute(gru_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gru_bwd_kernel<D><<<gru_num_blocks(B), 4 * D, smem, st>>>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, B, L, dGX,
+  gru_bwd_kernel<D><<<gru_num_blocks(B), 4 * D, smem, st>>>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, dOut, B, L, dGX,
                                                           dX, vec_partial);
   MTAM_LAUNCH_CHECK();
   return 0;
@@ -356,12 +360,12 @@ int gru_forward(int D, const float* X, const float* GX, const float* timelast, c
   return set_error(-1, "T-GRU: num_units=%d not supported (32, 64, 128)", D);
 }
 int gru_backward(int D, const float* X, const float* timelast, const int32_t* seq_len, const float* Wgru,
-                 const float* vecs, const float* Hs, const float* RUCT, const float* dq0, int B, int L, float* dGX,
+                 const float* vecs, const float* Hs, const float* RUCT, const float* dq0, const float* dOut, int B, int L, float* dGX,
                  float* dX, float* vec_partial, cudaStream_t st) {
   switch (D) {
-    case 32: return gru_bwd_launch<32>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, B, L, dGX, dX, vec_partial, st);
-    case 64: return gru_bwd_launch<64>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, B, L, dGX, dX, vec_partial, st);
-    case 128: return gru_bwd_launch<128>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, B, L, dGX, dX, vec_partial, st);
+    case 32: return gru_bwd_launch<32>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, dOut, B, L, dGX, dX, vec_partial, st);
+    case 64: return gru_bwd_launch<64>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, dOut, B, L, dGX, dX, vec_partial, st);
+    case 128: return gru_bwd_launch<128>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, dOut, B, L, dGX, dX, vec_partial, st);
   }
   return set_error(-1, "T-GRU: num_units=%d not supported (32, 64, 128)", D);
 }

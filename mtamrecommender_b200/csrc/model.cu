@@ -27,7 +27,7 @@ static const char* kGateLive[5] = {"_time_input_w1", "_time_input_b1", "time_out
 // norm can skip them; every block starts on a 4-float boundary.
 struct Layout {
   size_t user = 0, cat = 0, pos = 0, dense_begin = 0, item = 0, Wemb = 0, Wgru = 0, bgru = 0, gruvec = 0, Wq = 0,
-         bq = 0, Wkv = 0, bkv = 0, Wt = 0, gate = 0, gate_dead = 0, lnb = 0, lng = 0, lnfb = 0, lnfg = 0, item_b = 0,
+         bq = 0, Wkv = 0, bkv = 0, Wt = 0, gate = 0, gate_dead = 0, lnb = 0, lng = 0, lnfb = 0, lnfg = 0, lnsb = 0, lnsg = 0, item_b = 0,
          total = 0;
   SaLayout sa;
   std::vector<ParamDesc> params;
@@ -37,6 +37,7 @@ struct Workspace {
   // activations
   float *E2, *R, *X, *GX, *Hs, *RUCT, *RH, *KV;
   float *Qin, *Qr, *Qt, *AA, *PA, *ZZ, *DK, *GT, *XH, *RSTD, *XHF, *RSTDF, *pred;
+  float *q0raw, *dq0raw, *XHS, *RSTDS;   // MTAM_via_T_GRU: the short-term intent before its layer norm, and the norm's state
   float *tlogit, *lse, *loss_origin;
   // gradients of activations
   float *dpred, *dX, *dKV, *DOUT, *DQP, *DQT, *BKV, *GB, *dq0, *WqT, *WtT, *dGX, *vec_partial, *dR, *dE2, *dEp, *dEu;
@@ -92,6 +93,8 @@ struct mtam_model {
 
 namespace mtam {
 
+static inline bool is_mtam_family(int kind) { return kind == MTAM_KIND_MTAM || kind == MTAM_KIND_MTAM_VIA_T_GRU; }
+
 // phase boundary marker (cudaEventRecord on the step's stream when profiling is on)
 static inline void phase(mtam_model* h, int id, cudaStream_t st) {
   if (!h->prof) return;
@@ -128,7 +131,7 @@ static int build_layout(const mtam_config& c, Layout& l) {
     l.total = o;
     return 0;
   }
-  if (c.kind == MTAM_KIND_MTAM) {
+  if (is_mtam_family(c.kind)) {
     const std::string g = "ShortTermIntentEncoder/";
     l.Wgru = take((size_t)2 * D * 3 * D);
     add_param(l, g + "gates/kernel", 2 * D, 2 * D, 2, 3 * D, l.Wgru);
@@ -168,6 +171,12 @@ static int build_layout(const mtam_config& c, Layout& l) {
     l.lnfg = take(D);
     add_param(l, "NextItemDecoder/LayerNorm/beta", 1, D, 1, D, l.lnfb);
     add_param(l, "NextItemDecoder/LayerNorm/gamma", 1, D, 1, D, l.lnfg);
+    if (c.kind == MTAM_KIND_MTAM_VIA_T_GRU) {   // layer_norm of the short-term intent (MTAMRec_model.py:187)
+      l.lnsb = take(D);
+      l.lnsg = take(D);
+      add_param(l, g + "LayerNorm/beta", 1, D, 1, D, l.lnsb);
+      add_param(l, g + "LayerNorm/gamma", 1, D, 1, D, l.lnsg);
+    }
     l.total = o;
     return 0;
   }
@@ -209,7 +218,11 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
   auto G = [&](int M, int Nn, int K) { gemm_ws = std::max(gemm_ws, gemm_any_workspace_bytes(M, Nn, K)); };
   auto CS = [&](int M, int Nn) { colsum_ws = std::max(colsum_ws, colsum_workspace_bytes(M, Nn)); };
   G(2 * D, D, T);  // dWemb
-  if (c.kind == MTAM_KIND_MTAM) {
+  if (is_mtam_family(c.kind)) {
+    w.q0raw = b.take<float>(B * D);
+    w.dq0raw = b.take<float>(B * D);
+    w.XHS = b.take<float>(B * D);
+    w.RSTDS = b.take<float>(B);
     w.GX = b.take<float>(T * 3 * D);
     w.Hs = b.take<float>((T + 1) * D);
     w.RUCT = b.take<float>(T * 4 * D);
@@ -288,7 +301,7 @@ static int validate(const mtam_config* c) {
   if (!c) return set_error(MTAM_ERR_INVALID, "config is null");
   if (c->abi_version != MTAM_ABI_VERSION)
     return set_error(MTAM_ERR_INVALID, "abi_version %d != %d", c->abi_version, MTAM_ABI_VERSION);
-  if (c->kind < 0 || c->kind > MTAM_KIND_BPRMF) return set_error(MTAM_ERR_INVALID, "unknown model kind %d", c->kind);
+  if (c->kind < 0 || c->kind > MTAM_KIND_MTAM_VIA_T_GRU) return set_error(MTAM_ERR_INVALID, "unknown model kind %d", c->kind);
   if (c->D != 32 && c->D != 64 && c->D != 128)
     return set_error(MTAM_ERR_INVALID, "num_units=%d not supported (32, 64 or 128)", c->D);
   if (c->max_batch < 1 || c->L < 1 || c->N < 0) return set_error(MTAM_ERR_INVALID, "bad max_batch/L/N");
@@ -333,7 +346,10 @@ static HopArgs hop_args(mtam_model* h, const mtam_batch* bt) {
   HopArgs a;
   a.B = bt->B; a.L = c.L; a.D = c.D; a.H = c.H; a.N = c.N;
   a.seq_len = bt->seq_length; a.target_time = bt->target_item_time; a.time_list = bt->time_list;
-  a.X = w.X; a.KV = w.KV;
+  // the hops' memory ("user_history"): the embedded behaviours, or the T-GRU's output sequence (Hs holds h_{t-1} per
+  // row with a leading zero row, so the outputs -- zero from step seq_len-1 on, as dynamic_rnn leaves them -- are Hs + D)
+  a.X = c.kind == MTAM_KIND_MTAM_VIA_T_GRU ? w.Hs + c.D : w.X;
+  a.KV = w.KV;
   a.Wq = h->params + l.Wq; a.bq = h->params + l.bq; a.Wt = h->params + l.Wt; a.gate = h->params + l.gate;
   a.ln_gamma = h->params + l.lng; a.ln_beta = h->params + l.lnb;
   a.lnf_gamma = h->params + l.lnfg; a.lnf_beta = h->params + l.lnfb;
@@ -394,14 +410,17 @@ static int mtam_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   phase(h, MTAM_PH_GRU_FWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.Hs, 0, (size_t)(T + 1) * D * sizeof(float), st));
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.RH, 0, (size_t)T * D * sizeof(float), st));
+  const bool via = c.kind == MTAM_KIND_MTAM_VIA_T_GRU;
   MTAM_TRY(gru_forward(D, w.X, w.GX, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, B, L, w.Hs, w.RUCT,
-                       w.RH, w.Qin, st));
+                       w.RH, via ? w.q0raw : w.Qin, st));
+  if (via)   // short_term_intent = layer_norm(gather(...))  (MTAMRec_model.py:182-187)
+    MTAM_TRY(ln_rows_forward(w.q0raw, B, D, P + l.lnsg, P + l.lnsb, w.Qin, w.XHS, w.RSTDS, st));
   phase(h, MTAM_PH_KV_GEMM, st);
-  {  // K,V of all hops: relu([T,D] x [D,2ND] + b)
+  {  // K,V of all hops: relu(memory [T,D] x [D,2ND] + b)
     GemmEpilogue e;
     e.bias = P + l.bkv;
     e.relu = 1;
-    MTAM_TRY(gemm(h, 0, 0, (int)T, 2 * N * D, D, w.X, D, P + l.Wkv, 2 * N * D, w.KV, 2 * N * D, e, st));
+    MTAM_TRY(gemm(h, 0, 0, (int)T, 2 * N * D, D, via ? w.Hs + D : w.X, D, P + l.Wkv, 2 * N * D, w.KV, 2 * N * D, e, st));
   }
   phase(h, MTAM_PH_HOP_FWD, st);
   HopArgs a = hop_args(h, bt);
@@ -484,7 +503,13 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   }
   // hops
   phase(h, MTAM_PH_HOP_BWD, st);
+  const bool via = c.kind == MTAM_KIND_MTAM_VIA_T_GRU;
+  // gradient w.r.t. the hops' memory: dX itself, or (MTAM_via_T_GRU) the gradient of every T-GRU output step, kept in
+  // the dR buffer (free until the embedding backward)
+  float* dMem = via ? w.dR : w.dX;
+  const float* mem = via ? w.Hs + D : w.X;
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.dX, 0, (size_t)T * D * sizeof(float), st));
+  if (via) MTAM_CUDA_CHECK(cudaMemsetAsync(dMem, 0, (size_t)T * D * sizeof(float), st));
   const bool kv_bias_fused = hop_backward_writes_all_dkv(D, c.H, L, N);   // = the CTA-per-sequence path is taken
   if (!kv_bias_fused)   // the warp-per-sequence kernels leave masked keys untouched
     MTAM_CUDA_CHECK(cudaMemsetAsync(w.dKV, 0, (size_t)T * 2 * N * D * sizeof(float), st));
@@ -493,7 +518,7 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   MTAM_TRY(transpose_dd(P + l.Wt, w.WtT, D, N, st));
   HopArgs a = hop_args(h, bt);
   HopGradArgs g;
-  g.dpred = w.dpred; g.WqT = w.WqT; g.WtT = w.WtT; g.dX = w.dX; g.dKV = w.dKV; g.DOUT = w.DOUT; g.DQP = w.DQP; g.BKV = w.BKV;
+  g.dpred = w.dpred; g.WqT = w.WqT; g.WtT = w.WtT; g.dX = dMem; g.dKV = w.dKV; g.DOUT = w.DOUT; g.DQP = w.DQP; g.BKV = w.BKV;
   g.DQT = w.DQT; g.GB = w.GB; g.dq0 = w.dq0;
   MTAM_TRY(hop_backward(a, g, st));
   // Parameter gradients (weight-gradient GEMMs with K = B*L, column sums) feed nothing but the norm and the optimizer, so
@@ -523,6 +548,13 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
     // a second pass over the [B*L, 2ND] rows)
     if (kv_bias_fused) cb.job[cb.n_jobs++] = ColsumJob{w.BKV, 2 * N * D, nullptr, 0, 2 * N * D, G + l.bkv};
     MTAM_TRY(colsum_multi_f32(cb, B, pg));
+    if (via) {   // the short-term intent's layer norm: gain and bias gradients from d loss / d (its output) = dq0
+      ColsumBatch c2{};
+      c2.job[0] = ColsumJob{w.dq0, D, nullptr, 0, D, G + l.lnsb};
+      c2.job[1] = ColsumJob{w.dq0, D, w.XHS, D, D, G + l.lnsg};
+      c2.n_jobs = 2;
+      MTAM_TRY(colsum_multi_f32(c2, B, pg));
+    }
   }
   // dWq_i = Qin_i^T dQpre_i, dWt_i = Qin_i^T dQt_i: the N hops of each in one batched split-K launch
   MTAM_TRY(gemm_atb_batched_f32(N, D, D, B, w.Qin, D, (int64_t)B * D, w.DQP, N * D, D, G + l.Wq, D, (int64_t)D * D,
@@ -530,13 +562,18 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   MTAM_TRY(gemm_atb_batched_f32(N, D, D, B, w.Qin, D, (int64_t)B * D, w.DQT, N * D, D, G + l.Wt, D, (int64_t)D * D,
                                 w.gemm_ws2, w.gemm_ws_bytes, pg));
   if (!kv_bias_fused) MTAM_TRY(colsum2(h, w.dKV, 2 * N * D, nullptr, 0, (int)T, 2 * N * D, G + l.bkv, pg));
-  MTAM_TRY(gemm2(h, 1, 0, D, 2 * N * D, (int)T, w.X, D, w.dKV, 2 * N * D, G + l.Wkv, 2 * N * D, e0, pg));
-  MTAM_TRY(gemm(h, 0, 1, (int)T, D, 2 * N * D, w.dKV, 2 * N * D, P + l.Wkv, 2 * N * D, w.dX, D, eacc, st));
+  MTAM_TRY(gemm2(h, 1, 0, D, 2 * N * D, (int)T, mem, D, w.dKV, 2 * N * D, G + l.Wkv, 2 * N * D, e0, pg));
+  MTAM_TRY(gemm(h, 0, 1, (int)T, D, 2 * N * D, w.dKV, 2 * N * D, P + l.Wkv, 2 * N * D, dMem, D, eacc, st));
+  const float* dq0 = w.dq0;
+  if (via) {   // through the layer norm of the query
+    MTAM_TRY(ln_rows_backward(w.dq0, w.XHS, w.RSTDS, B, D, P + l.lnsg, w.dq0raw, st));
+    dq0 = w.dq0raw;
+  }
   // T-GRU
   phase(h, MTAM_PH_GRU_BWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.dGX, 0, (size_t)T * 3 * D * sizeof(float), st));
-  MTAM_TRY(gru_backward(D, w.X, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, w.Hs, w.RUCT, w.dq0, B, L,
-                        w.dGX, w.dX, w.vec_partial, st));
+  MTAM_TRY(gru_backward(D, w.X, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, w.Hs, w.RUCT, dq0,
+                        via ? dMem : nullptr, B, L, w.dGX, w.dX, w.vec_partial, st));
   phase(h, MTAM_PH_GRU_PARAM_GRADS, st);
   MTAM_TRY(pg_after_main(1));
   MTAM_TRY(colsum2(h, w.vec_partial, 8 * D, nullptr, 0, gru_num_blocks(B), 8 * D, G + l.gruvec, pg));
@@ -695,7 +732,8 @@ static int check_batch(mtam_model* h, const mtam_batch* bt) {
 static int fwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* scalars_out, bool with_loss,
                         cudaStream_t st) {
   switch (h->cfg.kind) {
-    case MTAM_KIND_MTAM: return mtam_fwd(h, bt, gb, scalars_out, with_loss, st);
+    case MTAM_KIND_MTAM:
+    case MTAM_KIND_MTAM_VIA_T_GRU: return mtam_fwd(h, bt, gb, scalars_out, with_loss, st);
     case MTAM_KIND_BPRMF: return bpr_fwd(h, bt, scalars_out, with_loss, st);
     default:
       MTAM_TRY(next_dropout_call(h, st));
@@ -704,7 +742,8 @@ static int fwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* scal
 }
 static int bwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* nsq, cudaStream_t st) {
   switch (h->cfg.kind) {
-    case MTAM_KIND_MTAM: return mtam_bwd(h, bt, gb, nsq, st);
+    case MTAM_KIND_MTAM:
+    case MTAM_KIND_MTAM_VIA_T_GRU: return mtam_bwd(h, bt, gb, nsq, st);
     case MTAM_KIND_BPRMF: return bpr_bwd(h, bt, nsq, st);
     default: return sa_bwd(h, bt, gb, nsq, st);
   }
@@ -915,7 +954,7 @@ int mtam_forward(mtam_handle h, const mtam_batch* batch, float* scalars_out, flo
 // ---- row-sharded item table ("scalable training variant") ----------------------------------------------
 static int rows_batch(mtam_handle h, const mtam_batch* batch, const float* item_rows, mtam_batch* out) {
   MTAM_TRY(check_batch(h, batch));
-  if (h->cfg.kind != MTAM_KIND_MTAM) return set_error(MTAM_ERR_UNSUPPORTED, "sharded item table: MTAM only");
+  if (!is_mtam_family(h->cfg.kind)) return set_error(MTAM_ERR_UNSUPPORTED, "sharded item table: MTAM kinds only");
   if (!item_rows) return set_error(MTAM_ERR_INVALID, "item_rows is null");
   *out = *batch;
   out->item_list = h->ws.iota;

@@ -26,8 +26,8 @@ int gru_forward(int D, const float* X, const float* GX, const float* timelast, c
                 const float* Wgru, const float* vecs, int B, int L, float* Hs, float* RUCT, float* RH, float* q0,
                 cudaStream_t st);
 int gru_backward(int D, const float* X, const float* timelast, const int32_t* seq_len, const float* Wgru,
-                 const float* vecs, const float* Hs, const float* RUCT, const float* dq0, int B, int L, float* dGX,
-                 float* dX, float* vec_partial, cudaStream_t st);
+                 const float* vecs, const float* Hs, const float* RUCT, const float* dq0, const float* dOut, int B, int L,
+                 float* dGX, float* dX, float* vec_partial, cudaStream_t st);
 
 // ---- hops.cu --------------------------------------------------------------------------------
 struct HopArgs {

@@ -378,7 +378,7 @@ __global__ void final_ln_fwd_kernel(const float* __restrict__ enc, const int32_t
                                     float* __restrict__ pred, float* __restrict__ XHF, float* __restrict__ RSTDF) {
   int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
-  int pos = min(max(seq_len[b] - 1, 0), L - 1);
+  int pos = seq_len ? min(max(seq_len[b] - 1, 0), L - 1) : 0;
   const float* x = enc + ((int64_t)b * L + pos) * D;
   float s1 = 0.f;
   for (int d = lane; d < D; d += 32) s1 += x[d];
@@ -398,7 +398,7 @@ __global__ void final_ln_bwd_kernel(const float* __restrict__ dpred, const float
                                     int D, const float* __restrict__ gamma, float* __restrict__ dEnc) {
   int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
-  int pos = min(max(seq_len[b] - 1, 0), L - 1);
+  int pos = seq_len ? min(max(seq_len[b] - 1, 0), L - 1) : 0;
   float s1 = 0.f, s2 = 0.f;
   for (int d = lane; d < D; d += 32) {
     float dxh = dpred[(int64_t)b * D + d] * gamma[d];
@@ -410,6 +410,20 @@ __global__ void final_ln_bwd_kernel(const float* __restrict__ dpred, const float
     float dxh = dpred[(int64_t)b * D + d] * gamma[d];
     dEnc[((int64_t)b * L + pos) * D + d] = (dxh - m1 - XHF[(int64_t)b * D + d] * m2) * rstd;
   }
+}
+
+// plain rows: the gather kernels above with L = 1 and no length array (row b itself)
+int ln_rows_forward(const float* x, int B, int D, const float* gamma, const float* beta, float* out, float* xhat, float* rstd,
+                    cudaStream_t st) {
+  final_ln_fwd_kernel<<<cdiv(B, 4), 128, 0, st>>>(x, nullptr, B, 1, D, gamma, beta, out, xhat, rstd);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+int ln_rows_backward(const float* dout, const float* xhat, const float* rstd, int B, int D, const float* gamma, float* dx,
+                     cudaStream_t st) {
+  final_ln_bwd_kernel<<<cdiv(B, 4), 128, 0, st>>>(dout, xhat, rstd, nullptr, B, 1, D, gamma, dx);
+  MTAM_LAUNCH_CHECK();
+  return 0;
 }
 
 static int sa_mode(int kind) { return time_aware(kind) ? 1 : (kind == MTAM_KIND_TISASREC ? 2 : 0); }

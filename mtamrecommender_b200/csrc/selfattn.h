@@ -54,6 +54,11 @@ struct SaCtx {
   const uint32_t* drop_counter = nullptr;   // device: the forward-call counter the mask is keyed on
 };
 int sa_forward(const SaCtx& c, cudaStream_t st);
+// tf.contrib.layers.layer_norm (eps 1e-12) of B rows of D floats, and its input gradient (net_utils.py:229-232)
+int ln_rows_forward(const float* x, int B, int D, const float* gamma, const float* beta, float* out, float* xhat, float* rstd,
+                    cudaStream_t st);
+int ln_rows_backward(const float* dout, const float* xhat, const float* rstd, int B, int D, const float* gamma, float* dx,
+                     cudaStream_t st);
 int sa_backward(const SaCtx& c, cudaStream_t st);
 
 }  // namespace mtam
