@@ -26,7 +26,14 @@ WORKLOADS = {
     # name: kind, B per GPU, L, D, N hops, H, items, cats, users
     "cfg3": dict(kind="MTAM", B=1024, L=50, D=64, N=6, H=1, items=100_000, cats=1_000, users=1_000_000),
     "cfg4": dict(kind="MTAM", B=1024, L=200, D=64, N=6, H=1, items=10_000_000, cats=1_000, users=1_000_000),
+    # BASELINE configs[0] / [1]: ml-1m-shaped, default flags (num_units 128, 6 blocks, dropout 0.5 where the
+    # reference applies it); PISTRec / the attention baselines use 8 heads as in config/model_parameter.py:13
     "cfg1": dict(kind="MTAM", B=256, L=50, D=128, N=6, H=1, items=3_706, cats=301, users=4_832),
+    "cfg1_via_t_gru": dict(kind="MTAM_VIA_T_GRU", B=256, L=50, D=128, N=6, H=1, items=3_706, cats=301, users=4_832),
+    "cfg2_pistrec": dict(kind="PISTREC", B=256, L=50, D=128, N=6, H=8, items=3_706, cats=301, users=4_832),
+    "cfg2_sasrec": dict(kind="SASREC", B=256, L=50, D=128, N=6, H=8, items=3_706, cats=301, users=4_832, dropout=0.5),
+    "cfg2_tisasrec": dict(kind="TISASREC", B=256, L=50, D=128, N=6, H=8, items=3_706, cats=301, users=4_832, dropout=0.5),
+    "cfg2_ta_sasrec": dict(kind="TA_SASREC", B=256, L=50, D=128, N=6, H=8, items=3_706, cats=301, users=4_832),
     "tiny": dict(kind="MTAM", B=64, L=16, D=64, N=2, H=1, items=2_000, cats=50, users=500),
 }
 METRIC = "train seqs/s fwd+bwd (full train step incl. clip+Adam)"
@@ -235,7 +242,7 @@ def _run_cuda(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     mc = E.ModelConfig(kind=w["kind"], max_batch=w["B"], L=w["L"], D=w["D"], H=w["H"], N=w["N"], user_count=w["users"],
-                       item_count=w["items"], category_count=w["cats"],
+                       item_count=w["items"], category_count=w["cats"], dropout=w.get("dropout", 0.0),
                        gemm_mode=_lib.GEMM_TF32X3 if args.gemm_mode == "tf32x3" else _lib.GEMM_FP32)
     eng = E.Engine(mc, device=dev, seed=1234)           # same seed on every rank: replicas start identical
     dp = None
@@ -281,16 +288,24 @@ def _run_cuda(args, w):
     W = max(args.warmup, 3)
     for i in range(W):
         step_dev(i)
-    use_graph = (dp is None) and (not args.no_graph)
+    use_graph = not args.no_graph
     if use_graph:
-        eng.capture_train_graph(w["B"])
-        stage = {k: v for k, v in eng._dev.items()}
+        # the whole step as one CUDA graph; with N > 1 the NCCL collectives of the data-parallel step are captured too
+        if dp is None:
+            eng.capture_train_graph(w["B"])
+        else:
+            dp.capture_graph(w["B"])
+        # device-resident copies of the packed feed (the layout of the engine's staging buffer): one device-to-device
+        # copy refreshes the captured step's inputs
+        packed = []
+        for f in feeds:
+            eng.upload(f)
+            packed.append(eng._dev_all.clone())
+        torch.cuda.synchronize()
 
         def step_graph(i):
-            b = batches[i % nb]
-            for k in E.FEED_KEYS:                     # device->device refresh of the captured input buffers
-                stage[k][:b.B].copy_(b.t[k], non_blocking=True)
-            eng.train_step_graph(LR)
+            eng._dev_all.copy_(packed[i % nb], non_blocking=True)
+            (eng if dp is None else dp).train_step_graph(LR)
         for i in range(2):
             step_graph(i)
         fn_dev = step_graph
@@ -304,6 +319,8 @@ def _run_cuda(args, w):
     launches = eng.launch_count() - l0
     if use_graph:   # launches inside a replayed graph are not re-counted by the host counter: count one eager step
         l0 = eng.launch_count(); step_dev(0); launches = (eng.launch_count() - l0) * args.steps
+        if dp is not None:
+            barrier()
     for i in range(2):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
@@ -330,7 +347,7 @@ def _run_cuda(args, w):
         # ---- per-phase device times of the same step (CUDA events on the step's stream) ----
         phases = {}
         reps = max(3, min(args.steps, 10))
-        if dp is None:
+        if dp is None and w["kind"] == "MTAM":
             for i in range(reps):
                 p = eng.profile_step(batches[i % nb], LR)
                 for k, v in p.items():
@@ -365,12 +382,12 @@ def _run_cuda(args, w):
             roofs = [roof_of(k) for k in ranked[:4]]
             roof = roofs[0] if roofs else None
         # ---- the two graded bandwidth kernels at cfg-4 shapes (n = 8192*200 rows, D = 64) ----
-        bw = bandwidth_kernels(eng, dev, pk)
+        bw = bandwidth_kernels(eng, dev, pk) if args.workload in ("cfg3", "cfg4") else None   # cfg-4-shape kernels: once
         ev = eval_topk_bench(eng, batches, w, pk) if dp is None else None
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32 (tcgen05 3xTF32 split, fp32 accumulate)" if args.gemm_mode == "tf32x3" else "f32", "data": "synthetic",
-               "config": {"workload": args.workload, "model": "MTAM", "batch_per_gpu": w["B"], "global_batch": w["B"] * world,
+               "config": {"workload": args.workload, "model": w["kind"], "batch_per_gpu": w["B"], "global_batch": w["B"] * world,
                           "seq_len": w["L"], "num_units": w["D"], "num_blocks": w["N"], "num_heads": w["H"],
                           "item_count": w["items"], "user_count": w["users"], "category_count": w["cats"],
                           "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "gemm_mode": args.gemm_mode,
@@ -383,17 +400,23 @@ def _run_cuda(args, w):
                         "what": "DataInput view of a PackedRecords store -> mtam_pack_records into pinned memory -> H2D -> step -> loss"}},
                "gpu_launches": int(launches), "clocks": clk, "phases_ms": phases, "roofline": roof,
                "rooflines_top_phases": roofs, "bandwidth_kernels": bw, "eval_topk": ev}
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and w["kind"] == "MTAM":
             out["cpu_baseline"] = cpu_baseline(w)
     # BASELINE configs[3] in the same run (every rank takes part; rank 0 reports)
     if args.workload == "cfg3" and not args.no_cfg4:
-        del eng, dp, batches
-        torch.cuda.empty_cache()
         c4 = cfg4_section(args, rank, world, local, dev, timed)
         if out is not None:
             out["cfg4"] = c4
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        # captured graphs hold NCCL work: drop them before the process group goes (destroying it first hangs)
+        import gc
+        if dp is not None:
+            dp._graph = None
+        eng._graph = None
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
     return json.dumps(out) if out is not None else None
 
@@ -582,6 +605,7 @@ def main():
     ap.add_argument("--gemm-mode", default="tf32x3", choices=["tf32x3", "fp32"],
                     help="dense contractions: tcgen05 3-term-split TF32 (fp32-class accuracy) or exact fp32 FFMA")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-bw", action="store_true", help="(unused; the bandwidth kernels run with cfg3 / cfg4 only)")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the cfg4 (10 M items, global batch 8192) section")
     ap.add_argument("--cpu-batch", type=int, default=0,
                     help="sequences per step of the CPU arm; 0 = the workload's own batch size (the default)")

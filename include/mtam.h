@@ -236,6 +236,13 @@ int mtam_forward_backward(mtam_handle h, const mtam_batch* batch, int32_t global
                           float* scalars_out, float* norm_sq_sparse, void* stream);
 int mtam_finish_grads(mtam_handle h, float* norm_sq, int32_t scatter_local, void* stream);
 int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_out, void* stream);
+/* mtam_apply in three parts, for a data-parallel driver that wants to update the regions of the arena whose gradients
+ * are complete while a collective for the others is still in flight: begin = clip scale + step preparation (lr_t),
+ * range = the optimizer update of arena floats [float_begin, float_end) (multiples of 4; each float exactly once per
+ * step), end = restores the gradient-arena invariants.  mtam_apply == begin, range(0, param_floats), end. */
+int mtam_apply_begin(mtam_handle h, double lr, const float* norm_sq, float* scalars_out, void* stream);
+int mtam_apply_range(mtam_handle h, uint64_t float_begin, uint64_t float_end, void* stream);
+int mtam_apply_end(mtam_handle h, void* stream);
 
 /* Data-parallel helpers.
  *  mtam_set_item_grad_event: `cuda_event` (a cudaEvent_t owned by the caller, or NULL to clear) is recorded on the

@@ -87,6 +87,9 @@ SIGNATURES = {
     "mtam_forward_backward": (C.c_int, [_VP, C.POINTER(Batch), _I32, _VP, _VP, _VP]),
     "mtam_finish_grads": (C.c_int, [_VP, _VP, _I32, _VP]),
     "mtam_apply": (C.c_int, [_VP, C.c_double, _VP, _VP, _VP]),
+    "mtam_apply_begin": (C.c_int, [_VP, C.c_double, _VP, _VP, _VP]),
+    "mtam_apply_range": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP]),
+    "mtam_apply_end": (C.c_int, [_VP, _VP]),
     "mtam_set_bpr_negative": (C.c_int, [_VP, _I32]),
     "mtam_forward_rows": (C.c_int, [_VP, C.POINTER(Batch), _VP, _VP, _VP, _VP]),
     "mtam_backward_rows": (C.c_int, [_VP, C.POINTER(Batch), _VP, _VP, _I32, _VP, _VP]),

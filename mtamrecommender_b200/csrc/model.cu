@@ -1111,32 +1111,56 @@ int mtam_scatter_sparse_into(mtam_handle h, float* item_dst, float* category_dst
   return 0;
 }
 
-int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_out, void* stream) {
+int mtam_apply_begin(mtam_handle h, double lr, const float* norm_sq, float* scalars_out, void* stream) {
   if (!h || !norm_sq) return set_error(MTAM_ERR_INVALID, "null argument");
   if (!h->grads_pending) return set_error(MTAM_ERR_INVALID, "mtam_apply without pending gradients");
   cudaStream_t st = (cudaStream_t)stream;
-  const mtam_config& c = h->cfg;
-  const Layout& l = h->lay;
-  Workspace& w = h->ws;
-  float* ds = w.dev_scalars;
-  MTAM_TRY(clip_scale(norm_sq, c.clip, ds + MTAM_S_GLOBAL_NORM, ds + MTAM_S_CLIP_SCALE, st));
+  float* ds = h->ws.dev_scalars;
+  MTAM_TRY(clip_scale(norm_sq, h->cfg.clip, ds + MTAM_S_GLOBAL_NORM, ds + MTAM_S_CLIP_SCALE, st));
   phase(h, MTAM_PH_ADAM, st);
   if (!h->step_prepared) MTAM_TRY(mtam_prepare_step(h, lr, stream));
   h->step_prepared = false;
-  if (c.optimizer == MTAM_OPT_SGD)
-    MTAM_TRY(sgd_apply(h->params, h->grads, (int64_t)l.total, ds + MTAM_S_CLIP_SCALE, ds + 9, st));
-  else
-    MTAM_TRY(adam_apply(h->params, h->m, h->v, h->grads, (int64_t)l.total, ds + MTAM_S_CLIP_SCALE, ds + 9, c.beta1, c.beta2,
-                        c.eps, st));
-  // restore the invariant "sparse-only table regions of the grads arena are zero"
-  MTAM_CUDA_CHECK(cudaMemsetAsync(h->grads + l.cat, 0, (l.dense_begin - l.cat) * sizeof(float), st));
-  if (c.kind != MTAM_KIND_PISTREC) MTAM_TRY(zero_rows(h->grads + l.user, h->last_batch.user_id, h->last_B, c.D, st));
   if (scalars_out)
     MTAM_CUDA_CHECK(cudaMemcpyAsync(scalars_out + MTAM_S_GLOBAL_NORM, ds + MTAM_S_GLOBAL_NORM, 2 * sizeof(float),
                                     cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int mtam_apply_range(mtam_handle h, uint64_t float_begin, uint64_t float_end, void* stream) {
+  if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
+  if (!h->grads_pending) return set_error(MTAM_ERR_INVALID, "mtam_apply_range without pending gradients");
+  const mtam_config& c = h->cfg;
+  if (float_end > h->lay.total || float_begin > float_end || (float_begin % 4) || (float_end % 4))
+    return set_error(MTAM_ERR_INVALID, "mtam_apply_range: [%llu, %llu) is not a 4-aligned range of the arena",
+                     (unsigned long long)float_begin, (unsigned long long)float_end);
+  if (float_begin == float_end) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ds = h->ws.dev_scalars;
+  const int64_t n = (int64_t)(float_end - float_begin);
+  if (c.optimizer == MTAM_OPT_SGD)
+    return sgd_apply(h->params + float_begin, h->grads + float_begin, n, ds + MTAM_S_CLIP_SCALE, ds + 9, st);
+  return adam_apply(h->params + float_begin, h->m + float_begin, h->v + float_begin, h->grads + float_begin, n,
+                    ds + MTAM_S_CLIP_SCALE, ds + 9, c.beta1, c.beta2, c.eps, st);
+}
+
+int mtam_apply_end(mtam_handle h, void* stream) {
+  if (!h) return set_error(MTAM_ERR_INVALID, "null handle");
+  if (!h->grads_pending) return set_error(MTAM_ERR_INVALID, "mtam_apply_end without pending gradients");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mtam_config& c = h->cfg;
+  const Layout& l = h->lay;
+  // restore the invariant "sparse-only table regions of the grads arena are zero"
+  MTAM_CUDA_CHECK(cudaMemsetAsync(h->grads + l.cat, 0, (l.dense_begin - l.cat) * sizeof(float), st));
+  if (c.kind != MTAM_KIND_PISTREC) MTAM_TRY(zero_rows(h->grads + l.user, h->last_batch.user_id, h->last_B, c.D, st));
   h->grads_pending = false;
   phase(h, MTAM_PHASE_COUNT, st);
   return 0;
+}
+
+int mtam_apply(mtam_handle h, double lr, const float* norm_sq, float* scalars_out, void* stream) {
+  MTAM_TRY(mtam_apply_begin(h, lr, norm_sq, scalars_out, stream));
+  MTAM_TRY(mtam_apply_range(h, 0, h->lay.total, stream));
+  return mtam_apply_end(h, stream);
 }
 
 int mtam_eval_topk(mtam_handle h, const mtam_batch* batch, int32_t k, int32_t* idx_out, float* score_out, void* stream) {

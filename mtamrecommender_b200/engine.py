@@ -249,7 +249,12 @@ class Engine:
                   ("category_list", c.category_count + 3), ("position_list", c.L + 3))
         for k, hi in bounds:
             a = np.asarray(feed[k])
-            if a.size and (int(a.min()) < 0 or int(a.max()) >= hi):
+            if a.size == 0:
+                continue
+            # one pass per array: viewed as unsigned, a negative id is a huge one
+            top = int(a.view(np.uint32).max()) if a.dtype == np.int32 and a.flags.c_contiguous else \
+                (int(a.max()) if int(a.min()) >= 0 else 1 << 40)
+            if top >= hi:
                 raise ValueError(f"feed array {k}: ids outside [0, {hi})")
         if c.kind != "BPRMF":
             sl = np.asarray(feed["seq_length"])

@@ -73,6 +73,7 @@ class DataParallel:
         self.scatter_ws = torch.empty(need, dtype=torch.uint8, device=dev)
         self.user_sort_ws = torch.empty(max(int(engine.lib.mtam_sort_workspace(W * B, c.user_rows)), 16), dtype=torch.uint8,
                                         device=dev)
+        self._graph, self._graph_B = None, -1
         self.comm = torch.cuda.Stream(dev)
         self.ev_item = torch.cuda.Event()
         self.ev_item.record(torch.cuda.current_stream(dev))   # materialises the cudaEvent_t
@@ -123,39 +124,94 @@ class DataParallel:
         dist.all_reduce(eng._grads_all[item_hi: eng.n_floats + _lib.S_COUNT + 1], group=self.group)
         main.wait_stream(self.comm)
         eng.finish_grads(scatter_local=False)          # adds the squared norm of the (global) dense pieces
-        # 3. sparse pieces
+        # 3. sparse pieces, 4. clip + optimizer.  The clip scale needs only the norm, which is complete here; the optimizer
+        #    then runs region by region, so that the all-reduce of the densified [item | category | position] pieces is
+        #    hidden behind the update of the user table (86 % of the parameters at cfg3).
+        st = main.cuda_stream
+        lib = eng.lib
+        if bool(sv.has_user) != has_user:
+            raise RuntimeError("user-table gradient pieces do not match the model kind")
+        check(lib.mtam_apply_begin(eng.h, float(lr), eng.norm_sq.data_ptr(), eng.scalars.data_ptr(), st), "mtam_apply_begin")
         if self.mode == "dense":
             sp_item = self.sp[:c.item_rows]
             sp_cat = self.sp[c.item_rows: c.item_rows + c.category_rows]
             sp_pos = self.sp[c.item_rows + c.category_rows:]
             self.sp.zero_()
-            check(eng.lib.mtam_scatter_sparse_into(eng.h, sp_item.data_ptr(), sp_cat.data_ptr(), sp_pos.data_ptr(), None,
-                                                   main.cuda_stream), "mtam_scatter_sparse_into")
-            dist.all_reduce(self.sp, group=self.group)
-            self._grad_region(int(sv.item_offset), c.item_rows).add_(sp_item)
-            self._grad_region(int(sv.category_offset), c.category_rows).copy_(sp_cat)
-            self._grad_region(int(sv.position_offset), c.position_rows).copy_(sp_pos)
+            check(lib.mtam_scatter_sparse_into(eng.h, sp_item.data_ptr(), sp_cat.data_ptr(), sp_pos.data_ptr(), None, st),
+                  "mtam_scatter_sparse_into")
+            self.comm.wait_stream(main)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.sp, group=self.group)
         else:
             g_item = self._gather(self.g_item, batch.t["item_list"].reshape(-1))
             g_cat = self._gather(self.g_cat, batch.t["category_list"].reshape(-1))
             g_pos = self._gather(self.g_pos, batch.t["position_list"].reshape(-1))
             g_dE2 = self._gather(self.g_dE2, self._ws_view(sv.item_cat_rows, T, 2 * D))
             g_dEp = self._gather(self.g_dEp, self._ws_view(sv.position_rows, T, D))
-            scatter_add(self._grad_region(int(sv.item_offset), c.item_rows), g_item, g_dE2[:, :D], self.scatter_ws)
-            scatter_add(self._grad_region(int(sv.category_offset), c.category_rows), g_cat, g_dE2[:, D:], self.scatter_ws)
-            scatter_add(self._grad_region(int(sv.position_offset), c.position_rows), g_pos, g_dEp, self.scatter_ws)
-        if bool(sv.has_user) != has_user:
-            raise RuntimeError("user-table gradient pieces do not match the model kind")
         if has_user:
             g_dEu = self._gather(self.g_dEu, self._ws_view(sv.user_rows, B, D))
             scatter_add_sorted(self._grad_region(int(sv.user_offset), c.user_rows), user_sorted, g_dEu, self.scatter_ws)
-        eng.apply(lr)
-        if has_user:   # apply() re-zeroes only the local users' rows of the grads arena
+        first_table = min(int(sv.category_offset), int(sv.position_offset), item_lo)       # the user table lies in front
+        check(lib.mtam_apply_range(eng.h, 0, first_table, st), "mtam_apply_range")           # user table
+        check(lib.mtam_apply_range(eng.h, item_hi, eng.n_floats, st), "mtam_apply_range")     # dense parameters
+        if self.mode == "dense":
+            main.wait_stream(self.comm)
+            self._grad_region(int(sv.item_offset), c.item_rows).add_(sp_item)
+            self._grad_region(int(sv.category_offset), c.category_rows).copy_(sp_cat)
+            self._grad_region(int(sv.position_offset), c.position_rows).copy_(sp_pos)
+        else:
+            scatter_add(self._grad_region(int(sv.item_offset), c.item_rows), g_item, g_dE2[:, :D], self.scatter_ws)
+            scatter_add(self._grad_region(int(sv.category_offset), c.category_rows), g_cat, g_dE2[:, D:], self.scatter_ws)
+            scatter_add(self._grad_region(int(sv.position_offset), c.position_rows), g_pos, g_dEp, self.scatter_ws)
+        check(lib.mtam_apply_range(eng.h, first_table, item_hi, st), "mtam_apply_range")     # category, position, item tables
+        check(lib.mtam_apply_end(eng.h, st), "mtam_apply_end")
+        if has_user:   # apply_end re-zeroes only the local users' rows of the grads arena
             self._grad_region(int(sv.user_offset), c.user_rows).index_fill_(0, g_user.long(), 0.0)
 
     def train_step(self, feed: Dict[str, np.ndarray], lr: float) -> float:
-        self.train_step_device(self.eng.upload(feed), lr)
+        batch = self.eng.upload(feed)
+        if self._graph is not None and batch.B == self._graph_B:
+            self.train_step_graph(lr)
+        else:
+            self.train_step_device(batch, lr)
         return float(self.eng.read_scalars()[_lib.S_LOSS])
+
+    # ---- the whole data-parallel step, collectives included, as one CUDA graph --------------------------------------
+    def capture_graph(self, B: int, warmup: int = 2) -> None:
+        """Captures `train_step_device` on the engine's staging batch (fixed addresses), NCCL collectives included, into
+        one CUDA graph; `train_step_graph(lr)` then advances the host-side optimizer state and replays it.  Every rank
+        must call this (the collectives are captured in the same order on all of them).  Weights, Adam moments and the
+        step counter are left exactly as they were."""
+        eng = self.eng
+        batch = DeviceBatch({k: v[:B] for k, v in eng._dev.items()}, B)
+        if eng._h2d_done is None:
+            eng._dev["seq_length"].fill_(2)
+        t0 = eng.adam_step()
+        keep = (eng.params.clone(), eng.adam_m.clone(), eng.adam_v.clone())
+        s = torch.cuda.Stream(eng.device)
+        s.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):                       # eager: sets kernel attributes, warms NCCL up on this stream
+                self.train_step_device(batch, 0.0)
+        torch.cuda.current_stream(eng.device).wait_stream(s)
+        torch.cuda.synchronize(eng.device)
+        dist.barrier(group=self.group)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            check(eng.lib.mtam_prepare_step(eng.h, 0.0, s.cuda_stream), "mtam_prepare_step")
+        with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
+            self.train_step_device(batch, 0.0)
+        torch.cuda.synchronize(eng.device)
+        eng.set_adam_step(t0)
+        eng.params.copy_(keep[0]); eng.adam_m.copy_(keep[1]); eng.adam_v.copy_(keep[2])
+        eng.grads.zero_()
+        del keep
+        self._graph, self._graph_B = g, B
+
+    def train_step_graph(self, lr: float) -> None:
+        check(self.eng.lib.mtam_prepare_step(self.eng.h, float(lr), torch.cuda.current_stream(self.eng.device).cuda_stream),
+              "mtam_prepare_step")
+        self._graph.replay()
 
 
 def combine_lse(lse_per_shard: torch.Tensor) -> torch.Tensor:
