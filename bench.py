@@ -374,7 +374,8 @@ def _run_cuda(args, w):
             else:
                 ach, peak, unit = amount / (ms * 1e-3) / 1e12, pk["tf_sust"], "TFLOP/s"
             return {"kernel": name, "bound": kind, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                    "traffic": traffic.get(name), "peak_source": pk["src"] + (" bf16 sustained" if kind == "tensor" else " copy"),
+                    "traffic": traffic.get(name), "traffic_source": "profiles/traffic_r02.json (ncu --set full capture of this step)",
+                    "peak_source": pk["src"] + (" bf16 sustained" if kind == "tensor" else " copy"),
                     "ms": ms, "share_of_step": ms / tot}
         roof, roofs = None, []
         if phases:
@@ -393,7 +394,7 @@ def _run_cuda(args, w):
                           "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "gemm_mode": args.gemm_mode,
                           "l2": "4 rotating batches; every step streams the 4 parameter/Adam arenas "
                                 f"({4 * 4 * eng.n_floats / 1e6:.0f} MB) through HBM, > 126 MB L2"},
-               "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
+               "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(eng._scalars_host.numel() * eng._scalars_host.element_size()),
                        "ms_per_step": ms_e2e / args.steps,
                        "from_record_store": None if ms_rec is None else
                        {"value": seqs / (ms_rec / 1e3), "unit": UNIT, "ms_per_step": ms_rec / args.steps,
@@ -466,10 +467,36 @@ def cfg4_section(args, rank, world, local, dev, timed_fn):
         ms = timed_fn(lambda i: step(batches[i % 2]), steps)
         clk = clocks.stop() if rank == 0 else {}
         loss = float(eng.read_scalars()[_lib.S_LOSS])
+        # BASELINE configs[4] (cfg5): full-catalogue top-50 eval over the 10 M items for the global batch of 8192 --
+        # metrics_topK (base_model.py:188-213).  N > 1: forward on looked-up rows, all-gather of pred, every rank scores
+        # its shard (tcgen05 filter + exact fp32 rescoring), all-gather of the [B,50] lists, merge.
+        ev_steps = 5
+        if world > 1:
+            ev = lambda b: tr.eval_topk(b, 50)
+            pr = torch.randn((B, w["D"]), device=dev)
+            sc = lambda b: tr.cat.topk(pr, 50)
+        else:
+            ev = lambda b: eng.eval_topk_device(b, 50)
+            pr = torch.randn((B, w["D"]), device=dev)
+            table = eng.param_view("embedding_layer/item")
+            sc = lambda b: E.score_topk(pr, table, 50, gemm_mode=gm)
+        for f in (ev, sc):
+            f(batches[0])
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        ms_ev = timed_fn(lambda i: ev(batches[i % 2]), ev_steps)
+        ms_sc = timed_fn(lambda i: sc(batches[i % 2]), ev_steps)
+        clk5 = clocks.stop() if rank == 0 else {}
+        flops = 2.0 * GB * w["D"] * V
+        cfg5 = {"workload": "cfg5 (BASELINE configs[4]): top-50 over 10 M items, global eval batch 8192", "n_gpus": world,
+                "ms_forward_score_top50_merge": ms_ev / ev_steps, "eval_seq_per_s": GB * ev_steps / (ms_ev / 1e3),
+                "ms_score_top50_merge_only": ms_sc / ev_steps,
+                "score_useful_TFLOPs_all_gpus": flops / (ms_sc / ev_steps) / 1e9, "clocks": clk5}
         out = {"workload": "cfg4 (BASELINE configs[3])", "items": w["items"], "seq_len": w["L"], "global_batch": GB,
                "batch_per_gpu": B, "n_gpus": world, "parallelism": par, "steps": steps, "ms_per_step": ms / steps,
                "seq_per_s": GB * steps / (ms / 1e3), "scaling": "strong", "loss": loss, "clocks": clk,
-               "gemm_mode": args.gemm_mode}
+               "gemm_mode": args.gemm_mode, "cfg5_eval": cfg5}
         del eng
         torch.cuda.empty_cache()
         return out
@@ -585,9 +612,10 @@ def _lib_sorted_ws(n, D):
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the kernels named in the rooflines, copied from the committed `ncu --set full`
-    captures (profiles/traffic_r01.json says which report each number came from)."""
-    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    """DRAM bytes per launch of the kernels named in the rooflines.  ncu cannot run inside a timed bench, so these are
+    taken from the committed `ncu --set full` capture of the same step (profiles/traffic_r02.json names the report and
+    is regenerated by tools/round_profile.sh); `roofline.traffic_source` says so in the JSON line."""
+    p = os.path.join(ROOT, "profiles", "traffic_r02.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
