@@ -46,8 +46,11 @@ typedef enum {
   MTAM_KIND_TA_SASREC = 3,  /* 'Time_Aware_Self_Attention_Model'   Model/attention_baseline_models.py:47-65 */
   MTAM_KIND_TISASREC = 4,   /* 'Ti_Self_Attention_Model'           Model/attention_baseline_models.py:66-84 */
   MTAM_KIND_BPRMF = 5,      /* 'bpr'                               Model/BPRMF.py:10-59 */
-  MTAM_KIND_MTAM_VIA_T_GRU = 6  /* 'MTAM_via_T_GRU'                Model/MTAMRec_model.py:167-204: the hops read the
+  MTAM_KIND_MTAM_VIA_T_GRU = 6, /* 'MTAM_via_T_GRU'                Model/MTAMRec_model.py:167-204: the hops read the
                                T-GRU's OUTPUT SEQUENCE as their memory, and the query is layer-normed first */
+  MTAM_KIND_MTAM_NO_TIME_AWARE_RNN = 7,  /* 'MTAM_no_time_aware_rnn'  MTAMRec_model.py:93-125: MTAM with a plain GRU
+                               (tf GRUCell, Model/Modules/gru.py:60-67) as the intent encoder */
+  MTAM_KIND_MTAM_VIA_RNN = 8    /* 'MTAM_via_rnn'                  MTAMRec_model.py:206-233: MTAM_via_T_GRU with the plain GRU */
 } mtam_kind;
 
 /* How the dense contractions are computed. */

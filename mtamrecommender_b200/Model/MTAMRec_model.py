@@ -19,3 +19,13 @@ class MTAM(MTAMRec_model):
 class MTAM_via_T_GRU(MTAMRec_model):
     """Model/MTAMRec_model.py:167-204: user_history = the T-GRU output sequence, query = layer_norm(short-term intent)."""
     KIND = "MTAM_VIA_T_GRU"
+
+
+class MTAM_no_time_aware_rnn(MTAMRec_model):
+    """Model/MTAMRec_model.py:93-125: MTAM whose short-term intent comes from a plain GRU (GRU.gru_net, gru.py:60-67)."""
+    KIND = "MTAM_NO_TIME_AWARE_RNN"
+
+
+class MTAM_via_rnn(MTAMRec_model):
+    """Model/MTAMRec_model.py:206-233: MTAM_via_T_GRU with the plain GRU."""
+    KIND = "MTAM_VIA_RNN"

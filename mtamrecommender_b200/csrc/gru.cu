@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
                                                         const int32_t* __restrict__ seq_len,
                                                         const float* __restrict__ Wgru, const float* __restrict__ vecs,
                                                         int B, int L, float* __restrict__ Hs, float* __restrict__ RUCT,
-                                                        float* __restrict__ RH, float* __restrict__ q0) {
+                                                        float* __restrict__ RH, float* __restrict__ q0, int plain) {
   extern __shared__ __align__(16) float sm[];
   float* Wh = sm;                   // [D][3D]  rows D..2D of W_gru (the h-side)
   float* hT = Wh + 3 * D * D;       // [D][RB]
@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
         float hold = hT[n2 * RB + row];
         float a = fmaxf(fmaf(xv[i], kw1, kb1) + hold * hw1, 0.f);
         float s = fmaxf(fmaf(tw1, dl[i], tb1), 0.f);
-        float Tg = sigmoidf_(kw2 * a + tw12 * s + tb12);
+        // plain: tf GRUCell (GRU.gru_net, gru.py:60-67) -- no time gate.  T = 1 is also what the backward pass needs:
+        // with it every gradient of the gate's parameters is exactly zero (dT * T * (1 - T) = 0)
+        float Tg = plain ? 1.f : sigmoidf_(kw2 * a + tw12 * s + tb12);
         float u = uS[n2 * RB + row];
         float hn = u * hold + (1.f - u) * c * Tg;
         RUCT[tok * (4 * D) + 2 * D + n2] = c;
@@ -330,10 +332,10 @@ int gru_num_blocks(int B) { return cdiv(B, RB); }
 template <int D>
 static int gru_fwd_launch(const float* X, const float* GX, const float* timelast, const int32_t* seq_len,
                           const float* Wgru, const float* vecs, int B, int L, float* Hs, float* RUCT, float* RH,
-                          float* q0, cudaStream_t st) {
+                          float* q0, int plain, cudaStream_t st) {
   size_t smem = gru_smem_bytes(D);
   MTAM_CUDA_CHECK(cudaFuncSetAttribute(gru_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gru_fwd_kernel<D><<<gru_num_blocks(B), 4 * D, smem, st>>>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0);
+  gru_fwd_kernel<D><<<gru_num_blocks(B), 4 * D, smem, st>>>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, plain);
   MTAM_LAUNCH_CHECK();
   return 0;
 }
@@ -351,11 +353,11 @@ static int gru_bwd_launch(const float* X, const float* timelast, const int32_t* 
 
 int gru_forward(int D, const float* X, const float* GX, const float* timelast, const int32_t* seq_len,
                 const float* Wgru, const float* vecs, int B, int L, float* Hs, float* RUCT, float* RH, float* q0,
-                cudaStream_t st) {
+                cudaStream_t st, int plain) {
   switch (D) {
-    case 32: return gru_fwd_launch<32>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, st);
-    case 64: return gru_fwd_launch<64>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, st);
-    case 128: return gru_fwd_launch<128>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, st);
+    case 32: return gru_fwd_launch<32>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, plain, st);
+    case 64: return gru_fwd_launch<64>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, plain, st);
+    case 128: return gru_fwd_launch<128>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, plain, st);
   }
   return set_error(-1, "T-GRU: num_units=%d not supported (32, 64, 128)", D);
 }

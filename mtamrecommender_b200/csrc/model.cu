@@ -93,7 +93,13 @@ struct mtam_model {
 
 namespace mtam {
 
-static inline bool is_mtam_family(int kind) { return kind == MTAM_KIND_MTAM || kind == MTAM_KIND_MTAM_VIA_T_GRU; }
+static inline bool is_mtam_family(int kind) {
+  return kind == MTAM_KIND_MTAM || (kind >= MTAM_KIND_MTAM_VIA_T_GRU && kind <= MTAM_KIND_MTAM_VIA_RNN);
+}
+// the hops' memory is the intent encoder's output sequence (and the query is layer-normed)
+static inline bool memory_is_rnn(int kind) { return kind == MTAM_KIND_MTAM_VIA_T_GRU || kind == MTAM_KIND_MTAM_VIA_RNN; }
+// the intent encoder is tf's GRUCell, without the time gate
+static inline bool plain_gru(int kind) { return kind == MTAM_KIND_MTAM_NO_TIME_AWARE_RNN || kind == MTAM_KIND_MTAM_VIA_RNN; }
 
 // phase boundary marker (cudaEventRecord on the step's stream when profiling is on)
 static inline void phase(mtam_model* h, int id, cudaStream_t st) {
@@ -140,9 +146,11 @@ static int build_layout(const mtam_config& c, Layout& l) {
     add_param(l, g + "gates/bias", 1, 2 * D, 1, 2 * D, l.bgru);
     add_param(l, g + "candidate/bias", 1, D, 1, D, l.bgru + 2 * D);
     l.gruvec = take((size_t)14 * D);
-    for (int i = 0; i < 8; ++i) add_param(l, g + kGruLive[i], 1, D, 1, D, l.gruvec + (size_t)i * D);
-    for (int i = 0; i < 6; ++i)
-      add_param(l, g + kGruDead[i], 1, D, 1, D, l.gruvec + (size_t)(8 + i) * D, MTAM_PARAM_DEAD);
+    if (!plain_gru(c.kind)) {   // the time gate's vectors: the region stays (zeros) for the plain cell, unnamed
+      for (int i = 0; i < 8; ++i) add_param(l, g + kGruLive[i], 1, D, 1, D, l.gruvec + (size_t)i * D);
+      for (int i = 0; i < 6; ++i)
+        add_param(l, g + kGruDead[i], 1, D, 1, D, l.gruvec + (size_t)(8 + i) * D, MTAM_PARAM_DEAD);
+    }
     l.Wq = take((size_t)N * D * D);
     l.bq = take((size_t)N * D);
     l.Wkv = take((size_t)D * 2 * N * D);
@@ -171,7 +179,7 @@ static int build_layout(const mtam_config& c, Layout& l) {
     l.lnfg = take(D);
     add_param(l, "NextItemDecoder/LayerNorm/beta", 1, D, 1, D, l.lnfb);
     add_param(l, "NextItemDecoder/LayerNorm/gamma", 1, D, 1, D, l.lnfg);
-    if (c.kind == MTAM_KIND_MTAM_VIA_T_GRU) {   // layer_norm of the short-term intent (MTAMRec_model.py:187)
+    if (memory_is_rnn(c.kind)) {   // layer_norm of the short-term intent (MTAMRec_model.py:187, :220)
       l.lnsb = take(D);
       l.lnsg = take(D);
       add_param(l, g + "LayerNorm/beta", 1, D, 1, D, l.lnsb);
@@ -301,7 +309,7 @@ static int validate(const mtam_config* c) {
   if (!c) return set_error(MTAM_ERR_INVALID, "config is null");
   if (c->abi_version != MTAM_ABI_VERSION)
     return set_error(MTAM_ERR_INVALID, "abi_version %d != %d", c->abi_version, MTAM_ABI_VERSION);
-  if (c->kind < 0 || c->kind > MTAM_KIND_MTAM_VIA_T_GRU) return set_error(MTAM_ERR_INVALID, "unknown model kind %d", c->kind);
+  if (c->kind < 0 || c->kind > MTAM_KIND_MTAM_VIA_RNN) return set_error(MTAM_ERR_INVALID, "unknown model kind %d", c->kind);
   if (c->D != 32 && c->D != 64 && c->D != 128)
     return set_error(MTAM_ERR_INVALID, "num_units=%d not supported (32, 64 or 128)", c->D);
   if (c->max_batch < 1 || c->L < 1 || c->N < 0) return set_error(MTAM_ERR_INVALID, "bad max_batch/L/N");
@@ -348,7 +356,7 @@ static HopArgs hop_args(mtam_model* h, const mtam_batch* bt) {
   a.seq_len = bt->seq_length; a.target_time = bt->target_item_time; a.time_list = bt->time_list;
   // the hops' memory ("user_history"): the embedded behaviours, or the T-GRU's output sequence (Hs holds h_{t-1} per
   // row with a leading zero row, so the outputs -- zero from step seq_len-1 on, as dynamic_rnn leaves them -- are Hs + D)
-  a.X = c.kind == MTAM_KIND_MTAM_VIA_T_GRU ? w.Hs + c.D : w.X;
+  a.X = memory_is_rnn(c.kind) ? w.Hs + c.D : w.X;
   a.KV = w.KV;
   a.Wq = h->params + l.Wq; a.bq = h->params + l.bq; a.Wt = h->params + l.Wt; a.gate = h->params + l.gate;
   a.ln_gamma = h->params + l.lng; a.ln_beta = h->params + l.lnb;
@@ -410,9 +418,9 @@ static int mtam_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   phase(h, MTAM_PH_GRU_FWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.Hs, 0, (size_t)(T + 1) * D * sizeof(float), st));
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.RH, 0, (size_t)T * D * sizeof(float), st));
-  const bool via = c.kind == MTAM_KIND_MTAM_VIA_T_GRU;
+  const bool via = memory_is_rnn(c.kind);
   MTAM_TRY(gru_forward(D, w.X, w.GX, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, B, L, w.Hs, w.RUCT,
-                       w.RH, via ? w.q0raw : w.Qin, st));
+                       w.RH, via ? w.q0raw : w.Qin, st, plain_gru(c.kind) ? 1 : 0));
   if (via)   // short_term_intent = layer_norm(gather(...))  (MTAMRec_model.py:182-187)
     MTAM_TRY(ln_rows_forward(w.q0raw, B, D, P + l.lnsg, P + l.lnsb, w.Qin, w.XHS, w.RSTDS, st));
   phase(h, MTAM_PH_KV_GEMM, st);
@@ -503,7 +511,7 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   }
   // hops
   phase(h, MTAM_PH_HOP_BWD, st);
-  const bool via = c.kind == MTAM_KIND_MTAM_VIA_T_GRU;
+  const bool via = memory_is_rnn(c.kind);
   // gradient w.r.t. the hops' memory: dX itself, or (MTAM_via_T_GRU) the gradient of every T-GRU output step, kept in
   // the dR buffer (free until the embedding backward)
   float* dMem = via ? w.dR : w.dX;
@@ -733,7 +741,9 @@ static int fwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* scal
                         cudaStream_t st) {
   switch (h->cfg.kind) {
     case MTAM_KIND_MTAM:
-    case MTAM_KIND_MTAM_VIA_T_GRU: return mtam_fwd(h, bt, gb, scalars_out, with_loss, st);
+    case MTAM_KIND_MTAM_VIA_T_GRU:
+    case MTAM_KIND_MTAM_NO_TIME_AWARE_RNN:
+    case MTAM_KIND_MTAM_VIA_RNN: return mtam_fwd(h, bt, gb, scalars_out, with_loss, st);
     case MTAM_KIND_BPRMF: return bpr_fwd(h, bt, scalars_out, with_loss, st);
     default:
       MTAM_TRY(next_dropout_call(h, st));
@@ -743,7 +753,9 @@ static int fwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* scal
 static int bwd_dispatch(mtam_model* h, const mtam_batch* bt, int gb, float* nsq, cudaStream_t st) {
   switch (h->cfg.kind) {
     case MTAM_KIND_MTAM:
-    case MTAM_KIND_MTAM_VIA_T_GRU: return mtam_bwd(h, bt, gb, nsq, st);
+    case MTAM_KIND_MTAM_VIA_T_GRU:
+    case MTAM_KIND_MTAM_NO_TIME_AWARE_RNN:
+    case MTAM_KIND_MTAM_VIA_RNN: return mtam_bwd(h, bt, gb, nsq, st);
     case MTAM_KIND_BPRMF: return bpr_bwd(h, bt, nsq, st);
     default: return sa_bwd(h, bt, gb, nsq, st);
   }

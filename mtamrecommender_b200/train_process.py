@@ -62,11 +62,9 @@ def model_class(experiment_type: str):
              "Time_Aware_Self_Attention_Model": Time_Aware_Self_Attention_Model,
              "Ti_Self_Attention_Model": Ti_Self_Attention_Model, "bpr": BPRMF,
              "pistrec": Time_Aware_self_Attention_model, "PISTRec": Time_Aware_self_Attention_model}
-    try:
-        from .Model.MTAMRec_model import MTAM_via_T_GRU
-        table["MTAM_via_T_GRU"] = MTAM_via_T_GRU
-    except ImportError:
-        pass
+    from .Model.MTAMRec_model import MTAM_no_time_aware_rnn, MTAM_via_rnn, MTAM_via_T_GRU
+    table.update({"MTAM_via_T_GRU": MTAM_via_T_GRU, "MTAM_no_time_aware_rnn": MTAM_no_time_aware_rnn,
+                  "MTAM_via_rnn": MTAM_via_rnn})
     if experiment_type not in table:
         raise NotImplementedError(f"experiment_type {experiment_type!r} is outside the hot path this library builds "
                                   f"(built: {sorted(table)})")

@@ -35,7 +35,12 @@ BPRMF = "BPRMF"                # 'bpr'                                  Model/BP
 KINDS = (MTAM, PISTREC, SASREC, TA_SASREC, TISASREC, BPRMF)
 # Oracle-only so far (the next widening step): no CUDA path is built for these yet.
 MTAM_VIA_T_GRU = "MTAM_VIA_T_GRU"   # 'MTAM_via_T_GRU': the T-GRU outputs are the memory   Model/MTAMRec_model.py:167-204
-NEXT_KINDS = (MTAM_VIA_T_GRU,)
+MTAM_NO_TA_RNN = "MTAM_NO_TIME_AWARE_RNN"   # 'MTAM_no_time_aware_rnn': plain GRU intent encoder      MTAMRec_model.py:93-125
+MTAM_VIA_RNN = "MTAM_VIA_RNN"               # 'MTAM_via_rnn': plain GRU, its outputs are the memory      MTAMRec_model.py:206-233
+NEXT_KINDS = (MTAM_VIA_T_GRU, MTAM_NO_TA_RNN, MTAM_VIA_RNN)
+MTAM_FAMILY = (MTAM, MTAM_VIA_T_GRU, MTAM_NO_TA_RNN, MTAM_VIA_RNN)
+PLAIN_GRU_KINDS = (MTAM_NO_TA_RNN, MTAM_VIA_RNN)     # GRU.gru_net: tf GRUCell, no time gate (gru.py:60-67)
+MEMORY_IS_RNN_KINDS = (MTAM_VIA_T_GRU, MTAM_VIA_RNN)
 
 MASK_VALUE = float(-2 ** 32 + 1)   # time_aware_attention.py:392 -> fp32 -4294967296.0
 LN_EPS_BLOCK = 1e-8                 # Time_Aware_Attention.normalize  time_aware_attention.py:7-34
@@ -91,17 +96,18 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
     if cfg.kind == BPRMF:
         s["embedding_layer/item_b"] = (cfg.V, 1)       # BPRMF.py:34-35
         return s
-    if cfg.kind in (MTAM, MTAM_VIA_T_GRU):
+    if cfg.kind in MTAM_FAMILY:
         g = "ShortTermIntentEncoder/"
-        if cfg.kind == MTAM_VIA_T_GRU:                 # layer_norm(short_term_intent) inside this scope, MTAMRec_model.py:186
+        if cfg.kind in MEMORY_IS_RNN_KINDS:            # layer_norm(short_term_intent) inside this scope, MTAMRec_model.py:186, :220
             s[g + "LayerNorm/beta"] = (D,)
             s[g + "LayerNorm/gamma"] = (D,)
         s[g + "gates/kernel"] = (2 * D, 2 * D)         # time_aware_rnn.py:166-169
         s[g + "gates/bias"] = (2 * D,)
         s[g + "candidate/kernel"] = (2 * D, D)
         s[g + "candidate/bias"] = (D,)
-        for v in GRU_LIVE_VECS + GRU_DEAD_VECS:
-            s[g + v] = (D,)
+        if cfg.kind not in PLAIN_GRU_KINDS:            # the time gate's vectors exist in the time-aware cell only
+            for v in GRU_LIVE_VECS + GRU_DEAD_VECS:
+                s[g + v] = (D,)
         scope, att, Tq = "NextItemDecoder/decoder", "vanilla_attention", 1
     else:
         scope, att, Tq = "UserHistoryEncoder/encoder", "self_attention", L
@@ -110,13 +116,13 @@ def param_shapes(cfg: OracleConfig) -> Dict[str, Tuple[int, ...]]:
         for dn in ("dense", "dense_1", "dense_2"):       # Q, K, V  (time_aware_attention.py:249-253)
             s[b + dn + "/kernel"] = (D, D)
             s[b + dn + "/bias"] = (D,)
-        if cfg.kind in (MTAM, MTAM_VIA_T_GRU, PISTREC, TA_SASREC):
+        if cfg.kind in MTAM_FAMILY + (PISTREC, TA_SASREC):
             s[b + att + "/_time_input_w"] = (D, D)
             for v in GATE_LIVE + GATE_DEAD:
                 s[b + att + "/" + v] = (Tq, L)
         s[b + att + "/ln/beta"] = (D,)
         s[b + att + "/ln/gamma"] = (D,)
-    top = "NextItemDecoder" if cfg.kind in (MTAM, MTAM_VIA_T_GRU) else "UserHistoryEncoder"
+    top = "NextItemDecoder" if cfg.kind in MTAM_FAMILY else "UserHistoryEncoder"
     s[top + "/LayerNorm/beta"] = (D,)
     s[top + "/LayerNorm/gamma"] = (D,)
     return s
@@ -272,24 +278,29 @@ def attention_block(kind, q, e, tq, tk, key_len, query_len, p, prefix, att, H, d
     return _ln(y, p[a + "ln/gamma"], p[a + "ln/beta"], LN_EPS_BLOCK)
 
 
-def tgru_new(X, timelast, seq_len, p, g):
+def tgru_new(X, timelast, seq_len, p, g, plain=False):
     """dynamic_rnn(TimeAwareGRUCell_decay_new, sequence_length=seq_len-1)
-    Model/Modules/time_aware_rnn.py:186-269, gru.py:69-77.  Returns outputs [B,L,D] (zeros past length)."""
+    Model/Modules/time_aware_rnn.py:186-269, gru.py:69-77.  Returns outputs [B,L,D] (zeros past length).
+    plain=True: GRU.gru_net (gru.py:60-67) -- tf.nn.rnn_cell.GRUCell, the same gates without the time gate T."""
     B, L, D = X.shape
     h = torch.zeros(B, D, dtype=X.dtype)
     Wg, bg = p[g + "gates/kernel"], p[g + "gates/bias"]
     Wc, bc = p[g + "candidate/kernel"], p[g + "candidate/bias"]
-    kw1, kb1, hw1 = p[g + "_time_kernel_w1"], p[g + "_time_kernel_b1"], p[g + "_time_history_w1"]
-    tw1, tb1 = p[g + "_time_w1"], p[g + "_time_b1"]
-    kw2, tw12, tb12 = p[g + "_time_kernel_w2"], p[g + "_time_w12"], p[g + "_time_b12"]
+    if not plain:
+        kw1, kb1, hw1 = p[g + "_time_kernel_w1"], p[g + "_time_kernel_b1"], p[g + "_time_history_w1"]
+        tw1, tb1 = p[g + "_time_w1"], p[g + "_time_b1"]
+        kw2, tw12, tb12 = p[g + "_time_kernel_w2"], p[g + "_time_w12"], p[g + "_time_b12"]
     outs = []
     n = seq_len - 1
     for t in range(L):
         x = X[:, t]
         dlt = timelast[:, t:t + 1]
-        a = torch.relu(x * kw1 + kb1 + h * hw1)                       # :228
-        s = torch.relu(tw1 * dlt + tb1)                               # :236
-        T = torch.sigmoid(kw2 * a + tw12 * s + tb12)                  # :237
+        if plain:
+            T = 1.0
+        else:
+            a = torch.relu(x * kw1 + kb1 + h * hw1)                   # :228
+            s = torch.relu(tw1 * dlt + tb1)                           # :236
+            T = torch.sigmoid(kw2 * a + tw12 * s + tb12)              # :237
         ru = torch.sigmoid(torch.cat([x, h], 1) @ Wg + bg)            # :243-247
         r, u = ru[:, :D], ru[:, D:]                                   # :248
         c = torch.tanh(torch.cat([x, r * h], 1) @ Wc + bc)            # :250-256
@@ -347,15 +358,15 @@ def forward(cfg: OracleConfig, params: Dict[str, torch.Tensor], feed: Dict[str, 
 
     X = torch.relu(torch.cat([Ei, Ec], 2) @ p["position_embedding/dense4emb/kernel"]) + Ep   # :95-103
     out["X"] = X
-    if cfg.kind in (MTAM, MTAM_VIA_T_GRU):
+    if cfg.kind in MTAM_FAMILY:
         g = "ShortTermIntentEncoder/"
-        rnn = tgru_new(X, fl["timelast_list"], seq_len, p, g)
+        rnn = tgru_new(X, fl["timelast_list"], seq_len, p, g, plain=cfg.kind in PLAIN_GRU_KINDS)
         out["rnn"] = rnn
         pos = (seq_len - 2).clamp(min=0)                               # mask_index-1, MTAMRec_model.py:75-79
         q = rnn[torch.arange(B), pos][:, None, :]                      # gather_indexes net_utils.py:82-92
         memory = X                                                     # MTAM: user_history = the embedded behaviours (:65)
-        if cfg.kind == MTAM_VIA_T_GRU:
-            # the memory is the T-GRU's output sequence (zeros from step seq_len-1 on, dynamic_rnn), keys still masked
+        if cfg.kind in MEMORY_IS_RNN_KINDS:
+            # the memory is the (T-)GRU's output sequence (zeros from step seq_len-1 on, dynamic_rnn), keys still masked
             # by seq_length; the query is layer-normed first                       MTAMRec_model.py:180-189
             memory = rnn
             q = _ln(q[:, 0], p[g + "LayerNorm/gamma"], p[g + "LayerNorm/beta"], LN_EPS_FINAL)[:, None, :]

@@ -22,6 +22,9 @@ CASES = {
     "BPRMF": dict(L=7, D=32, H=1, N=1, user_count=12, item_count=60, category_count=5),
     # oracle-only so far (O.NEXT_KINDS): pinned now so that the CUDA path of the next round has a fixed target
     "MTAM_VIA_T_GRU": dict(L=9, D=32, H=2, N=2, user_count=12, item_count=60, category_count=5),
+    # round 2: the plain-GRU siblings (MTAMRec_model.py:93-125, 206-233)
+    "MTAM_NO_TIME_AWARE_RNN": dict(L=9, D=32, H=2, N=2, user_count=12, item_count=60, category_count=5),
+    "MTAM_VIA_RNN": dict(L=9, D=32, H=2, N=2, user_count=12, item_count=60, category_count=5),
 }
 
 
@@ -37,7 +40,10 @@ def build(kind):
 
 
 def main():
+    only = sys.argv[1:]
     for kind in CASES:
+        if only and kind not in only:       # regenerate named kinds only (the others stay byte-identical in git)
+            continue
         cfg, P, feed = build(kind)
         fwd, grads, pieces = O.loss_and_grads(cfg, P, feed, bpr_negative=7)
         tr = O.OracleTrainer(cfg, P)

@@ -24,16 +24,17 @@ def _name():
     return os.environ.get("PYTEST_CURRENT_TEST", "?").split("::", 1)[-1].split(" ")[0]
 
 
-def make(D, L, N, H, B, items, users, cats, seed=7, gemm_mode=0):
+def make(D, L, N, H, B, items, users, cats, seed=7, gemm_mode=0, kind=None):
     from mtamrecommender_b200 import engine as E
-    cfg = O.OracleConfig(kind=O.MTAM_VIA_T_GRU, L=L, D=D, H=H, N=N, user_count=users, item_count=items, category_count=cats)
+    kind = kind or O.MTAM_VIA_T_GRU
+    cfg = O.OracleConfig(kind=kind, L=L, D=D, H=H, N=N, user_count=users, item_count=items, category_count=cats)
     P = O.init_params(cfg, seed)
     rng = np.random.default_rng(seed + 1)
     for k in P:
         if k.endswith("/bias") or k.endswith("/beta"):
             P[k] = (P[k] + 0.1 * rng.standard_normal(P[k].shape)).astype(np.float32)
     feed = O.synth_batch(cfg, B, seed + 2)
-    eng = E.Engine(E.ModelConfig(kind="MTAM_VIA_T_GRU", max_batch=B, L=L, D=D, H=H, N=N, user_count=users, item_count=items,
+    eng = E.Engine(E.ModelConfig(kind=kind, max_batch=B, L=L, D=D, H=H, N=N, user_count=users, item_count=items,
                                  category_count=cats, gemm_mode=gemm_mode))
     eng.set_params(P)
     return cfg, P, feed, eng
@@ -45,11 +46,13 @@ CASES = [dict(D=64, L=12, N=2, H=1, B=37, items=500, users=50, cats=11),
          dict(D=64, L=50, N=6, H=1, B=130, items=5000, users=1000, cats=100)]
 
 
+# MTAM_via_T_GRU, and the two plain-GRU siblings (MTAM_no_time_aware_rnn :93-125, MTAM_via_rnn :206-233)
+@pytest.mark.parametrize("kind", [O.MTAM_VIA_T_GRU, O.MTAM_NO_TA_RNN, O.MTAM_VIA_RNN])
 @pytest.mark.parametrize("gemm_mode", [0, 1])
 @pytest.mark.parametrize("case", CASES)
-def test_forward_gradients_and_steps(case, gemm_mode):
+def test_forward_gradients_and_steps(case, gemm_mode, kind):
     import torch
-    cfg, P, feed, eng = make(**case, gemm_mode=gemm_mode)
+    cfg, P, feed, eng = make(**case, gemm_mode=gemm_mode, kind=kind)
     assert set(eng.param_names()) == set(P)
     fwd, grads, pieces = O.loss_and_grads(cfg, P, feed)
     _, g32, _ = O.loss_and_grads(cfg, P, feed, torch.float32)

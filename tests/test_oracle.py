@@ -134,11 +134,11 @@ def test_record_construction_and_feed_padding():
 
 
 # ---- finite differences ----------------------------------------------------------------------
-@pytest.mark.parametrize("kind", [O.MTAM, O.PISTREC, O.TISASREC, O.SASREC, O.MTAM_VIA_T_GRU])
+@pytest.mark.parametrize("kind", [O.MTAM, O.PISTREC, O.TISASREC, O.SASREC, O.MTAM_VIA_T_GRU, O.MTAM_NO_TA_RNN, O.MTAM_VIA_RNN])
 def test_oracle_gradients_by_finite_differences(kind):
     cfg = O.OracleConfig(kind=kind, L=6, D=32, H=2, N=2, user_count=5, item_count=20, category_count=3)
     P = {k: v.astype(np.float64) for k, v in O.init_params(cfg, 8).items()}
-    if kind == O.MTAM_VIA_T_GRU:
+    if kind in O.MEMORY_IS_RNN_KINDS:
         # its memory rows are exactly zero from step seq_len-1 on, so with the zero-initialised biases the K,V ReLU
         # pre-activations of those (unmasked) keys sit exactly on the kink, where no derivative exists: move off it
         brng = np.random.default_rng(5)
