@@ -109,6 +109,14 @@ __global__ void __launch_bounds__(OS_THREADS, 2) os_pass_kernel(const int32_t* _
     const int64_t j = wbase + r * 32 + lane;
     key[r] = (j < n) ? __ldg(keys_in + j) : 0;
   }
+  // the values travel with the keys from the start: loading them only when they are placed costs one more exposed
+  // memory latency per pass
+  int32_t val[OS_ITEMS];
+#pragma unroll
+  for (int r = 0; r < OS_ITEMS; ++r) {
+    const int64_t j = wbase + r * 32 + lane;
+    val[r] = FIRST ? (int32_t)j : ((j < n) ? __ldg(vals_in + j) : 0);
+  }
 #pragma unroll
   for (int r = 0; r < OS_ITEMS; ++r) {
     const int64_t j = wbase + r * 32 + lane;
@@ -219,10 +227,8 @@ __global__ void __launch_bounds__(OS_THREADS, 2) os_pass_kernel(const int32_t* _
   }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < OS_ITEMS; ++r) {
-    const int64_t j = wbase + r * 32 + lane;
-    if (pos[r] >= 0) sbuf[pos[r]] = FIRST ? (int32_t)j : __ldg(vals_in + j);
-  }
+  for (int r = 0; r < OS_ITEMS; ++r)
+    if (pos[r] >= 0) sbuf[pos[r]] = val[r];
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < OS_ITEMS; ++r) {
