@@ -56,7 +56,13 @@ typedef enum {
 /* How the dense contractions are computed. */
 typedef enum {
   MTAM_GEMM_FP32 = 0,       /* fp32 FFMA everywhere (tightest parity) */
-  MTAM_GEMM_TF32X3 = 1      /* tcgen05 kind::tf32, 3-term error-compensated split (fp32-class accuracy) */
+  MTAM_GEMM_TF32X3 = 1,     /* tcgen05 kind::tf32, 3-term error-compensated split (fp32-class accuracy) */
+  MTAM_GEMM_TF32 = 2        /* the separately-toleranced fast mode (SURVEY 8c "bf16-operand GEMM mode"): as TF32X3, except
+                               that the three products of the softmax cross-entropy (logits, dPred, dTable: over 90 % of
+                               the FLOPs of a large-catalogue step) are issued as ONE kind::tf32 MMA each, operands
+                               rounded to nearest tf32 (10 mantissa bits), fp32 accumulation.  Tolerance (tests):
+                               loss rel 1e-2, gradients norm-wise rel 2e-2, recall@50 >= 0.99.  The top-k filter keeps
+                               the 3-term product (its result is exact either way). */
 } mtam_gemm_mode;
 
 /* base_model.init_optimizer (base_model.py:71-80).  Adam is what every preset uses; any name the reference does not

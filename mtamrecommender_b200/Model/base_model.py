@@ -13,7 +13,7 @@ import time
 import numpy as np
 
 from .. import _lib
-from .._lib import GEMM_FP32, GEMM_TF32X3
+from .._lib import GEMM_FP32, GEMM_TF32, GEMM_TF32X3
 from ..engine import Engine, ModelConfig
 from ..util import checkpoint as ckpt
 from ..util import summary as tb
@@ -58,7 +58,7 @@ class base_model(object):
                           D=self.num_units, H=self.num_heads, N=self.num_blocks, user_count=emb.user_count,
                           item_count=emb.item_count, category_count=emb.category_count, reg=F.regulation_rate,
                           clip=F.max_gradient_norm,
-                          gemm_mode=GEMM_FP32 if getattr(F, "gemm_mode", "tf32x3") == "fp32" else GEMM_TF32X3,
+                          gemm_mode={"fp32": GEMM_FP32, "tf32": GEMM_TF32}.get(getattr(F, "gemm_mode", "tf32x3"), GEMM_TF32X3),
                           optimizer=self.optimizer_name,
                           # attention dropout: applied by the plain / TiSAS blocks only (multihead_attention.py:179,
                           # time_aware_attention.py:198); the time-aware kinds ignore it, as in the reference

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmtam_b200.so")
 ABI_VERSION = 2
 KINDS = {"MTAM": 0, "PISTREC": 1, "SASREC": 2, "TA_SASREC": 3, "TISASREC": 4, "BPRMF": 5, "MTAM_VIA_T_GRU": 6,
          "MTAM_NO_TIME_AWARE_RNN": 7, "MTAM_VIA_RNN": 8}
-GEMM_FP32, GEMM_TF32X3 = 0, 1
+GEMM_FP32, GEMM_TF32X3, GEMM_TF32 = 0, 1, 2
 OPTIMIZERS = {"adam": 0, "sgd": 1}
 S_LOSS, S_LOSS_ORIGIN, S_L2_NORM, S_GLOBAL_NORM, S_CLIP_SCALE, S_COUNT = 0, 1, 2, 3, 4, 8
 PARAM_DEAD, PARAM_TABLE = 1, 2

@@ -357,14 +357,15 @@ int ce_backward_f32(int D, const float* pred, const float* table, const int32_t*
 
 int ce_forward(int mode, int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
                float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st) {
-  if (mode == MTAM_GEMM_TF32X3 && ce_tc_supported(D))
-    return ce_forward_tc(D, pred, table, target, B, V, ws, tlogit, lse, loss_origin, block_partial, n_partial, st);
+  if (gemm_mode_is_tc(mode) && ce_tc_supported(D))
+    return ce_forward_tc(D, pred, table, target, B, V, ws, tlogit, lse, loss_origin, block_partial, n_partial, st,
+                         gemm_mode_ce_terms(mode));
   return ce_forward_f32(D, pred, table, target, B, V, ws, tlogit, lse, loss_origin, block_partial, n_partial, st);
 }
 int ce_backward(int mode, int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B,
                 int V, float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st) {
-  if (mode == MTAM_GEMM_TF32X3 && ce_tc_supported(D))
-    return ce_backward_tc(D, pred, table, target, lse, B, V, inv_batch, ws, dTable, dpred, st);
+  if (gemm_mode_is_tc(mode) && ce_tc_supported(D))
+    return ce_backward_tc(D, pred, table, target, lse, B, V, inv_batch, ws, dTable, dpred, st, 3, gemm_mode_ce_terms(mode));
   return ce_backward_f32(D, pred, table, target, lse, B, V, inv_batch, ws, dTable, dpred, st);
 }
 

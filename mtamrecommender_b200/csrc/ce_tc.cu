@@ -30,17 +30,20 @@ using namespace tc;
 namespace {
 
 constexpr int QM = 128;          // Q tile rows = UMMA M
-constexpr int kEpiWarps = 8, kProdWarps = 4;
-constexpr int kEpi = kEpiWarps * 32, kProd = kProdWarps * 32;
-constexpr int kWarpS = kEpiWarps + kProdWarps, kWarpPV = kWarpS + 1;   // the two MMA-issuing warps
-constexpr int kWarpLd = kWarpPV + 1;                                    // bulk-copy issuing warp
-constexpr int kThreads = (kWarpLd + 1) * 32;
+constexpr int kProdWarps = 4, kProd = kProdWarps * 32;
 constexpr float kLog2e = 1.4426950408889634f;
 enum { CE_FWD = 0, CE_DP = 1, CE_DT = 2, CE_BMAX = 3 };
 // X tile rows = UMMA N of S (and K of O).  The forward pass has no second product and room in TMEM for
 // 128-column S buffers; a 128-wide MMA keeps the tensor pipe ahead of the issuing thread.
 __host__ __device__ constexpr int ce_bx(int mode) { return (mode == CE_FWD || mode == CE_BMAX) ? 128 : 64; }
 __host__ __device__ constexpr bool ce_pv(int mode) { return mode == CE_DP || mode == CE_DT; }
+// Epilogue warps.  A warp reaches the TMEM lanes of quadrant (warp % 4), so they come in sets of four; set p handles the
+// p-th slice of a tile's columns.  Two sets everywhere: four sets (16 warps, measured with tools/ce_trace.cu) made the
+// backward passes SLOWER (dPred pass 117 -> 138 us at cfg3): the 64 x 128 exponentials of a tile keep the MUFU pipe busy
+// for about 1000 cycles whatever the number of warps that issue them, and the extra warps only add barrier traffic.
+__host__ __device__ constexpr int ce_epi_warps(int mode) { return 8; }
+// warp roles: [0, EW) epilogue, [EW, EW + 4) producers, then the S issuer, the O issuer and the bulk-copy warp
+__host__ __device__ constexpr int ce_threads(int mode) { return (ce_epi_warps(mode) + kProdWarps + 3) * 32; }
 // raw fp32 staging slots (64 X rows each) filled by bulk copies.  CE_DT keeps to 2 (161 KB of shared memory in all) so
 // that one of its CTAs fits on an SM beside a T-GRU / hop CTA of the backward chain it overlaps with (model.cu)
 __host__ __device__ constexpr int ce_nsg(int mode) { return mode == CE_DT ? 2 : (mode == CE_DP ? 3 : 4); }
@@ -89,6 +92,8 @@ struct CeTcArgs {
   float* dTable;            // DT : [V][D]
   float* bmax;              // BMAX: [B][bmax_ld] maxima of the logits over buckets of bmax_bs (16 / 64) consecutive items
   int bmax_ld, bmax_bs;
+  int terms;                // 3: error-compensated hi/lo split (MTAM_GEMM_TF32X3); 1: one MMA per product on operands
+                            // rounded to tf32 (MTAM_GEMM_TF32) -- the lo tiles / TMEM columns are then left unused
 };
 
 struct Bars {
@@ -97,7 +102,9 @@ struct Bars {
 };
 
 template <int D, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
+__global__ void __launch_bounds__(ce_threads(MODE), 1) ce_tc_kernel(const CeTcArgs a) {
+  constexpr int kEpiWarps = ce_epi_warps(MODE), kEpi = kEpiWarps * 32, EP = kEpiWarps / 4;
+  constexpr int kWarpS = kEpiWarps + kProdWarps, kWarpPV = kWarpS + 1, kWarpLd = kWarpPV + 1;
   constexpr int BX = ce_bx(MODE);
   constexpr int KC = D / 32;                      // 32-float (128-byte) chunks of D
   constexpr int XT = BX * 32;                     // floats per chunk tile
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
   __shared__ __align__(16) int tgt_s[MAXST][64];     // CE_DT: their target item ids
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool t3 = a.terms != 1;
   const float* Qsrc;
   const float* Xsrc;
   int q0, qmax, xmax, xt_begin, n;
@@ -159,15 +167,18 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
   const uint32_t tmem = tmem_slot;
   if (tid == 0) CE_TRACE(10, 0);     // CTA set up
 
-  // epilogue thread geometry: TMEM lane quadrant = warp % 4; the two warps of a quadrant split the columns
-  const int quad = warp & 3, half = (warp >> 2) & 1;
+  // epilogue thread geometry: TMEM lane quadrant = warp % 4; the EP warps of a quadrant split the columns
+  const int quad = warp & 3, half = (warp >> 2) & (EP - 1);
+  // the D columns of the Q tile and of O are split over QP of the EP sets, 16 or 32 columns each
+  constexpr int QP = (D / 16 < EP) ? D / 16 : EP;
+  constexpr int QC = D / QP;
+  const bool qo_owner = half < QP;
   const int qrow = q0 + quad * 32 + lane;
   const bool qvalid = qrow < qmax;
   const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
 
-  if (warp < kEpiWarps) {
-    // stationary Q tile -> TMEM (hi / lo split): thread = row, D/2 columns each
-    constexpr int QC = D / 2;
+  if (warp < kEpiWarps && qo_owner) {
+    // stationary Q tile -> TMEM (hi / lo split): thread = row, QC columns each
 #pragma unroll
     for (int c = 0; c < QC; c += 16) {
       uint32_t hi[16], lo[16];
@@ -179,12 +190,12 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float h = tf32_hi(e[u]);
-          hi[j + u] = __float_as_uint(h);
+          hi[j + u] = t3 ? __float_as_uint(h) : tf32_rn(e[u]);
           lo[j + u] = __float_as_uint(e[u] - h);
         }
       }
       tmem_st16(lane_base + COL_QH + half * QC + c, hi);
-      tmem_st16(lane_base + COL_QL + half * QC + c, lo);
+      if (t3) tmem_st16(lane_base + COL_QL + half * QC + c, lo);
     }
     tmem_st_wait();
   }
@@ -228,7 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       for (int j = 0; j < PER; ++j) {
         const int q = pt + j * kProd;
         const int row = hrow + q / (D / 4), c4 = q % (D / 4);
-        store_chunk_split<false>(xs + (c4 >> 3) * XT, xs + KC * XT + (c4 >> 3) * XT, row, c4 & 7, r[j]);
+        if (t3) store_chunk_split<false>(xs + (c4 >> 3) * XT, xs + KC * XT + (c4 >> 3) * XT, row, c4 & 7, r[j]);
+        else store_chunk_rn<false>(xs + (c4 >> 3) * XT, row, c4 & 7, r[j]);
       }
       mbar_arrive(&bars.stg_empty[u % NSG]);     // every register of r[] has been read by the stores above
       if (hrow + 64 == BX) {
@@ -243,7 +255,8 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
         for (int j = 0; j < PER; ++j) {
           const int q = pt + j * kProd;
           const int row = q / (D / 4), c4 = q % (D / 4);
-          store_chunk_split<true>(xm + (c4 >> 3) * XT, xm + KC * XT + (c4 >> 3) * XT, row, c4 & 7, r[j]);
+          if (t3) store_chunk_split<true>(xm + (c4 >> 3) * XT, xm + KC * XT + (c4 >> 3) * XT, row, c4 & 7, r[j]);
+          else store_chunk_rn<true>(xm + (c4 >> 3) * XT, row, c4 & 7, r[j]);
         }
         if (MODE == CE_DT && pt < 64) {
           const int gr = (xt_begin + i) * BX + pt;
@@ -260,8 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       stash(ra, u);
     }
   } else if (warp == kWarpLd) {
-    // ================= loader (one thread): bulk copies of 64 contiguous X rows into the staging ring =================
-    if (lane == 0) {
+    // ================= loader (converged warp, one elected thread): bulk copies of 64 contiguous X rows into the ring ====
+    {
       const int nu = n * (BX / 64);
       for (int u = 0; u < nu; ++u) {
         const int sl = u % NSG;
@@ -269,19 +282,22 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
         if (u >= NSG) mbar_wait(&bars.stg_empty[sl], ((u / NSG) - 1) & 1);
         const int rows = min(64, xmax - x0);
         const uint32_t bytes = rows > 0 ? (uint32_t)rows * D * 4 : 0;
-        mbar_arrive_expect_tx(&bars.stg_full[sl], bytes);
-        if (bytes) bulk_g2s(Stg + sl * SLOT, Xsrc + (int64_t)x0 * D, bytes, &bars.stg_full[sl]);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars.stg_full[sl], bytes);
+          if (bytes) bulk_g2s(Stg + sl * SLOT, Xsrc + (int64_t)x0 * D, bytes, &bars.stg_full[sl]);
+        }
       }
     }
   } else if (warp == kWarpS) {
-    // ================= S issuer (one thread): S(i) = Q X(i)^T, Q read from TMEM =================
-    if (lane == 0) {
+    // ================= S issuer (the warp stays converged, one elected thread issues): S(i) = Q X(i)^T =================
+    {
       constexpr uint32_t idS = idesc_tf32(QM, BX, 0, 0);
       for (int i = 0; i < n; ++i) {
         const int st = i % NST, use = i / NST, b = i & 1;
         mbar_wait(&bars.xk_full[st], use & 1);
         if (i >= 2) mbar_wait(PV ? &bars.sg_empty[b] : &bars.s_empty[b], ((i >> 1) - 1) & 1);   // buffer b consumed
         tc_fence_after();
+        if (!elect_one()) continue;
         CE_TRACE(1, i);
         const uint32_t xh = desc_lo(smem_u32(Xs + st * STAGE), 16);
         const uint32_t sacc = tmem + COL_S0 + b * SW;
@@ -292,9 +308,13 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
             const uint32_t qh = tmem + COL_QH + kc * 32 + ks * 8, ql = tmem + COL_QL + kc * 32 + ks * 8;
             const uint64_t bh = desc_join(xh + ((kc * XT * 4 + ks * 32) >> 4), kDescHiK);
             const uint64_t bl = desc_join(xh + (((KC + kc) * XT * 4 + ks * 32) >> 4), kDescHiK);
-            mma_tf32_ts(sacc, ql, bh, idS, (kc | ks) != 0);   // small terms first
-            mma_tf32_ts(sacc, qh, bl, idS, true);
-            mma_tf32_ts(sacc, qh, bh, idS, true);
+            bool acc = (kc | ks) != 0;
+            if (t3) {                                         // small terms first
+              mma_tf32_ts(sacc, ql, bh, idS, acc);
+              mma_tf32_ts(sacc, qh, bl, idS, true);
+              acc = true;
+            }
+            mma_tf32_ts(sacc, qh, bh, idS, acc);
           }
         }
         mma_commit(&bars.s_full[b]);
@@ -303,8 +323,8 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       }
     }
   } else if (warp == kWarpPV) {
-    // ================= O issuer (one thread): O += G(j) X(j), G read from TMEM =================
-    if (PV && lane == 0) {
+    // ================= O issuer (converged warp, one elected thread issues): O += G(j) X(j), G read from TMEM =================
+    if (PV) {
       constexpr uint32_t idO = idesc_tf32(QM, D, 0, 1);
       for (int j = 0; j < n; ++j) {
         const int st = j % NST, use = j / NST, b = j & 1;
@@ -313,6 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
         mbar_wait(&bars.g_full[b], (j >> 1) & 1);
         if (j % kPromote == 0 && chunk >= 2) mbar_wait(&bars.o_empty[ob], ((chunk >> 1) - 1) & 1);   // drained
         tc_fence_after();
+        if (!elect_one()) continue;
         CE_TRACE(5, j);
         const uint32_t xmh = desc_lo(smem_u32(Xs + st * STAGE + 2 * KC * XT), BX * 128);
         const uint32_t ghi = tmem + COL_S0 + b * SW, glo = tmem + COL_GL0 + b * SW;
@@ -321,9 +342,13 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
         for (int ks = 0; ks < BX / 8; ++ks) {
           const uint64_t bh = desc_join(xmh + ((ks * 1024) >> 4), kDescHiMN);
           const uint64_t bl = desc_join(xmh + ((KC * XT * 4 + ks * 1024) >> 4), kDescHiMN);
-          mma_tf32_ts(oacc, glo + ks * 8, bh, idO, ((j % kPromote) | ks) != 0);
-          mma_tf32_ts(oacc, ghi + ks * 8, bl, idO, true);
-          mma_tf32_ts(oacc, ghi + ks * 8, bh, idO, true);
+          bool acc = ((j % kPromote) | ks) != 0;
+          if (t3) {
+            mma_tf32_ts(oacc, glo + ks * 8, bh, idO, acc);
+            mma_tf32_ts(oacc, ghi + ks * 8, bl, idO, true);
+            acc = true;
+          }
+          mma_tf32_ts(oacc, ghi + ks * 8, bh, idO, acc);
         }
         mma_commit(&bars.xm_empty[st]);
         mma_commit(&bars.sg_empty[b]);
@@ -332,8 +357,8 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       }
     }
   } else {
-    // ================= epilogue warps: thread = one Q row (TMEM lane) x half of the tile's columns =================
-    constexpr int HC = BX / 2;    // columns per thread per tile
+    // ================= epilogue warps: thread = one Q row (TMEM lane) x 1/EP of the tile's columns =================
+    constexpr int HC = BX / EP;   // columns per thread per tile
     int tg = -1;
     float nl2 = 0.f;              // CE_DP: -lse[row]*log2(e)
     float m = -INFINITY, s = 0.f;
@@ -342,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       if (MODE == CE_DP) nl2 = -__ldg(a.lse + qrow) * kLog2e;
     }
     const float gscale = qvalid ? a.inv_batch : 0.f;
-    constexpr int OC = D / 2;     // O columns per thread
+    constexpr int OC = QC;        // O columns per thread (sets >= QP own none)
     float osum[PV ? OC : 1];      // promoted accumulator (see kPromote)
 #pragma unroll
     for (int c = 0; c < (PV ? OC : 1); ++c) osum[c] = 0.f;
@@ -351,12 +376,14 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       const int ob = chunk & 1;
       mbar_wait(&bars.o_full[ob], (chunk >> 1) & 1);
       tc_fence_after();
+      if (qo_owner) {
 #pragma unroll
-      for (int c = 0; c < OC; c += 16) {
-        float v[16];
-        tmem_ld16(lane_base + COL_O + ob * 64 + half * OC + c, v);
+        for (int c = 0; c < OC; c += 16) {
+          float v[16];
+          tmem_ld16(lane_base + COL_O + ob * 64 + half * OC + c, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) osum[(PV ? c : 0) + (PV ? j : 0)] += v[j];
+          for (int j = 0; j < 16; ++j) osum[(PV ? c : 0) + (PV ? j : 0)] += v[j];
+        }
       }
       tc_fence_before();
       mbar_arrive(&bars.o_empty[ob]);
@@ -367,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
       mbar_wait(&bars.s_full[b], ub & 1);
       if (MODE == CE_DT) mbar_wait(&bars.xm_full[st], (i / NST) & 1);
       tc_fence_after();
-      if (lane == 0 && quad == 0) CE_TRACE(3 + 5 * half, i);
+      if (lane == 0 && quad == 0 && half < 2) CE_TRACE(3 + 5 * half, i);
       const uint32_t scol = lane_base + COL_S0 + b * SW + half * HC, gcol = lane_base + COL_GL0 + b * SW + half * HC;
       const bool ragged = x0 + HC > xmax;          // only the catalogue's last tile (warp-uniform)
       if (!PV) {
@@ -382,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
         }
         tc_fence_before();
         mbar_arrive(&bars.s_empty[b]);
-        if (lane == 0 && quad == 0) CE_TRACE(4 + 5 * half, i);
+        if (lane == 0 && quad == 0 && half < 2) CE_TRACE(4 + 5 * half, i);
         float v[HC];
 #pragma unroll
         for (int j = 0; j < HC; ++j) v[j] = __uint_as_float(r[j]);
@@ -477,27 +504,27 @@ __global__ void __launch_bounds__(kThreads, 1) ce_tc_kernel(const CeTcArgs a) {
           for (int j = 0; j < 16; ++j) {
             const float g = v[j] * gscale;          // rows past the Q range: 0
             const float h = tf32_hi(g);
-            hi[j] = __float_as_uint(h);
+            hi[j] = t3 ? __float_as_uint(h) : tf32_rn(g);
             lo[j] = __float_as_uint(g - h);
           }
           tmem_st16(scol + c, hi);
-          tmem_st16(gcol + c, lo);
+          if (t3) tmem_st16(gcol + c, lo);
         }
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bars.g_full[b]);
-      if (lane == 0 && quad == 0) CE_TRACE(4 + 5 * half, i);
+      if (lane == 0 && quad == 0 && half < 2) CE_TRACE(4 + 5 * half, i);
       // the chunk that ended with tile i-1 has had this tile's epilogue time to finish its MMAs: promote it
       if (PV && i >= 1 && (i - 1) % kPromote == kPromote - 1) drain((i - 1) / kPromote);
     }
     if (MODE == CE_BMAX) {
     } else if (MODE == CE_FWD) {
-      if (qvalid) a.ms_partial[(int64_t)(blockIdx.x * 2 + half) * a.B + qrow] = make_float2(m, s);
+      if (qvalid) a.ms_partial[(int64_t)(blockIdx.x * EP + half) * a.B + qrow] = make_float2(m, s);
     } else {
       if (PV) drain((n - 1) / kPromote);     // the last chunk (every earlier one was promoted inside the loop)
       if (tid == 0) CE_TRACE(12, 0);   // accumulator complete
-      if (qvalid) {
+      if (qvalid && qo_owner) {
         float* dst = ((MODE == CE_DP) ? a.dpred_partial + ((int64_t)blockIdx.x * a.B + qrow) * D : a.dTable + (int64_t)qrow * D) + half * OC;
 #pragma unroll
         for (int c = 0; c < (PV ? OC : 0); c += 4)
@@ -519,7 +546,7 @@ int ce_tc_launch(dim3 grid, const CeTcArgs& a, cudaStream_t st) {
   constexpr int KC = D / 32;
   const size_t smem = (size_t)(2 * (ce_pv(MODE) ? 4 : 2) * KC * ce_bx(MODE) * 32 + ce_nsg(MODE) * 64 * D) * sizeof(float) + 1024;
   MTAM_CUDA_CHECK(cudaFuncSetAttribute(ce_tc_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ce_tc_kernel<D, MODE><<<grid, kThreads, smem, st>>>(a);
+  ce_tc_kernel<D, MODE><<<grid, ce_threads(MODE), smem, st>>>(a);
   MTAM_LAUNCH_CHECK();
   return 0;
 }
@@ -544,8 +571,10 @@ int ce_tc_ranges(int B, int V) {
 }
 
 int ce_forward_tc(int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
-                  float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st) {
+                  float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st,
+                  int terms) {
   CeTcArgs a{};
+  a.terms = terms;
   a.pred = pred; a.table = table; a.target = target; a.B = B; a.V = V;
   int G;
   ce_tc_partition(CE_FWD, B, V, &G, &a.tiles_per_cta);
@@ -560,8 +589,9 @@ int ce_forward_tc(int D, const float* pred, const float* table, const int32_t* t
 
 // parts: 1 = dpred only, 2 = the dense item-table gradient only (independent of part 1; may run on another stream), 3 = both
 int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
-                   float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st, int parts) {
+                   float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st, int parts, int terms) {
   CeTcArgs a{};
+  a.terms = terms;
   a.pred = pred; a.table = table; a.target = target; a.lse = lse; a.B = B; a.V = V; a.inv_batch = inv_batch;
   int G;
   ce_tc_partition(CE_DP, B, V, &G, &a.tiles_per_cta);
@@ -587,6 +617,7 @@ int ce_bucket_max_tc(int D, const float* pred, int B, const float* table, int V,
                      cudaStream_t st) {
   if (bs != 16 && bs != 64) return set_error(MTAM_ERR_INVALID, "bucket maxima: bucket size %d not in {16, 64}", bs);
   CeTcArgs a{};
+  a.terms = 3;
   a.pred = pred; a.table = table; a.B = B; a.V = V; a.bmax = bmax; a.bmax_ld = ld; a.bmax_bs = bs;
   int G;
   ce_tc_partition(CE_BMAX, B, V, &G, &a.tiles_per_cta);

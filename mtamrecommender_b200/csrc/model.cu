@@ -317,7 +317,7 @@ static int validate(const mtam_config* c) {
     return set_error(MTAM_ERR_INVALID, "num_heads=%d must divide 32 and num_units", c->H);
   if (c->user_rows < 1 || c->item_rows < 1 || c->category_rows < 1 || c->position_rows < 1)
     return set_error(MTAM_ERR_INVALID, "table row counts must be positive");
-  if (c->gemm_mode != MTAM_GEMM_FP32 && c->gemm_mode != MTAM_GEMM_TF32X3)
+  if (c->gemm_mode != MTAM_GEMM_FP32 && !gemm_mode_is_tc(c->gemm_mode))
     return set_error(MTAM_ERR_INVALID, "unknown gemm_mode %d", c->gemm_mode);
   if (c->optimizer != MTAM_OPT_ADAM && c->optimizer != MTAM_OPT_SGD)
     return set_error(MTAM_ERR_UNSUPPORTED, "optimizer %d not built (adam, sgd)", c->optimizer);
@@ -492,18 +492,19 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   // The dense item-table gradient (dT = G^T pred, a full-machine tensor-core pass) feeds only the norm and Adam; the
   // chain behind dpred (hops, T-GRU, embedding) is latency-bound kernels on a fraction of the SMs.  Run dT beside it.
   // (Not while profiling: the per-phase times would no longer add up.)
-  const bool dt_aside = c.gemm_mode == MTAM_GEMM_TF32X3 && ce_tc_supported(D) && !h->prof && !h->rows_mode;
+  const bool dt_aside = gemm_mode_is_tc(c.gemm_mode) && ce_tc_supported(D) && !h->prof && !h->rows_mode;
+  const int ce_terms = gemm_mode_ce_terms(c.gemm_mode);
   if (h->rows_mode) {
     // dpred was placed in the workspace by mtam_backward_rows (softmax against the sharded table: the caller's)
   } else if (dt_aside) {
     MTAM_CUDA_CHECK(cudaEventRecord(h->ev_fork2, st));
     MTAM_CUDA_CHECK(cudaStreamWaitEvent(h->side2, h->ev_fork2, 0));
     MTAM_TRY(ce_backward_tc(D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
-                            w.ce_ws, G + l.item, w.dpred, h->side2, 2));
+                            w.ce_ws, G + l.item, w.dpred, h->side2, 2, ce_terms));
     if (h->ev_ce_done) MTAM_CUDA_CHECK(cudaEventRecord(h->ev_ce_done, h->side2));
     MTAM_CUDA_CHECK(cudaEventRecord(h->ev_join2, h->side2));
     MTAM_TRY(ce_backward_tc(D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
-                            w.ce_ws, G + l.item, w.dpred, st, 1));
+                            w.ce_ws, G + l.item, w.dpred, st, 1, ce_terms));
   } else {
     MTAM_TRY(ce_backward(c.gemm_mode, D, w.pred, P + l.item, bt->target_item_id, w.lse, B, c.item_rows, 1.0f / (float)global_batch,
                          w.ce_ws, G + l.item, w.dpred, st));

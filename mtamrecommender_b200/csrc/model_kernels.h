@@ -98,7 +98,10 @@ int bpr_backward(const BprArgs& a, int* n_sq, cudaStream_t st);
 // ---- ce.cu ----------------------------------------------------------------------------------
 int ce_grid(int V);
 size_t ce_workspace_bytes(int B, int D, int V);
-// mode = mtam_gemm_mode: exact-fp32 FFMA tiles (ce.cu) or tcgen05 3xTF32 (ce_tc.cu; num_units 32 / 64)
+// mode = mtam_gemm_mode: exact-fp32 FFMA tiles (ce.cu) or tcgen05 (ce_tc.cu; num_units 32 / 64): 3xTF32, or one tf32
+// MMA per product (MTAM_GEMM_TF32)
+inline bool gemm_mode_is_tc(int mode) { return mode == 1 || mode == 2; }     // MTAM_GEMM_TF32X3, MTAM_GEMM_TF32
+inline int gemm_mode_ce_terms(int mode) { return mode == 2 ? 1 : 3; }
 int ce_forward(int mode, int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
                float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st);
 int ce_backward(int mode, int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B,
@@ -110,9 +113,10 @@ bool ce_tc_supported(int D);
 int ce_tc_ranges(int B, int V);
 size_t ce_ms_region_bytes(int B, int V);
 int ce_forward_tc(int D, const float* pred, const float* table, const int32_t* target, int B, int V, void* ws,
-                  float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st);
+                  float* tlogit, float* lse, float* loss_origin, float* block_partial, int* n_partial, cudaStream_t st,
+                  int terms = 3);
 int ce_backward_tc(int D, const float* pred, const float* table, const int32_t* target, const float* lse, int B, int V,
-                   float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st, int parts = 3);
+                   float inv_batch, void* ws, float* dTable, float* dpred, cudaStream_t st, int parts = 3, int terms = 3);
 
 // top-k filter pass: maxima of the logits over buckets of bs (16 / 64) consecutive table rows, [B][ld]
 int ce_bucket_max_tc(int D, const float* pred, int B, const float* table, int V, int bs, float* bmax, int ld,

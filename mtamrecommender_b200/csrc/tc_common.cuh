@@ -118,6 +118,16 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, 
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// One lane of a CONVERGED warp.  tcgen05.mma / commit take their operands from uniform registers; inside a plain
+// `if (lane == 0)` the compiler cannot know that a single thread is active and wraps every such instruction in an
+// elect / execute / branch-if-any-left loop with fresh R2UR moves (~50 issue cycles per MMA, more than a 128x64x8 MMA
+// takes to execute).  With the issuing warp kept converged and the issuing thread chosen by elect.sync, the
+// instructions are emitted straight.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n @p mov.u32 %0, 1;\n}" : "+r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
   asm volatile(
@@ -180,6 +190,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ int chunk_pos_k(int row, int chunk) { return chunk ^ (row & 7); }
 __device__ __forceinline__ int chunk_pos_mn(int row, int chunk) { return ((((chunk >> 1) ^ (row & 3)) << 1) | (chunk & 1)); }
+// round to nearest tf32, ties away from zero (the tensor core itself would truncate the low 13 bits): the single-term
+// mode's operand.  Two integer instructions (cvt.rna.tf32.f32 runs at a fraction of the ALU rate).
+__device__ __forceinline__ uint32_t tf32_rn(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+// single-term mode: only the (rounded) hi tile is written
+template <bool MN>
+__device__ __forceinline__ void store_chunk_rn(float* hi_tile, int row, int chunk, float4 v) {
+  const uint32_t off = (uint32_t)(row * 32 + ((MN ? chunk_pos_mn(row, chunk) : chunk_pos_k(row, chunk)) << 2)) * 4u;
+  sts128(smem_u32(hi_tile) + off, tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+}
 // writes the 16-byte chunk `chunk` of row `row` of the hi and lo tiles (MN: the MN-major swizzle)
 template <bool MN>
 __device__ __forceinline__ void store_chunk_split(float* hi_tile, float* lo_tile, int row, int chunk, float4 v) {

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(int M, int N, int K, const
     rb.template stash<TB == 0>(Bhi, Blo);
     fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {          // converged warp + elect.sync: straight-line MMA issue (tc_common.cuh)
       tc_fence_after();
       const uint32_t ah = smem_u32(Ahi), al = smem_u32(Alo), bh = smem_u32(Bhi), bl = smem_u32(Blo);
 #pragma unroll
@@ -256,7 +256,7 @@ int gemm_tf32x3(int transA, int transB, int M, int N, int K, const float* A, int
 int gemm_any(int mode, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const GemmEpilogue& e, void* ws, size_t ws_bytes, cudaStream_t st) {
   const bool tiny = (int64_t)cdiv(M, TM) * cdiv(N, 64) <= 4 && K <= 8192;   // a handful of tiles: no tensor-core win
-  if (mode == MTAM_GEMM_TF32X3 && !tiny) return gemm_tf32x3(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ws, ws_bytes, st);
+  if ((mode == MTAM_GEMM_TF32X3 || mode == MTAM_GEMM_TF32) && !tiny) return gemm_tf32x3(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ws, ws_bytes, st);
   return gemm_f32(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, e, ws, ws_bytes, st);
 }
 size_t gemm_any_workspace_bytes(int M, int N, int K) {

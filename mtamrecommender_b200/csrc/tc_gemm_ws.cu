@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(kWThreads, 1) tc_gemm_ws_kernel(const WsArgs g
       for (int s = 0; s < kBGroups && it.valid; ++s) it.next(g, units);
     }
   } else if (warp == kWMma) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer: the warp stays converged, one elected thread issues (tc_common.cuh: elect_one) ====
+    {
       constexpr uint32_t idesc = idesc_tf32(WM, BN, 0, TB ? 0 : 1);
       int c = 0, sc = 0;                       // chunk and sub-unit counters of this CTA
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -244,23 +244,25 @@ __global__ void __launch_bounds__(kWThreads, 1) tc_gemm_ws_kernel(const WsArgs g
             mbar_wait(&bars.a_full[sa], (c / NSA) & 1);
             mbar_wait(&bars.b_full[sb], (c / NSB) & 1);
             tc_fence_after();
-            WS_TRACE(3, c);
             const uint32_t ah = tmem + COL_A + sa * 64, al = ah + 32;
             const uint32_t bh = smem_u32(Bs + sb * 2 * BT), bl = bh + BT * 4;
+            if (elect_one()) {
+              WS_TRACE(3, c);
 #pragma unroll
-            for (int ks = 0; ks < WK / 8; ++ks) {
-              const uint64_t dbh = TB ? desc_kmajor(bh, ks) : desc_mnmajor(bh, ks, 4096);
-              const uint64_t dbl = TB ? desc_kmajor(bl, ks) : desc_mnmajor(bl, ks, 4096);
-              mma_tf32_ts(acc, al + ks * 8, dbh, idesc, !first);   // small terms first
-              mma_tf32_ts(acc, ah + ks * 8, dbl, idesc, true);
-              mma_tf32_ts(acc, ah + ks * 8, dbh, idesc, true);
-              first = false;
+              for (int ks = 0; ks < WK / 8; ++ks) {
+                const uint64_t dbh = TB ? desc_kmajor(bh, ks) : desc_mnmajor(bh, ks, 4096);
+                const uint64_t dbl = TB ? desc_kmajor(bl, ks) : desc_mnmajor(bl, ks, 4096);
+                mma_tf32_ts(acc, al + ks * 8, dbh, idesc, !first || ks > 0);   // small terms first
+                mma_tf32_ts(acc, ah + ks * 8, dbl, idesc, true);
+                mma_tf32_ts(acc, ah + ks * 8, dbh, idesc, true);
+              }
+              mma_commit(&bars.a_empty[sa]);
+              mma_commit(&bars.b_empty[sb]);
+              WS_TRACE(4, c);
             }
-            mma_commit(&bars.a_empty[sa]);
-            mma_commit(&bars.b_empty[sb]);
-            WS_TRACE(4, c);
+            first = false;
           }
-          mma_commit(&bars.acc_full[ab]);
+          if (elect_one()) mma_commit(&bars.acc_full[ab]);
         }
       }
     }

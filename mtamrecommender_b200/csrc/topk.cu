@@ -532,8 +532,8 @@ int score_topk(int mode, const float* pred, int B, int D, const float* table, in
                int32_t* idx_out, float* score_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (k < 1 || k > KMAX) return set_error(MTAM_ERR_INVALID, "top-k: k=%d outside [1,%d]", k, KMAX);
   if (row_end - row_begin < k) return set_error(MTAM_ERR_INVALID, "top-k: fewer than k=%d rows to score", k);
-  if (mode != MTAM_GEMM_FP32 && mode != MTAM_GEMM_TF32X3) return set_error(MTAM_ERR_INVALID, "top-k: unknown gemm_mode %d", mode);
-  if (mode == MTAM_GEMM_TF32X3 && ce_tc_supported(D)) {
+  if (mode != MTAM_GEMM_FP32 && !gemm_mode_is_tc(mode)) return set_error(MTAM_ERR_INVALID, "top-k: unknown gemm_mode %d", mode);
+  if (gemm_mode_is_tc(mode) && ce_tc_supported(D)) {
     if (D == 64) return score_topk_tc_launch<64>(pred, B, table, row_begin, row_end, k, idx_out, score_out, ws, ws_bytes, st);
     return score_topk_tc_launch<32>(pred, B, table, row_begin, row_end, k, idx_out, score_out, ws, ws_bytes, st);
   }

@@ -101,3 +101,72 @@ def test_softmax_ce_kernels_at_catalogue_size_against_fp64(B, V):
     # row-wise too: no single pred row may be off (a stale tile or a drifting accumulator shows here first)
     row_err = (dpred.double() - want_dp).norm(dim=1) / want_dp.norm(dim=1)
     assert float(row_err.max()) < 2e-5, float(row_err.max())
+
+
+@pytest.mark.parametrize("B,V", [(1024, 100_003), (300, 250_007)])
+def test_single_pass_tf32_softmax_ce_against_fp64(B, V):
+    """MTAM_GEMM_TF32, the separately-toleranced fast mode (SURVEY 8c): one kind::tf32 MMA per product, operands rounded
+    to 10 mantissa bits (2^-11 relative per operand), fp32 accumulation.  Stated tolerance: log-sum-exp abs 5e-3
+    (loss rel 1e-2 with room), dpred / dTable norm-wise rel 5e-3 -- three orders of magnitude looser than the fp32-class
+    claim of the 3xTF32 mode, and never mixed with it."""
+    import torch
+    from mtamrecommender_b200 import _lib, engine as E
+    D = 64
+    g = torch.Generator(device="cuda").manual_seed(B + V)
+    table = (torch.rand((V, D), generator=g, device="cuda") - 0.5) * 0.6
+    pred = torch.randn((B, D), generator=g, device="cuda")
+    target = torch.randint(0, V, (B,), generator=g, device="cuda", dtype=torch.int32)
+    lse, tl = E.softmax_ce_forward(pred, table, target, gemm_mode=_lib.GEMM_TF32)
+    logits = pred.double() @ table.double().T
+    lse64 = torch.logsumexp(logits, dim=1)
+    e_lse = float((lse.double() - lse64).abs().max())
+    e_tl = float((tl.double() - logits.gather(1, target.long()[:, None])[:, 0]).abs().max())
+    assert e_lse < 5e-3 and e_tl < 5e-3, (e_lse, e_tl)
+    assert e_tl > 1e-6, "the single-pass mode gave 3xTF32-class logits: is it wired?"
+    dtable, dpred = E.softmax_ce_backward(pred, table, target, lse, 1.0 / B, gemm_mode=_lib.GEMM_TF32)
+    G = torch.exp(logits - lse64[:, None])
+    G[torch.arange(B, device="cuda"), target.long()] -= 1.0
+    G /= B
+    want_dp, want_dt = G @ table.double(), G.T @ pred.double()
+    rel = lambda a, b: float((a.double() - b).norm() / b.norm())
+    assert rel(dpred, want_dp) < 5e-3, rel(dpred, want_dp)
+    assert rel(dtable, want_dt) < 5e-3, rel(dtable, want_dt)
+    print(f"\n[tf32 single pass B={B} V={V}] lse abs {e_lse:.2e}, target logit abs {e_tl:.2e}, "
+          f"dpred rel {rel(dpred, want_dp):.2e}, dtable rel {rel(dtable, want_dt):.2e}")
+
+
+def test_cfg3_step_in_the_single_pass_tf32_mode():
+    """The whole cfg3 train step with gemm_mode = MTAM_GEMM_TF32 against the fp64 oracle, at the mode's own tolerance:
+    loss rel 1e-2, gradients norm-wise rel 2e-2, top-50 overlap with the oracle's >= 0.99 (recall@50)."""
+    import torch
+    from mtamrecommender_b200 import _lib, engine as E
+    from mtamrecommender_b200.synth import ZipfSampler, synth_feed
+    B, L, D, N, items, cats, users = 1024, 50, 64, 6, 100_000, 1_000, 100_000
+    cfg = O.OracleConfig(kind=O.MTAM, L=L, D=D, H=1, N=N, user_count=users, item_count=items, category_count=cats)
+    P = O.init_params(cfg, 1234)
+    feed = synth_feed(B, L, items, cats, users, 4321, ZipfSampler(items, 1.05))
+    eng = E.Engine(E.ModelConfig(kind="MTAM", max_batch=B, L=L, D=D, H=1, N=N, user_count=users, item_count=items,
+                                 category_count=cats, gemm_mode=_lib.GEMM_TF32))
+    eng.set_params(P)
+    fwd, grads, pieces = O.loss_and_grads(cfg, P, feed)
+    out = eng.forward(feed)
+    lo = float(fwd["loss"].detach())
+    assert abs(out["loss"] - lo) <= 1e-2 * abs(lo)
+    g = eng.gradients(feed)
+    worst = ("", 0.0)
+    for k, v in grads.items():
+        if v is None:
+            continue
+        r = rel(g[k], v)
+        if r > worst[1]:
+            worst = (k, r)
+        assert r < 2e-2, (k, r)
+    print(f"\n[tf32 single pass cfg3] loss rel {abs(out['loss'] - lo) / abs(lo):.2e}, worst gradient {worst[0]} rel {worst[1]:.2e}")
+    tr = O.OracleTrainer(cfg, P)
+    for s in range(2):
+        lo, lc = tr.train_step(feed, 1e-3), eng.train_step(feed, 1e-3)
+        assert abs(lo - lc) <= 1e-2 * abs(lo), (s, lo, lc)
+    idx, _ = eng.eval_topk_device(eng.upload(feed), 50)
+    _, oidx, _ = O.metrics_topk(cfg, {k: v for k, v in tr.params.items()}, feed)
+    overlap = np.mean([len(set(a) & set(b)) / 50.0 for a, b in zip(idx.cpu().numpy(), oidx)])
+    assert overlap >= 0.99, overlap

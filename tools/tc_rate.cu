@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(128) rate_kernel(int iters, long long* out) {
   fence_proxy_async();
   tc_fence_before(); __syncthreads(); tc_fence_after();
   const uint32_t tm = slot;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32 && elect_one()) {     // converged warp + elect.sync: no per-MMA election loop (tc_common.cuh)
     const uint32_t a = smem_u32(sm), b = smem_u32(sm + 128 * 32);
     constexpr uint32_t id = idesc_tf32(128, N, 0, 0);
     long long t0 = clock64();
