@@ -84,6 +84,7 @@ class base_model(object):
         """base_model.py:274-287: writers under data/tensorboard_result/<type>_<experiment_type>_<version>_<time>/.
         FLAGS.summary_dir (not a reference flag) moves the root; an empty string keeps the scalars in memory only."""
         self.merged = None
+        self._pipe, self._pipe_lr = None, 0.0       # train_submit's input pipeline (engine.FeedPipeline)
         root = getattr(self.FLAGS, "summary_dir", "data/tensorboard_result")
         if root:
             stamp = time.strftime("%Y-%m-%d--%H:%M:%S", time.localtime(time.time()))
@@ -158,6 +159,34 @@ class base_model(object):
         self.merged = tb.scalars((("Training Loss", sc[_lib.S_LOSS_ORIGIN]), ("normalized Training Loss", sc[_lib.S_LOSS]),
                                   ("l2_norm", sc[_lib.S_L2_NORM]), ("Learning_rate", float(learning_rate))))
         return np.float32(loss), self.merged
+
+    def _merged(self, sc, learning_rate):
+        return tb.scalars((("Training Loss", sc[_lib.S_LOSS_ORIGIN]), ("normalized Training Loss", sc[_lib.S_LOSS]),
+                           ("l2_norm", sc[_lib.S_L2_NORM]), ("Learning_rate", float(learning_rate))))
+
+    def train_submit(self, batch_data, learning_rate):
+        """Pipelined `train` (engine.FeedPipeline): queues this step and returns `(loss, merged)` of the step submitted
+        BEFORE it -- None for the first -- so the host's padding / copy of the next batch overlaps the device's step.
+        The driver loop (train_process.py) uses it; `train` stays the blocking call of the reference
+        (base_model.py:150-167).  Call `train_flush()` before evaluating, saving or reading weights."""
+        if self._pipe is None:
+            from ..engine import FeedPipeline
+            self._pipe = FeedPipeline(self.engine)
+        feed = batch_data if hasattr(batch_data, "pack_into") else self._feed(batch_data)
+        sc = self._pipe.submit(feed, learning_rate)
+        prev_lr, self._pipe_lr = self._pipe_lr, learning_rate
+        if sc is None:
+            return None
+        return np.float32(sc[_lib.S_LOSS]), self._merged(sc, prev_lr)
+
+    def train_flush(self):
+        """`(loss, merged)` of the last step queued by `train_submit`, None if there is none."""
+        if self._pipe is None:
+            return None
+        sc = self._pipe.flush()
+        if sc is None:
+            return None
+        return np.float32(sc[_lib.S_LOSS]), self._merged(sc, self._pipe_lr)
 
     def metrics_topK(self, sess, batch_data, global_step, topk):
         if hasattr(batch_data, "pack_into"):

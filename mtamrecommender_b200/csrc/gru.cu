@@ -189,15 +189,31 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
   float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // kw1,kb1,hw1,tw1,tb1,kw2,tw12,tb12
   float dh[2] = {0.f, 0.f};
 
+  // (as in the forward kernel: both rows of a thread are computed together and branch-free -- a row that has ended
+  // sees zeros everywhere, so only the stores are predicated --, the dot products run 8 independent accumulators, and
+  // the rows' step counts, base pointers and d loss / d q0 live in registers)
+  int st[2];
+  float dq[2];
+  float* dgx[2];
+  float* dxp[2];
+  int64_t tok0[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = rg * 2 + i;
+    st[i] = steps[row];
+    tok0[i] = (int64_t)(b0 + row) * L;
+    dq[i] = (b0 + row < B) ? __ldg(dq0 + (int64_t)(b0 + row) * D + n) : 0.f;
+    dgx[i] = dGX + tok0[i] * (3 * D) + n;
+    dxp[i] = dX + tok0[i] * D + n;
+  }
   // the step's saved activations are independent of the recurrence: the loads of step t-1 are issued at the top of
   // step t and land while its two matrix-vector loops run
   struct StepIn { float r, u, c, Tg, hold, x, dl, dx, dout; };
   auto fetch = [&](int t, StepIn (&v)[2]) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const int row = rg * 2 + i;
-      const bool live = t >= 0 && t < steps[row];
-      const int64_t tok = (int64_t)(b0 + row) * L + (live ? t : 0);
+      const bool live = t >= 0 && t < st[i];
+      const int64_t tok = tok0[i] + (live ? t : 0);
       const float* s4 = RUCT + tok * (4 * D);
       v[i].r = ld_nc_pred(s4 + n, live); v[i].u = ld_nc_pred(s4 + D + n, live);
       v[i].c = ld_nc_pred(s4 + 2 * D + n, live); v[i].Tg = ld_nc_pred(s4 + 3 * D + n, live);
@@ -224,87 +240,88 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
   StepIn cur[2], nxt[2];
   fetch(tmax - 1, cur);
   for (int t = tmax - 1; t >= 0; --t) {
-    float dhacc[2], rr[2], hh[2];
+    float dhacc[2], rr[2], hh[2], dpc[2], dupre[2];
     fetch(t - 1, nxt);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      int row = rg * 2 + i;
-      dhacc[i] = 0.f; rr[i] = 0.f; hh[i] = 0.f;
-      if (t < steps[row]) {
-        int64_t b = b0 + row;
-        int64_t tok = b * L + t;
-        if (t == steps[row] - 1) dh[i] += __ldg(dq0 + b * D + n);
-        dh[i] += cur[i].dout;
-        const float r = cur[i].r, u = cur[i].u, c = cur[i].c, Tg = cur[i].Tg, hold = cur[i].hold, x = cur[i].x,
-                    dl = cur[i].dl;
-        float d = dh[i];
-        float du = d * (hold - c * Tg), dc = d * (1.f - u) * Tg, dT = d * (1.f - u) * c;
-        dhacc[i] = d * u;
-        float dpc = dc * (1.f - c * c);
-        dpcS[n * RB + row] = dpc;
-        dGX[tok * (3 * D) + 2 * D + n] = dpc;
-        float dpT = dT * Tg * (1.f - Tg);
-        float apre = fmaf(x, kw1, kb1) + hold * hw1, spre = fmaf(tw1, dl, tb1);
-        float a = fmaxf(apre, 0.f), s = fmaxf(spre, 0.f);
-        float dpa = (apre > 0.f) ? dpT * kw2 : 0.f;
-        float dps = (spre > 0.f) ? dpT * tw12 : 0.f;
-        dX[tok * D + n] = fmaf(dpa, kw1, cur[i].dx);   // each element is read (a step earlier) and written exactly once
-        dhacc[i] = fmaf(dpa, hw1, dhacc[i]);
-        g[0] = fmaf(dpa, x, g[0]); g[1] += dpa; g[2] = fmaf(dpa, hold, g[2]);
-        g[3] = fmaf(dps, dl, g[3]); g[4] += dps;
-        g[5] = fmaf(dpT, a, g[5]); g[6] = fmaf(dpT, s, g[6]); g[7] += dpT;
-        float dupre = du * u * (1.f - u);
-        dpgS[(D + n) * RB + row] = dupre;
-        dGX[tok * (3 * D) + D + n] = dupre;
-        rr[i] = r; hh[i] = hold;
-      } else {
-        dpcS[n * RB + row] = 0.f;
-        dpgS[(D + n) * RB + row] = 0.f;
+      const bool live = t < st[i];
+      const float r = cur[i].r, u = cur[i].u, c = cur[i].c, Tg = cur[i].Tg, hold = cur[i].hold, x = cur[i].x,
+                  dl = cur[i].dl;
+      // a row that has not started yet (t >= its step count): dh is still 0 and every saved value was loaded as 0
+      const float d = dh[i] + ((t == st[i] - 1) ? dq[i] : 0.f) + cur[i].dout;
+      const float du = d * (hold - c * Tg), dc = d * (1.f - u) * Tg, dT = d * (1.f - u) * c;
+      dhacc[i] = d * u;
+      dpc[i] = dc * (1.f - c * c);
+      const float dpT = dT * Tg * (1.f - Tg);
+      const float apre = fmaf(x, kw1, kb1) + hold * hw1, spre = fmaf(tw1, dl, tb1);
+      const float a = fmaxf(apre, 0.f), s = fmaxf(spre, 0.f);
+      const float dpa = (apre > 0.f) ? dpT * kw2 : 0.f;
+      const float dps = (spre > 0.f) ? dpT * tw12 : 0.f;
+      dhacc[i] = fmaf(dpa, hw1, dhacc[i]);
+      g[0] = fmaf(dpa, x, g[0]); g[1] += dpa; g[2] = fmaf(dpa, hold, g[2]);
+      g[3] = fmaf(dps, dl, g[3]); g[4] += dps;
+      g[5] = fmaf(dpT, a, g[5]); g[6] = fmaf(dpT, s, g[6]); g[7] += dpT;
+      dupre[i] = du * u * (1.f - u);
+      rr[i] = r; hh[i] = hold;
+      if (live) {
+        dgx[i][t * (3 * D) + 2 * D] = dpc[i];
+        dxp[i][t * D] = fmaf(dpa, kw1, cur[i].dx);   // each element is read (a step earlier) and written exactly once
+        dgx[i][t * (3 * D) + D] = dupre[i];
       }
     }
+    *reinterpret_cast<float2*>(&dpcS[n * RB + rg * 2]) = make_float2(dpc[0], dpc[1]);
+    *reinterpret_cast<float2*>(&dpgS[(D + n) * RB + rg * 2]) = make_float2(dupre[0], dupre[1]);
     __syncthreads();
     // d(r*h)[n] = sum_m dpc[m] * Wc_h[n][m]
-    float acc[2] = {0.f, 0.f};
-#pragma unroll REGW ? D : 8
-    for (int m = 0; m < D; ++m) {
-      const float w = REGW ? wc[REGW ? m : 0] : WhT[(2 * D + m) * D + n];
-      float2 d2 = *reinterpret_cast<const float2*>(&dpcS[m * RB + rg * 2]);
-      acc[0] = fmaf(d2.x, w, acc[0]);
-      acc[1] = fmaf(d2.y, w, acc[1]);
-    }
+    float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll REGW ? D / 4 : 2
+    for (int m = 0; m < D; m += 4) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      int row = rg * 2 + i;
-      float drpre = 0.f;
-      if (t < steps[row]) {
-        float drh = acc[i];
-        dhacc[i] = fmaf(drh, rr[i], dhacc[i]);
-        drpre = drh * hh[i] * rr[i] * (1.f - rr[i]);
-        dGX[((int64_t)(b0 + row) * L + t) * (3 * D) + n] = drpre;
+      for (int j = 0; j < 4; ++j) {
+        const float w = REGW ? wc[REGW ? m + j : 0] : WhT[(2 * D + m + j) * D + n];
+        const float2 d2 = *reinterpret_cast<const float2*>(&dpcS[(m + j) * RB + rg * 2]);
+        acc[j][0] = fmaf(d2.x, w, acc[j][0]);
+        acc[j][1] = fmaf(d2.y, w, acc[j][1]);
       }
-      dpgS[n * RB + row] = drpre;
+    }
+    {
+      float drpre[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float drh = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
+        dhacc[i] = fmaf(drh, rr[i], dhacc[i]);
+        drpre[i] = drh * hh[i] * rr[i] * (1.f - rr[i]);          // 0 for a row that has not started (r = h = 0)
+        if (t < st[i]) dgx[i][t * (3 * D)] = drpre[i];
+      }
+      *reinterpret_cast<float2*>(&dpgS[n * RB + rg * 2]) = make_float2(drpre[0], drpre[1]);
     }
     __syncthreads();
     // dh_prev[n] += sum_m dpg[m] * Wg_h[n][m],  m over 2D
-    float acc2[2] = {0.f, 0.f};
+    float acc2[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     if (REGW) {
 #pragma unroll
-      for (int m = 0; m < RW; ++m) {
-        const float2 d2 = *reinterpret_cast<const float2*>(&dpgS[m * RB + rg * 2]);
-        acc2[0] = fmaf(d2.x, wg[m], acc2[0]);
-        acc2[1] = fmaf(d2.y, wg[m], acc2[1]);
+      for (int m = 0; m < RW; m += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 d2 = *reinterpret_cast<const float2*>(&dpgS[(m + j) * RB + rg * 2]);
+          acc2[j][0] = fmaf(d2.x, wg[REGW ? m + j : 0], acc2[j][0]);
+          acc2[j][1] = fmaf(d2.y, wg[REGW ? m + j : 0], acc2[j][1]);
+        }
       }
     }
-#pragma unroll 8
-    for (int m = REGW ? D : 0; m < 2 * D; ++m) {
-      float w = WhT[m * D + n];
-      float2 d2 = *reinterpret_cast<const float2*>(&dpgS[m * RB + rg * 2]);
-      acc2[0] = fmaf(d2.x, w, acc2[0]);
-      acc2[1] = fmaf(d2.y, w, acc2[1]);
+#pragma unroll 2
+    for (int m = REGW ? D : 0; m < 2 * D; m += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w = WhT[(m + j) * D + n];
+        const float2 d2 = *reinterpret_cast<const float2*>(&dpgS[(m + j) * RB + rg * 2]);
+        acc2[j][0] = fmaf(d2.x, w, acc2[j][0]);
+        acc2[j][1] = fmaf(d2.y, w, acc2[j][1]);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      if (t < steps[rg * 2 + i]) dh[i] = dhacc[i] + acc2[i];
+      if (t < st[i]) dh[i] = dhacc[i] + ((acc2[0][i] + acc2[1][i]) + (acc2[2][i] + acc2[3][i]));
       cur[i] = nxt[i];
     }
     __syncthreads();

@@ -425,6 +425,102 @@ class Engine:
         return out
 
 
+class FeedPipeline:
+    """Double-buffered input pipeline for training (pinned memory, async H2D, CUDA-graphed step).
+
+    `submit(feed, lr)` pads / packs the batch into a free pinned buffer, starts its host->device copy on a copy stream,
+    queues the step behind it (one device-to-device copy refreshes the fixed staging buffers the step -- eager or
+    captured graph -- reads) and the device->host copy of its scalars, and only THEN waits for the PREVIOUS step, whose
+    scalars it returns: the host's share of step i+1 (id validation, padding, the copy's submission) runs while the
+    device computes step i, and the device always has the next step queued.  `flush()` returns the scalars of the last
+    submitted step.  Same arithmetic, same order of steps as calling `Engine.train_step` in a loop (tested).
+    `step_fn(lr)` runs one step on the engine's staging batch (default: the engine's own graph or eager step; a
+    DataParallel driver passes its own)."""
+
+    def __init__(self, eng: "Engine", step_fn=None):
+        self.eng = eng
+        dev = eng.device
+        n = eng._pinned_all.numel()
+        self._pin = [torch.zeros(n, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._stage = [torch.zeros(n, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self._np = []
+        for b in self._pin:             # the same 11 views as Engine._pinned_np, over this slot's buffer
+            views = {}
+            for k in FEED_KEYS:
+                ref = eng._pinned[k]
+                off = ref.data_ptr() - eng._pinned_all.data_ptr()
+                views[k] = b[off: off + ref.numel() * 4].view(ref.dtype).view(ref.shape).numpy()
+            self._np.append(views)
+        self._scal = [torch.zeros(_lib.S_COUNT, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._copy = torch.cuda.Stream(dev)
+        self._h2d = [torch.cuda.Event() for _ in range(2)]        # slot's H2D copy done
+        self._used = [torch.cuda.Event() for _ in range(2)]       # slot's device staging buffer consumed by its step
+        self._done = [torch.cuda.Event() for _ in range(2)]       # slot's step finished, scalars on the host
+        self._n = 0
+        self._B = [0, 0]
+        self._step_fn = step_fn
+
+    def _run(self, B: int, lr: float) -> None:
+        eng = self.eng
+        if self._step_fn is not None:
+            self._step_fn(B, lr)
+        elif eng._graph is not None and B == eng._graph_B:
+            eng.train_step_graph(lr)
+        else:
+            eng.train_step_device(DeviceBatch({k: v[:B] for k, v in eng._dev.items()}, B), lr)
+
+    def submit(self, feed, lr: float) -> Optional[np.ndarray]:
+        """feed: the mapping of 11 arrays (make_feed_dic_new) or a PackedRecords view.  Returns the scalars
+        (mtam_scalar order) of the step submitted before this one, None for the first."""
+        eng = self.eng
+        slot = self._n & 1
+        records = hasattr(feed, "pack_into")
+        B = len(feed) if records else int(len(feed["user_id"]))
+        if B < 1 or B > eng.cfg.max_batch:
+            raise ValueError(f"batch size {B} outside [1, {eng.cfg.max_batch}]")
+        if self._n >= 2:
+            self._h2d[slot].synchronize()            # the pinned buffer's previous copy (two steps ago) has left it
+        if records:
+            feed.pack_into(self._np[slot], eng.cfg.L)
+        else:
+            eng._validate_ids(feed, B)
+            for k in FEED_KEYS:
+                np.copyto(self._np[slot][k][:B], feed[k], casting="same_kind")
+        main = torch.cuda.current_stream(eng.device)
+        with torch.cuda.stream(self._copy):
+            if self._n >= 2:
+                self._copy.wait_event(self._used[slot])            # the step two back has read this staging buffer
+            self._stage[slot].copy_(self._pin[slot], non_blocking=True)
+            self._h2d[slot].record(self._copy)
+        main.wait_event(self._h2d[slot])
+        eng._dev_all.copy_(self._stage[slot], non_blocking=True)
+        self._used[slot].record(main)
+        self._run(B, lr)
+        self._scal[slot].copy_(eng.scalars, non_blocking=True)
+        self._done[slot].record(main)
+        self._B[slot] = B
+        self._n += 1
+        eng._h2d_done = self._h2d[slot]       # (a later Engine.upload must not capture its graph on unset lengths)
+        if self._n == 1:
+            return None
+        return self._collect(1 - slot)
+
+    def _collect(self, slot: int) -> np.ndarray:
+        self._done[slot].synchronize()
+        out = self._scal[slot].numpy().copy()
+        self.eng.last_scalars = out
+        return out
+
+    def flush(self) -> Optional[np.ndarray]:
+        """Scalars of the last submitted step (None if nothing was submitted since the last flush)."""
+        if self._n == 0:
+            return None
+        out = self._collect((self._n - 1) & 1)
+        torch.cuda.current_stream(self.eng.device).synchronize()
+        self._n = 0
+        return out
+
+
 def dropout_keep_mask(seed: int, counter: int, block: int, B: int, H: int, L: int, rate: float) -> np.ndarray:
     """Host restatement of csrc/selfattn.cu sa_keep(): the multiplicative attention-dropout mask [B,H,L,L]
     (keep / (1 - rate), else 0) of block `block` in forward call `counter`.  Test / inspection helper."""

@@ -176,6 +176,17 @@ class DataParallel:
             self.train_step_device(batch, lr)
         return float(self.eng.read_scalars()[_lib.S_LOSS])
 
+    def pipeline(self):
+        """engine.FeedPipeline over the data-parallel step: the next batch is padded and copied while this one runs."""
+        from .engine import FeedPipeline
+
+        def step(B: int, lr: float) -> None:
+            if self._graph is not None and B == self._graph_B:
+                self.train_step_graph(lr)
+            else:
+                self.train_step_device(DeviceBatch({k: v[:B] for k, v in self.eng._dev.items()}, B), lr)
+        return FeedPipeline(self.eng, step_fn=step)
+
     # ---- the whole data-parallel step, collectives included, as one CUDA graph --------------------------------------
     def capture_graph(self, B: int, warmup: int = 2) -> None:
         """Captures `train_step_device` on the engine's staging batch (fixed addresses), NCCL collectives included, into

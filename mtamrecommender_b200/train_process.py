@@ -142,16 +142,35 @@ class Train_main_process:
             self.logger.info("tain_set:%d" % len(self.train_set))
             epoch_start_time = time.time()
             learning_rate = F.learning_rate
+            # The step is queued (model.train_submit: padding, the host->device copy and the launch of step i+1 overlap
+            # the device's step i) and its loss is booked one iteration later; the pipeline is drained wherever the
+            # reference looks at the model (evaluation, saving, the end of an epoch).  FLAGS.pipeline_input = False
+            # gives the reference's blocking model.train call per step.
+            pipelined = bool(getattr(F, "pipeline_input", True)) and hasattr(self.model, "train_submit")
+            pending = []                              # global steps whose results have not been booked yet
+
+            def book(res):
+                nonlocal avg_loss, step_loss
+                if res is None:
+                    return
+                step_loss, merge = res
+                self.model.train_writer.add_summary(merge, pending.pop(0))
+                avg_loss += float(step_loss)
+
             for _, train_batch_data in DataInput(data, F.train_batch_size):
                 learning_rate = lr_schedule(learning_rate, self.global_step, F.learning_rate, F.decay_rate)
                 self.learning_rates.append(learning_rate)
                 add_summary = bool(self.global_step % F.display_freq == 0)
-                step_loss, merge = self.model.train(self.sess, train_batch_data, learning_rate, add_summary,
-                                                    self.global_step, epoch)
-                self.model.train_writer.add_summary(merge, self.global_step)
-                avg_loss += float(step_loss)
+                pending.append(self.global_step)
+                if pipelined:
+                    book(self.model.train_submit(train_batch_data, learning_rate))
+                else:
+                    book(self.model.train(self.sess, train_batch_data, learning_rate, add_summary, self.global_step, epoch))
                 self.global_step += 1
                 self.one_epoch_step += 1
+                last = max_steps is not None and self.global_step >= max_steps
+                if pipelined and (self.global_step % F.eval_freq == 0 or last):
+                    book(self.model.train_flush())
                 if self.global_step % F.eval_freq == 0:
                     self.logger.info("Epoch step is " + str(self.one_epoch_step))
                     self.logger.info("Global step is " + str(self.global_step))
@@ -162,6 +181,8 @@ class Train_main_process:
                 if max_steps is not None and self.global_step >= max_steps:
                     done = True
                     break
+            if pipelined:
+                book(self.model.train_flush())
             self.logger.info("one epoch Cost time: %.2f" % (time.time() - epoch_start_time))
             self.logger.info("Global step is " + str(self.global_step))
             self.logger.info("Train_loss is " + str(step_loss))

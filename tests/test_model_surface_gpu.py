@@ -101,3 +101,63 @@ def test_train_process_driver_schedule_summaries_and_checkpoint(tmp_path):
         _model(_flags(load_type="sideways"), users, items, cats)
     with pytest.raises(NotImplementedError):
         _model(_flags(optimizer="rmsprop"), users, items, cats)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_pipelined_training_equals_the_blocking_calls(graph):
+    """engine.FeedPipeline / model.train_submit (the input pipeline of SURVEY 8f row 1: padding and the host->device
+    copy of step i+1 overlap step i, the loss comes back one call later): the same losses, in the same order, and
+    bit-identical weights as model.train called step by step -- from 9-tuples, from the record store, with ragged
+    batch sizes (eager steps) and with the captured CUDA graph; and Train_main_process gives the same result with
+    FLAGS.pipeline_input on and off."""
+    from oracle import mtam_oracle as O
+    from mtamrecommender_b200.DataHandle.get_input_data import DataInput
+    from mtamrecommender_b200.DataHandle.record_store import PackedRecords
+    from mtamrecommender_b200.train_process import Train_main_process
+    users, items, cats = 30, 400, 7
+    F = _flags()
+    cfg = O.OracleConfig(kind=O.MTAM, L=12, D=64, H=1, N=2, user_count=users, item_count=items, category_count=cats)
+    recs = O.synth_records(cfg, 16 * 7 + (0 if graph else 5), 11)
+    rs = PackedRecords.from_records(recs)
+    m1, s1 = _model(F, users, items, cats)
+    m2, _ = _model(F, users, items, cats)
+    m3, _ = _model(F, users, items, cats)
+    P = m1.engine.get_params()
+    m2.engine.set_params(P)
+    m3.engine.set_params(P)
+    if graph:
+        for m in (m1, m2, m3):
+            m.engine.capture_train_graph(16)
+    want, got2, got3 = [], [], []
+    for i, b in DataInput(recs, 16):
+        want.append(float(m1.train(s1, b, 1e-3 * (1 + i))[0]))
+    for n, ((i, b2), (_, b3)) in enumerate(zip(DataInput(recs, 16), DataInput(rs, 16))):
+        for m, b, got in ((m2, b2, got2), (m3, b3, got3)):
+            r = m.train_submit(b, 1e-3 * (1 + i))
+            assert (r is None) == (n == 0)
+            if r is not None:
+                got.append(float(r[0]))
+    got2.append(float(m2.train_flush()[0]))
+    got3.append(float(m3.train_flush()[0]))
+    assert m2.train_flush() is None
+    assert want == got2 == got3
+    assert bool((m1.engine.params == m2.engine.params).all()) and bool((m1.engine.params == m3.engine.params).all())
+    assert bool((m1.engine.adam_m == m2.engine.adam_m).all())
+    # a second round after the flush (the pipeline starts over), then the blocking call again: still in step
+    for m in (m2, m3):
+        assert m.train_submit(recs[:16], 2e-3) is None
+        m.train_flush()
+    m1.train(s1, recs[:16], 2e-3)
+    assert float(m1.train(s1, recs[16:32], 1e-3)[0]) == float(m2.train(None, recs[16:32], 1e-3)[0])
+    if graph:
+        return
+    res = []
+    for pipelined in (True, False):
+        Fd = _flags(max_epochs=2, eval_freq=3, learning_rate=0.002, decay_rate=0.5, pipeline_input=pipelined)
+        drv = Train_main_process(FLAGS=Fd, train_set=recs[:70], test_set=recs[70:90], user_count=users, item_count=items,
+                                 category_count=cats)
+        last = drv.train()
+        ev = [(s, t, v) for s, t, v in drv.model.train_writer.events if t == "normalized Training Loss"]
+        res.append((float(last), drv.global_step, ev, drv.model.engine.params.clone()))
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1] == 10 and res[0][2] == res[1][2] and len(res[0][2]) == 10
+    assert bool((res[0][3] == res[1][3]).all())
