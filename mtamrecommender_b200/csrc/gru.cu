@@ -20,6 +20,17 @@ namespace mtam {
 
 constexpr int RB = 8;  // batch rows per CTA
 
+// developer timeline (tools/gru_trace.cu builds this file with -DMTAM_GRU_TRACE): clock64 of the phases of step 10, CTA 0
+#ifdef MTAM_GRU_TRACE
+__device__ long long g_gru_trace[32];
+#define GRU_TRACE(slot, t)                                                                       \
+  do {                                                                                           \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (t) == 10) g_gru_trace[slot] = clock64();         \
+  } while (0)
+#else
+#define GRU_TRACE(slot, t) ((void)0)
+#endif
+
 // vecs layout [8][D]: kw1, kb1, hw1, tw1, tb1, kw2, tw12, tb12   (GRU_LIVE_VECS order)
 template <int D>
 __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict__ X, const float* __restrict__ GX,
@@ -153,6 +164,197 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_kernel(const float* __restrict_
   for (int i = 0; i < 2; ++i) {
     int row = rg2 * 2 + i;
     if (b0 + row < B) q0[(int64_t)(b0 + row) * D + n2] = hT[n2 * RB + row];
+  }
+}
+
+// =============================================================================================
+// Forward recurrence with the h-side products on the tensor cores (mma.sync m16n8k8, 3xTF32), for the tensor-core
+// arithmetic modes at num_units 32 / 64.
+//
+// The FFMA kernel above is bound by shared-memory RETURN bandwidth, not by latency or FMA issue: every thread pulls
+// the whole state through broadcast loads (4*D threads x D x 16 B = 262 KB for the gates + 131 KB for the candidate per
+// step per CTA, against 128 B/clk: ~3000 of a step's ~4400 cycles; splitting each column over two threads left the time
+// unchanged for that reason).  Operand fragments do not have that problem: per step the gates are the product
+//     [r|u]^T [2D x RB] = Wg_h^T [2D x D]  x  h^T [D x RB]          (M = 2D gate columns, N = RB = 8 batch rows, K = D)
+// so the constant weights are the A operand and live in registers as fragments for all L steps (hi and lo of the 3xTF32
+// split: 64 registers per 16-column tile), the state is the B operand (two conflict-free 4-byte loads per lane per
+// k-step, split on the fly), and a warp owns one 16-column tile: D/8 k-steps x 3 MMAs in three independent
+// accumulator chains.  The candidate is the same product with r*h as the B operand (the first D/16 warps).
+// The C fragment leaves each thread with 2 columns x 2 rows, on which it applies the gates.
+// =============================================================================================
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tf32_top(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+// The gates of the tensor-core kernel.  After the products moved to mma.sync, two thirds of a step's ~900 instructions
+// per thread were the twelve transcendental calls (expf + IEEE division: ~40 instructions each, one dependent chain per
+// warp).  MUFU-based forms: ex2.approx on x * log2(e) and an approximate reciprocal, ~1e-6 relative -- the accuracy
+// class of the 3xTF32 products beside them (the exact-fp32 mode keeps expf / tanhf and true division).
+__device__ __forceinline__ float sigmoid_mufu(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_mufu(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+template <int D>
+__global__ void __launch_bounds__(4 * D) gru_fwd_mma_kernel(const float* __restrict__ X, const float* __restrict__ GX,
+                                                            const float* __restrict__ timelast,
+                                                            const int32_t* __restrict__ seq_len,
+                                                            const float* __restrict__ Wgru, const float* __restrict__ vecs,
+                                                            int B, int L, float* __restrict__ Hs, float* __restrict__ RUCT,
+                                                            float* __restrict__ RH, float* __restrict__ q0, int plain) {
+  static_assert(RB == 8, "the batch rows of a CTA are the N = 8 of the MMA");
+  constexpr int NT = 4 * D, KS = D / 8, W2 = D / 16;      // threads (2D/16 warps); k-steps; warps that own a candidate tile
+  __shared__ __align__(16) float hT[D * RB], rhT[D * RB], uS[D * RB];   // [k][row]
+  __shared__ int steps[RB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const int b0 = blockIdx.x * RB;
+  for (int i = tid; i < D * RB; i += NT) hT[i] = 0.f;
+  if (tid < RB) steps[tid] = (b0 + tid < B) ? min(max(seq_len[b0 + tid] - 1, 0), L) : 0;
+  __syncthreads();
+  int tmax = 0;
+#pragma unroll
+  for (int r = 0; r < RB; ++r) tmax = max(tmax, steps[r]);
+  // this thread's outputs: columns cA, cA + 8 of [r|u] (and of c for the first W2 warps) x rows r0, r0 + 1
+  const int cA = 16 * warp + gid, r0 = 2 * tig;
+  const bool cand = warp < W2;                              // warp-uniform
+  const int st0 = steps[r0], st1 = steps[r0 + 1];
+  const int64_t tk0 = (int64_t)(b0 + r0) * L, tk1 = tk0 + L;
+  // A fragments: A[m][k] = W_gru[D + k][col0 + m]  (a0: m = gid, k = tig; a1: m = gid + 8; a2: k = tig + 4; a3: both)
+  const float* Wh = Wgru + (int64_t)D * 3 * D;
+  uint32_t ah[KS][4], al[KS][4], ch[KS][4], cl[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = ks * 8 + tig + (j >> 1) * 4, m = (j & 1) * 8;
+      const float x = __ldg(Wh + (int64_t)k * 3 * D + cA + m);
+      ah[ks][j] = tf32_top(x);
+      al[ks][j] = __float_as_uint(x - __uint_as_float(ah[ks][j]));
+      const float y = cand ? __ldg(Wh + (int64_t)k * 3 * D + 2 * D + cA + m) : 0.f;
+      ch[ks][j] = tf32_top(y);
+      cl[ks][j] = __float_as_uint(y - __uint_as_float(ch[ks][j]));
+    }
+  }
+  float kw1[2], kb1[2], hw1[2], tw1[2], tb1[2], kw2[2], tw12[2], tb12[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = (cand ? cA : 0) + 8 * j;
+    kw1[j] = vecs[0 * D + c]; kb1[j] = vecs[1 * D + c]; hw1[j] = vecs[2 * D + c]; tw1[j] = vecs[3 * D + c];
+    tb1[j] = vecs[4 * D + c]; kw2[j] = vecs[5 * D + c]; tw12[j] = vecs[6 * D + c]; tb12[j] = vecs[7 * D + c];
+  }
+  // x-side inputs of a step do not depend on the recurrence: those of step t+1 are loaded during step t.
+  // index [j][i]: column cA + 8j, row r0 + i
+  struct StepIn { float g1[2][2], g2[2][2], xv[2][2], dl[2]; };
+  auto fetch = [&](int t, StepIn& v) {
+    const bool l0 = t < st0, l1 = t < st1;
+    const int64_t t0 = tk0 + (l0 ? t : 0), t1 = tk1 + (l1 ? t : 0);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      v.g1[j][0] = ld_nc_pred(GX + t0 * (3 * D) + cA + 8 * j, l0);
+      v.g1[j][1] = ld_nc_pred(GX + t1 * (3 * D) + cA + 8 * j, l1);
+    }
+    if (cand) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        v.g2[j][0] = ld_nc_pred(GX + t0 * (3 * D) + 2 * D + cA + 8 * j, l0);
+        v.g2[j][1] = ld_nc_pred(GX + t1 * (3 * D) + 2 * D + cA + 8 * j, l1);
+        v.xv[j][0] = ld_nc_pred(X + t0 * D + cA + 8 * j, l0);
+        v.xv[j][1] = ld_nc_pred(X + t1 * D + cA + 8 * j, l1);
+      }
+      v.dl[0] = ld_nc_pred(timelast + t0, l0);
+      v.dl[1] = ld_nc_pred(timelast + t1, l1);
+    }
+  };
+  // D^T tile += A (hi/lo fragments) x B^T, B = src[k][row] in shared memory; three independent accumulator chains
+  auto product = [&](const uint32_t (&fh)[KS][4], const uint32_t (&fl)[KS][4], const float* src, float (&out)[4]) {
+    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float x0 = src[(ks * 8 + tig) * RB + gid], x1 = src[(ks * 8 + tig + 4) * RB + gid];
+      const uint32_t h0 = tf32_top(x0), h1 = tf32_top(x1);
+      const uint32_t l0 = __float_as_uint(x0 - __uint_as_float(h0)), l1 = __float_as_uint(x1 - __uint_as_float(h1));
+      mma_tf32_16x8x8(d0, fl[ks], h0, h1);
+      mma_tf32_16x8x8(d1, fh[ks], l0, l1);
+      mma_tf32_16x8x8(d2, fh[ks], h0, h1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = (d0[i] + d1[i]) + d2[i];      // small terms first
+  };
+  StepIn cur, nxt;
+  fetch(0, cur);
+  for (int t = 0; t < tmax; ++t) {
+    GRU_TRACE(0, t);
+    fetch(t + 1, nxt);          // rows whose sequence has ended (and t + 1 == tmax) load nothing
+    GRU_TRACE(1, t);
+    const bool l0 = t < st0, l1 = t < st1;
+    // ---- phase 1: r,u ----   acc: [0] (cA, r0), [1] (cA, r0+1), [2] (cA+8, r0), [3] (cA+8, r0+1)
+    float acc[4];
+    product(ah, al, hT, acc);
+    GRU_TRACE(2, t);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int col = cA + 8 * j;
+      const float va = sigmoid_mufu(acc[2 * j] + cur.g1[j][0]), vb = sigmoid_mufu(acc[2 * j + 1] + cur.g1[j][1]);
+      // rows that have ended leave rh / u entries nobody reads (phase 2 discards those rows)
+      if (col < D) {                          // warp-uniform (a tile lies on one side of D)
+        const float2 h2 = *reinterpret_cast<const float2*>(&hT[col * RB + r0]);
+        const float2 rh = make_float2(va * h2.x, vb * h2.y);
+        *reinterpret_cast<float2*>(&rhT[col * RB + r0]) = rh;
+        if (l0) RH[(tk0 + t) * D + col] = rh.x;
+        if (l1) RH[(tk1 + t) * D + col] = rh.y;
+      } else {
+        *reinterpret_cast<float2*>(&uS[(col - D) * RB + r0]) = make_float2(va, vb);
+      }
+      if (l0) RUCT[(tk0 + t) * (4 * D) + col] = va;      // r at [0,D), u at [D,2D)
+      if (l1) RUCT[(tk1 + t) * (4 * D) + col] = vb;
+    }
+    GRU_TRACE(3, t);
+    __syncthreads();
+    GRU_TRACE(4, t);
+    // ---- phase 2: candidate, time gate, state update (the warps that own a candidate tile) ----
+    if (cand) {
+      float acc2[4];
+      product(ch, cl, rhT, acc2);
+      GRU_TRACE(5, t);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = cA + 8 * j;
+        const float2 hold2 = *reinterpret_cast<const float2*>(&hT[col * RB + r0]);
+        const float2 u2 = *reinterpret_cast<const float2*>(&uS[col * RB + r0]);
+        const float hold[2] = {hold2.x, hold2.y}, u[2] = {u2.x, u2.y};
+        float hn[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const bool live = i ? l1 : l0;
+          const float c = tanh_mufu(acc2[2 * j + i] + cur.g2[j][i]);
+          const float a = fmaxf(fmaf(cur.xv[j][i], kw1[j], kb1[j]) + hold[i] * hw1[j], 0.f);
+          const float sg = fmaxf(fmaf(tw1[j], cur.dl[i], tb1[j]), 0.f);
+          // plain: tf GRUCell (GRU.gru_net, gru.py:60-67) -- no time gate (T = 1: every gradient of its parameters is 0)
+          const float Tg = plain ? 1.f : sigmoid_mufu(kw2[j] * a + tw12[j] * sg + tb12[j]);
+          hn[i] = live ? u[i] * hold[i] + (1.f - u[i]) * c * Tg : hold[i];
+          if (live) {
+            const int64_t tok = (i ? tk1 : tk0) + t;
+            float* s4 = RUCT + tok * (4 * D) + 2 * D + col;
+            s4[0] = c;
+            s4[D] = Tg;
+            Hs[(tok + 1) * D + col] = hn[i];      // Hs has one leading zero row
+          }
+        }
+        *reinterpret_cast<float2*>(&hT[col * RB + r0]) = make_float2(hn[0], hn[1]);   // only this thread's elements
+      }
+    }
+    GRU_TRACE(6, t);
+    cur = nxt;
+    GRU_TRACE(7, t);
+    __syncthreads();
+    GRU_TRACE(8, t);
+  }
+  if (cand) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (b0 + r0 + i < B) q0[(int64_t)(b0 + r0 + i) * D + cA + 8 * j] = hT[(cA + 8 * j) * RB + r0 + i];
   }
 }
 
@@ -370,7 +572,13 @@ static int gru_bwd_launch(const float* X, const float* timelast, const int32_t* 
 
 int gru_forward(int D, const float* X, const float* GX, const float* timelast, const int32_t* seq_len,
                 const float* Wgru, const float* vecs, int B, int L, float* Hs, float* RUCT, float* RH, float* q0,
-                cudaStream_t st, int plain) {
+                cudaStream_t st, int plain, int tensor_cores) {
+  if (tensor_cores && (D == 64 || D == 32)) {      // h-side products on mma.sync (3xTF32); num_units 128: the FFMA kernel
+    if (D == 64) gru_fwd_mma_kernel<64><<<gru_num_blocks(B), 256, 0, st>>>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, plain);
+    else gru_fwd_mma_kernel<32><<<gru_num_blocks(B), 128, 0, st>>>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, plain);
+    MTAM_LAUNCH_CHECK();
+    return 0;
+  }
   switch (D) {
     case 32: return gru_fwd_launch<32>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, plain, st);
     case 64: return gru_fwd_launch<64>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, plain, st);

@@ -420,7 +420,7 @@ static int mtam_fwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.RH, 0, (size_t)T * D * sizeof(float), st));
   const bool via = memory_is_rnn(c.kind);
   MTAM_TRY(gru_forward(D, w.X, w.GX, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, B, L, w.Hs, w.RUCT,
-                       w.RH, via ? w.q0raw : w.Qin, st, plain_gru(c.kind) ? 1 : 0));
+                       w.RH, via ? w.q0raw : w.Qin, st, plain_gru(c.kind) ? 1 : 0, gemm_mode_is_tc(c.gemm_mode) ? 1 : 0));
   if (via)   // short_term_intent = layer_norm(gather(...))  (MTAMRec_model.py:182-187)
     MTAM_TRY(ln_rows_forward(w.q0raw, B, D, P + l.lnsg, P + l.lnsb, w.Qin, w.XHS, w.RSTDS, st));
   phase(h, MTAM_PH_KV_GEMM, st);

@@ -24,7 +24,7 @@ int zero_rows(float* dst, const int32_t* idx, int64_t n, int D, cudaStream_t st)
 int gru_num_blocks(int B);
 int gru_forward(int D, const float* X, const float* GX, const float* timelast, const int32_t* seq_len,
                 const float* Wgru, const float* vecs, int B, int L, float* Hs, float* RUCT, float* RH, float* q0,
-                cudaStream_t st, int plain = 0);
+                cudaStream_t st, int plain = 0, int tensor_cores = 0);
 int gru_backward(int D, const float* X, const float* timelast, const int32_t* seq_len, const float* Wgru,
                  const float* vecs, const float* Hs, const float* RUCT, const float* dq0, const float* dOut, int B, int L,
                  float* dGX, float* dX, float* vec_partial, cudaStream_t st);
