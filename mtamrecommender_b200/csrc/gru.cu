@@ -245,24 +245,33 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_mma_kernel(const float* __restr
   // x-side inputs of a step do not depend on the recurrence: those of step t+1 are loaded during step t.
   // index [j][i]: column cA + 8j, row r0 + i
   struct StepIn { float g1[2][2], g2[2][2], xv[2][2], dl[2]; };
+  // element offsets of this thread's (row, column cA) in the [token, .] arrays: a step adds t times the row length
+  // (32-bit: B * L * 4D < 2^31 is checked by the launcher)
+  uint32_t og0 = (uint32_t)tk0 * (3 * D) + cA, og1 = (uint32_t)tk1 * (3 * D) + cA;     // GX
+  uint32_t ox0 = (uint32_t)tk0 * D + cA, ox1 = (uint32_t)tk1 * D + cA;                 // X, RH, Hs
+  uint32_t or0 = (uint32_t)tk0 * (4 * D) + cA, or1 = (uint32_t)tk1 * (4 * D) + cA;     // RUCT
+  uint32_t ot0 = (uint32_t)tk0, ot1 = (uint32_t)tk1;                                   // timelast
   auto fetch = [&](int t, StepIn& v) {
     const bool l0 = t < st0, l1 = t < st1;
-    const int64_t t0 = tk0 + (l0 ? t : 0), t1 = tk1 + (l1 ? t : 0);
+    const float* g0 = GX + (og0 + (uint32_t)(l0 ? t : 0) * (3 * D));
+    const float* g1p = GX + (og1 + (uint32_t)(l1 ? t : 0) * (3 * D));
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      v.g1[j][0] = ld_nc_pred(GX + t0 * (3 * D) + cA + 8 * j, l0);
-      v.g1[j][1] = ld_nc_pred(GX + t1 * (3 * D) + cA + 8 * j, l1);
+      v.g1[j][0] = ld_nc_pred(g0 + 8 * j, l0);
+      v.g1[j][1] = ld_nc_pred(g1p + 8 * j, l1);
     }
     if (cand) {
+      const float* x0 = X + (ox0 + (uint32_t)(l0 ? t : 0) * D);
+      const float* x1 = X + (ox1 + (uint32_t)(l1 ? t : 0) * D);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        v.g2[j][0] = ld_nc_pred(GX + t0 * (3 * D) + 2 * D + cA + 8 * j, l0);
-        v.g2[j][1] = ld_nc_pred(GX + t1 * (3 * D) + 2 * D + cA + 8 * j, l1);
-        v.xv[j][0] = ld_nc_pred(X + t0 * D + cA + 8 * j, l0);
-        v.xv[j][1] = ld_nc_pred(X + t1 * D + cA + 8 * j, l1);
+        v.g2[j][0] = ld_nc_pred(g0 + 2 * D + 8 * j, l0);
+        v.g2[j][1] = ld_nc_pred(g1p + 2 * D + 8 * j, l1);
+        v.xv[j][0] = ld_nc_pred(x0 + 8 * j, l0);
+        v.xv[j][1] = ld_nc_pred(x1 + 8 * j, l1);
       }
-      v.dl[0] = ld_nc_pred(timelast + t0, l0);
-      v.dl[1] = ld_nc_pred(timelast + t1, l1);
+      v.dl[0] = ld_nc_pred(timelast + (ot0 + (uint32_t)(l0 ? t : 0)), l0);
+      v.dl[1] = ld_nc_pred(timelast + (ot1 + (uint32_t)(l1 ? t : 0)), l1);
     }
   };
   // D^T tile += A (hi/lo fragments) x B^T, B = src[k][row] in shared memory; three independent accumulator chains
@@ -287,6 +296,9 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_mma_kernel(const float* __restr
     fetch(t + 1, nxt);          // rows whose sequence has ended (and t + 1 == tmax) load nothing
     GRU_TRACE(1, t);
     const bool l0 = t < st0, l1 = t < st1;
+    // this step's rows of the saved-activation arrays
+    float* const ru0 = RUCT + (or0 + (uint32_t)t * (4 * D));
+    float* const ru1 = RUCT + (or1 + (uint32_t)t * (4 * D));
     // ---- phase 1: r,u ----   acc: [0] (cA, r0), [1] (cA, r0+1), [2] (cA+8, r0), [3] (cA+8, r0+1)
     float acc[4];
     product(ah, al, hT, acc);
@@ -300,13 +312,13 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_mma_kernel(const float* __restr
         const float2 h2 = *reinterpret_cast<const float2*>(&hT[col * RB + r0]);
         const float2 rh = make_float2(va * h2.x, vb * h2.y);
         *reinterpret_cast<float2*>(&rhT[col * RB + r0]) = rh;
-        if (l0) RH[(tk0 + t) * D + col] = rh.x;
-        if (l1) RH[(tk1 + t) * D + col] = rh.y;
+        if (l0) RH[ox0 + (uint32_t)t * D + 8 * j] = rh.x;
+        if (l1) RH[ox1 + (uint32_t)t * D + 8 * j] = rh.y;
       } else {
         *reinterpret_cast<float2*>(&uS[(col - D) * RB + r0]) = make_float2(va, vb);
       }
-      if (l0) RUCT[(tk0 + t) * (4 * D) + col] = va;      // r at [0,D), u at [D,2D)
-      if (l1) RUCT[(tk1 + t) * (4 * D) + col] = vb;
+      if (l0) ru0[8 * j] = va;      // r at [0,D), u at [D,2D)
+      if (l1) ru1[8 * j] = vb;
     }
     GRU_TRACE(3, t);
     __syncthreads();
@@ -333,11 +345,10 @@ __global__ void __launch_bounds__(4 * D) gru_fwd_mma_kernel(const float* __restr
           const float Tg = plain ? 1.f : sigmoid_mufu(kw2[j] * a + tw12[j] * sg + tb12[j]);
           hn[i] = live ? u[i] * hold[i] + (1.f - u[i]) * c * Tg : hold[i];
           if (live) {
-            const int64_t tok = (i ? tk1 : tk0) + t;
-            float* s4 = RUCT + tok * (4 * D) + 2 * D + col;
+            float* s4 = (i ? ru1 : ru0) + 2 * D + 8 * j;
             s4[0] = c;
             s4[D] = Tg;
-            Hs[(tok + 1) * D + col] = hn[i];      // Hs has one leading zero row
+            Hs[(i ? ox1 : ox0) + (uint32_t)(t + 1) * D + 8 * j] = hn[i];      // Hs has one leading zero row
           }
         }
         *reinterpret_cast<float2*>(&hT[col * RB + r0]) = make_float2(hn[0], hn[1]);   // only this thread's elements
@@ -573,7 +584,8 @@ static int gru_bwd_launch(const float* X, const float* timelast, const int32_t* 
 int gru_forward(int D, const float* X, const float* GX, const float* timelast, const int32_t* seq_len,
                 const float* Wgru, const float* vecs, int B, int L, float* Hs, float* RUCT, float* RH, float* q0,
                 cudaStream_t st, int plain, int tensor_cores) {
-  if (tensor_cores && (D == 64 || D == 32)) {      // h-side products on mma.sync (3xTF32); num_units 128: the FFMA kernel
+  // h-side products on mma.sync (3xTF32); num_units 128 and arrays of 2^31 elements or more: the FFMA kernel
+  if (tensor_cores && (D == 64 || D == 32) && (int64_t)gru_num_blocks(B) * RB * L * 4 * D < (1ll << 31)) {
     if (D == 64) gru_fwd_mma_kernel<64><<<gru_num_blocks(B), 256, 0, st>>>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, plain);
     else gru_fwd_mma_kernel<32><<<gru_num_blocks(B), 128, 0, st>>>(X, GX, timelast, seq_len, Wgru, vecs, B, L, Hs, RUCT, RH, q0, plain);
     MTAM_LAUNCH_CHECK();
