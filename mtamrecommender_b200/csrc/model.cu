@@ -46,6 +46,8 @@ struct Workspace {
   float *bU, *bIP, *bdot, *bbpos, *browsum, *bcolsum, *bloss, *bdU, *bdIP, *bdINp, *bdIN, *bdbneg, *bl2, *bsq;  // BPRMF
   int32_t* bneg_idx;
   int32_t* iota;     // 0..max_batch*L-1: token numbers as row ids of a caller-supplied [B*L, D] item-row array
+  unsigned* user_marks;   // one bit per user row: named by the current batch (zero between steps)
+  size_t user_marks_words;
   void *ce_ws, *gemm_ws, *colsum_ws, *gemm_ws2, *colsum_ws2, *scatter_ws, *sa_ws, *topk_ws, *sort_ws[4], *seg_ws;
   size_t ce_ws_bytes, gemm_ws_bytes, colsum_ws_bytes, scatter_ws_bytes, sa_ws_bytes, topk_ws_bytes, sort_ws_bytes[4],
       seg_ws_bytes;
@@ -75,6 +77,8 @@ struct mtam_model {
   cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
   cudaStream_t side3 = nullptr;      // parameter gradients (weight-gradient GEMMs, column sums): nothing downstream of the
   cudaEvent_t ev_pg[3] = {}, ev_join3 = nullptr;   // backward chain reads them, so they run beside it
+  cudaStream_t side4 = nullptr;      // the user table's gradient-free Adam rows, from the start of the step (optim.cu)
+  cudaEvent_t ev_fork4 = nullptr, ev_join4 = nullptr;
   cudaEvent_t ev_ce_done = nullptr;  // caller-owned: recorded once the dense item-table gradient is complete
   const float* item_rows_ext = nullptr;   // row-sharded item table: the batch's item rows, fetched by the caller
   bool rows_mode = false;                 // ... and the softmax is the caller's too (mtam_forward_rows / mtam_backward_rows)
@@ -300,6 +304,8 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
   }
   w.topk_ws_bytes = score_topk_workspace_bytes((int)B, c.item_rows, std::min(50, c.item_rows));
   w.topk_ws = b.take<char>(w.topk_ws_bytes);
+  w.user_marks_words = (size_t)(c.user_rows + 31) / 32 + 8;
+  w.user_marks = b.take<unsigned>(w.user_marks_words);
   w.total_bytes = b.off + 1024;
   if (base && !b.ok()) return set_error(MTAM_ERR_WORKSPACE, "workspace %zu bytes < required %zu", cap, w.total_bytes);
   return 0;
@@ -807,7 +813,9 @@ int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam
     return set_error(MTAM_ERR_CUDA, "cudaMallocHost failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   memset(&h->last_batch, 0, sizeof(h->last_batch));
-  if (fill_iota(h->ws.iota, (int64_t)cfg->max_batch * cfg->L, nullptr) != 0 || cudaStreamSynchronize(nullptr) != cudaSuccess) {
+  if (fill_iota(h->ws.iota, (int64_t)cfg->max_batch * cfg->L, nullptr) != 0 ||
+      cudaMemsetAsync(h->ws.user_marks, 0, h->ws.user_marks_words * sizeof(unsigned), nullptr) != cudaSuccess ||
+      cudaStreamSynchronize(nullptr) != cudaSuccess) {
     delete h;
     return set_error(MTAM_ERR_CUDA, "workspace initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
@@ -821,7 +829,10 @@ int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam
       cudaEventCreateWithFlags(&h->ev_pg[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_pg[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_pg[2], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&h->side4, cudaStreamNonBlocking, 0) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork4, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming) != cudaSuccess) {
     int e = set_error(MTAM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     mtam_destroy(h);
     return e;
@@ -843,6 +854,9 @@ int mtam_destroy(mtam_handle h) {
     for (int i = 0; i < 3; ++i)
       if (h->ev_pg[i]) cudaEventDestroy(h->ev_pg[i]);
     if (h->ev_join3) cudaEventDestroy(h->ev_join3);
+    if (h->side4) cudaStreamDestroy(h->side4);
+    if (h->ev_fork4) cudaEventDestroy(h->ev_fork4);
+    if (h->ev_join4) cudaEventDestroy(h->ev_join4);
     for (int i = 0; i <= MTAM_PHASE_COUNT; ++i)
       if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   }
@@ -1188,12 +1202,35 @@ int mtam_eval_topk(mtam_handle h, const mtam_batch* batch, int32_t k, int32_t* i
 int mtam_train_step(mtam_handle h, const mtam_batch* batch, double lr, float* scalars_out, void* stream) {
   MTAM_TRY(check_batch(h, batch));
   cudaStream_t st = (cudaStream_t)stream;
+  const mtam_config& c = h->cfg;
+  const Layout& l = h->lay;
   float* nsq = h->ws.dev_scalars + 8;
+  float* ds = h->ws.dev_scalars;
+  // The user table's rows that this batch does not name have a zero gradient: their Adam update needs lr_t only and
+  // starts now, on its own low-priority stream beside the forward and backward pass (optim.cu).  (MTAM kinds: the
+  // forward pass reads the batch's user rows only.  Not while profiling: the phase times would no longer add up.)
+  const bool early = c.optimizer == MTAM_OPT_ADAM && is_mtam_family(c.kind) && !h->prof;
+  if (early) {
+    if (!h->step_prepared) MTAM_TRY(mtam_prepare_step(h, lr, stream));      // lr_t is on the device from here on
+    MTAM_TRY(mark_rows(batch->user_id, batch->B, h->ws.user_marks, st));
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_fork4, st));
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(h->side4, h->ev_fork4, 0));
+    MTAM_TRY(adam_rows_nograd(h->params + l.user, h->m + l.user, h->v + l.user, c.user_rows, c.D, h->ws.user_marks, ds + 9,
+                              c.beta1, c.beta2, c.eps, h->side4));
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_join4, h->side4));
+  }
   MTAM_CUDA_CHECK(cudaMemsetAsync(nsq, 0, sizeof(float), st));
   MTAM_TRY(mtam_forward_backward(h, batch, batch->B, scalars_out, nsq, stream));
   MTAM_TRY(mtam_finish_grads(h, nsq, 1, stream));
-  MTAM_TRY(mtam_apply(h, lr, nsq, scalars_out, stream));
-  return 0;
+  if (!early) return mtam_apply(h, lr, nsq, scalars_out, stream);
+  MTAM_TRY(mtam_apply_begin(h, lr, nsq, scalars_out, stream));
+  MTAM_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join4, 0));
+  // the batch's user rows (sorted ids: the scatter-add's sort), then everything behind the user table
+  MTAM_TRY(adam_rows_listed(h->params + l.user, h->m + l.user, h->v + l.user, h->grads + l.user, h->sk[3], batch->B, c.D,
+                            ds + MTAM_S_CLIP_SCALE, ds + 9, c.beta1, c.beta2, c.eps, st));
+  MTAM_TRY(mtam_apply_range(h, l.cat, l.total, stream));
+  MTAM_TRY(clear_marks(batch->user_id, batch->B, h->ws.user_marks, st));
+  return mtam_apply_end(h, stream);
 }
 
 }  // extern "C"

@@ -130,6 +130,13 @@ int set_scalar(float* p, float v, cudaStream_t st);
 int set_scalar_u32(uint32_t* p, uint32_t v, cudaStream_t st);
 int fill_iota(int32_t* p, int64_t n, cudaStream_t st);
 int sgd_apply(float* w, const float* g, int64_t n, const float* scale_p, const float* lr, cudaStream_t st);
+// the user table's Adam in two parts: rows without a gradient (bitmap of the batch's rows clear) early, the batch's rows late
+int mark_rows(const int32_t* idx, int n, unsigned* marks, cudaStream_t st);
+int clear_marks(const int32_t* idx, int n, unsigned* marks, cudaStream_t st);
+int adam_rows_nograd(float* w, float* m, float* v, int64_t rows, int D, const unsigned* marks, const float* lr_t, float b1,
+                     float b2, float eps, cudaStream_t st);
+int adam_rows_listed(float* w, float* m, float* v, const float* g, const int32_t* ids_sorted, int n, int D,
+                     const float* scale_p, const float* lr_t, float b1, float b2, float eps, cudaStream_t st);
 int adam_apply(float* w, float* m, float* v, const float* g, int64_t n, const float* scale_p, const float* lr_t, float b1,
                float b2, float eps, cudaStream_t st);
 
