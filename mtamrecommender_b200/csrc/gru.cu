@@ -556,6 +556,215 @@ __global__ void __launch_bounds__(4 * D) gru_bwd_kernel(
   }
 }
 
+// The same reverse-time pass with its two matrix-vector products per step on mma.sync (3xTF32), for the tensor-core
+// arithmetic modes at num_units 32 / 64 (see gru_fwd_mma_kernel).  The element-wise work keeps the FFMA kernel's thread
+// mapping (column n = tid % D, rows 2 rg, 2 rg + 1); the products' halves travel through `part`.
+template <int D>
+__global__ void __launch_bounds__(4 * D) gru_bwd_mma_kernel(
+    const float* __restrict__ X, const float* __restrict__ timelast, const int32_t* __restrict__ seq_len,
+    const float* __restrict__ Wgru, const float* __restrict__ vecs, const float* __restrict__ Hs,
+    const float* __restrict__ RUCT, const float* __restrict__ dq0, const float* __restrict__ dOut, int B, int L,
+    float* __restrict__ dGX, float* __restrict__ dX, float* __restrict__ vec_partial) {
+  static_assert(RB == 8, "the batch rows of a CTA are the N = 8 of the MMA");
+  __shared__ __align__(16) float dpcS[D * RB];        // [m][row]: B operand of the candidate product
+  __shared__ __align__(16) float dpgS[2 * D * RB];    // [m][row]: B operand of the gate product
+  __shared__ __align__(16) float part[2][D * RB];     // [k half][n][row]: the two halves of a product's k range
+  __shared__ __align__(16) float red[4 * 8 * D];      // the final reduction of the vector-parameter gradients
+  __shared__ int steps[RB];
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * RB;
+  if (tid < RB) steps[tid] = (b0 + tid < B) ? min(max(seq_len[b0 + tid] - 1, 0), L) : 0;
+  __syncthreads();
+  int tmax = 0;
+#pragma unroll
+  for (int r = 0; r < RB; ++r) tmax = max(tmax, steps[r]);
+
+  const int n = tid % D, rg = tid / D;  // rows rg*2, rg*2+1
+  const float kw1 = vecs[0 * D + n], kb1 = vecs[1 * D + n], hw1 = vecs[2 * D + n], tw1 = vecs[3 * D + n],
+              tb1 = vecs[4 * D + n], kw2 = vecs[5 * D + n], tw12 = vecs[6 * D + n], tb12 = vecs[7 * D + n];
+  float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // kw1,kb1,hw1,tw1,tb1,kw2,tw12,tb12
+  float dh[2] = {0.f, 0.f};
+
+  // (as in the forward kernel: both rows of a thread are computed together and branch-free -- a row that has ended
+  // sees zeros everywhere, so only the stores are predicated --, the dot products run 8 independent accumulators, and
+  // the rows' step counts, base pointers and d loss / d q0 live in registers)
+  int st[2];
+  float dq[2];
+  float* dgx[2];
+  float* dxp[2];
+  int64_t tok0[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = rg * 2 + i;
+    st[i] = steps[row];
+    tok0[i] = (int64_t)(b0 + row) * L;
+    dq[i] = (b0 + row < B) ? __ldg(dq0 + (int64_t)(b0 + row) * D + n) : 0.f;
+    dgx[i] = dGX + tok0[i] * (3 * D) + n;
+    dxp[i] = dX + tok0[i] * D + n;
+  }
+  // the step's saved activations are independent of the recurrence: the loads of step t-1 are issued at the top of
+  // step t and land while its two matrix-vector loops run
+  struct StepIn { float r, u, c, Tg, hold, x, dl, dx, dout; };
+  auto fetch = [&](int t, StepIn (&v)[2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool live = t >= 0 && t < st[i];
+      const int64_t tok = tok0[i] + (live ? t : 0);
+      const float* s4 = RUCT + tok * (4 * D);
+      v[i].r = ld_nc_pred(s4 + n, live); v[i].u = ld_nc_pred(s4 + D + n, live);
+      v[i].c = ld_nc_pred(s4 + 2 * D + n, live); v[i].Tg = ld_nc_pred(s4 + 3 * D + n, live);
+      v[i].hold = ld_nc_pred(Hs + tok * D + n, live);      // h_{t-1}: Hs is shifted by one (leading zero row)
+      v[i].x = ld_nc_pred(X + tok * D + n, live);
+      v[i].dl = ld_nc_pred(timelast + tok, live);
+      v[i].dx = ld_cg_pred(dX + tok * D + n, live);         // dX[t] is updated in place: read it a step ahead too
+      // d loss / d output[t] when the whole output sequence is consumed (MTAM_via_T_GRU: it is the hops' memory)
+      v[i].dout = dOut ? ld_nc_pred(dOut + tok * D + n, live) : 0.f;
+    }
+  };
+  // Both products of a step are  out[n][row] = sum_m A[n][m] * src[m][row]  with constant A: the candidate path
+  // A[n][m] = W_gru[D+n][2D+m] (m < D) and the gate path A[n][m] = W_gru[D+n][m] (m < 2D).  M = D output columns = D/16
+  // tiles; a tile is shared by the warp PAIR (w, w + D/16), each taking half of the k-steps, so that all warps work and the
+  // fragments (3xTF32 hi / lo) of both products fit the register file: (D/16 + D/8) k-steps x 8 registers.
+  constexpr int NTILE = D / 16, KC = D / 16, KG = D / 8;       // k-steps per warp: candidate product, gate product
+  const int warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const int tile = warp % NTILE, khalf = warp / NTILE;
+  const float* Wh = Wgru + (int64_t)D * 3 * D;                 // W_gru[D + n][.]
+  uint32_t fch[KC][4], fcl[KC][4], fgh[KG][4], fgl[KG][4];
+#pragma unroll
+  for (int ks = 0; ks < KC; ++ks)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = 16 * tile + gid + (j & 1) * 8, m = (khalf * KC + ks) * 8 + tig + (j >> 1) * 4;
+      const float x = __ldg(Wh + (int64_t)nn * 3 * D + 2 * D + m);
+      fch[ks][j] = tf32_top(x);
+      fcl[ks][j] = __float_as_uint(x - __uint_as_float(fch[ks][j]));
+    }
+#pragma unroll
+  for (int ks = 0; ks < KG; ++ks)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = 16 * tile + gid + (j & 1) * 8, m = (khalf * KG + ks) * 8 + tig + (j >> 1) * 4;
+      const float x = __ldg(Wh + (int64_t)nn * 3 * D + m);
+      fgh[ks][j] = tf32_top(x);
+      fgl[ks][j] = __float_as_uint(x - __uint_as_float(fgh[ks][j]));
+    }
+  // this warp's half of a product -> part[khalf][n][row]  (C fragment: n = 16 tile + gid (+8), rows 2 tig, 2 tig + 1)
+  auto store_part = [&](const float (&o)[4]) {
+    float* pp = part[khalf] + (16 * tile + gid) * RB + 2 * tig;
+    *reinterpret_cast<float2*>(pp) = make_float2(o[0], o[1]);
+    *reinterpret_cast<float2*>(pp + 8 * RB) = make_float2(o[2], o[3]);
+  };
+  StepIn cur[2], nxt[2];
+  fetch(tmax - 1, cur);
+  for (int t = tmax - 1; t >= 0; --t) {
+    float dhacc[2], rr[2], hh[2], dpc[2], dupre[2];
+    fetch(t - 1, nxt);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool live = t < st[i];
+      const float r = cur[i].r, u = cur[i].u, c = cur[i].c, Tg = cur[i].Tg, hold = cur[i].hold, x = cur[i].x,
+                  dl = cur[i].dl;
+      // a row that has not started yet (t >= its step count): dh is still 0 and every saved value was loaded as 0
+      const float d = dh[i] + ((t == st[i] - 1) ? dq[i] : 0.f) + cur[i].dout;
+      const float du = d * (hold - c * Tg), dc = d * (1.f - u) * Tg, dT = d * (1.f - u) * c;
+      dhacc[i] = d * u;
+      dpc[i] = dc * (1.f - c * c);
+      const float dpT = dT * Tg * (1.f - Tg);
+      const float apre = fmaf(x, kw1, kb1) + hold * hw1, spre = fmaf(tw1, dl, tb1);
+      const float a = fmaxf(apre, 0.f), s = fmaxf(spre, 0.f);
+      const float dpa = (apre > 0.f) ? dpT * kw2 : 0.f;
+      const float dps = (spre > 0.f) ? dpT * tw12 : 0.f;
+      dhacc[i] = fmaf(dpa, hw1, dhacc[i]);
+      g[0] = fmaf(dpa, x, g[0]); g[1] += dpa; g[2] = fmaf(dpa, hold, g[2]);
+      g[3] = fmaf(dps, dl, g[3]); g[4] += dps;
+      g[5] = fmaf(dpT, a, g[5]); g[6] = fmaf(dpT, s, g[6]); g[7] += dpT;
+      dupre[i] = du * u * (1.f - u);
+      rr[i] = r; hh[i] = hold;
+      if (live) {
+        dgx[i][t * (3 * D) + 2 * D] = dpc[i];
+        dxp[i][t * D] = fmaf(dpa, kw1, cur[i].dx);   // each element is read (a step earlier) and written exactly once
+        dgx[i][t * (3 * D) + D] = dupre[i];
+      }
+    }
+    *reinterpret_cast<float2*>(&dpcS[n * RB + rg * 2]) = make_float2(dpc[0], dpc[1]);
+    *reinterpret_cast<float2*>(&dpgS[(D + n) * RB + rg * 2]) = make_float2(dupre[0], dupre[1]);
+    __syncthreads();
+    // d(r*h)[n] = sum_m dpc[m] * Wc_h[n][m]: each warp its half of the k range, then the halves meet in shared memory
+    {
+      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+#pragma unroll
+      for (int ks = 0; ks < KC; ++ks) {
+        const int kk = (khalf * KC + ks) * 8 + tig;
+        const float x0 = dpcS[kk * RB + gid], x1 = dpcS[(kk + 4) * RB + gid];
+        const uint32_t h0 = tf32_top(x0), h1 = tf32_top(x1);
+        const uint32_t l0 = __float_as_uint(x0 - __uint_as_float(h0)), l1 = __float_as_uint(x1 - __uint_as_float(h1));
+        mma_tf32_16x8x8(d0, fcl[ks], h0, h1);
+        mma_tf32_16x8x8(d1, fch[ks], l0, l1);
+        mma_tf32_16x8x8(d2, fch[ks], h0, h1);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = (d0[i] + d1[i]) + d2[i];
+      store_part(o);
+    }
+    __syncthreads();
+    const float2 pb0 = *reinterpret_cast<const float2*>(&part[0][n * RB + rg * 2]);
+    const float2 pb1 = *reinterpret_cast<const float2*>(&part[1][n * RB + rg * 2]);
+    const float acc_b[2] = {pb0.x + pb1.x, pb0.y + pb1.y};
+    {
+      float drpre[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float drh = acc_b[i];
+        dhacc[i] = fmaf(drh, rr[i], dhacc[i]);
+        drpre[i] = drh * hh[i] * rr[i] * (1.f - rr[i]);          // 0 for a row that has not started (r = h = 0)
+        if (t < st[i]) dgx[i][t * (3 * D)] = drpre[i];
+      }
+      *reinterpret_cast<float2*>(&dpgS[n * RB + rg * 2]) = make_float2(drpre[0], drpre[1]);
+    }
+    __syncthreads();
+    // dh_prev[n] += sum_m dpg[m] * Wg_h[n][m],  m over 2D
+    {
+      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+#pragma unroll
+      for (int ks = 0; ks < KG; ++ks) {
+        const int kk = (khalf * KG + ks) * 8 + tig;
+        const float x0 = dpgS[kk * RB + gid], x1 = dpgS[(kk + 4) * RB + gid];
+        const uint32_t h0 = tf32_top(x0), h1 = tf32_top(x1);
+        const uint32_t l0 = __float_as_uint(x0 - __uint_as_float(h0)), l1 = __float_as_uint(x1 - __uint_as_float(h1));
+        mma_tf32_16x8x8(d0, fgl[ks], h0, h1);
+        mma_tf32_16x8x8(d1, fgh[ks], l0, l1);
+        mma_tf32_16x8x8(d2, fgh[ks], h0, h1);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = (d0[i] + d1[i]) + d2[i];
+      store_part(o);       // (the candidate product's halves were read before the barrier above)
+    }
+    __syncthreads();
+    const float2 pc0 = *reinterpret_cast<const float2*>(&part[0][n * RB + rg * 2]);
+    const float2 pc1 = *reinterpret_cast<const float2*>(&part[1][n * RB + rg * 2]);
+    const float acc_c[2] = {pc0.x + pc1.x, pc0.y + pc1.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (t < st[i]) dh[i] = dhacc[i] + acc_c[i];
+      cur[i] = nxt[i];
+    }
+    __syncthreads();
+  }
+  // per-CTA reduction of the vector-parameter gradients over the 4 row groups (fixed order)
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[(rg * 8 + j) * D + n] = g[j];
+  __syncthreads();
+  if (rg == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = red[(0 * 8 + j) * D + n] + red[(1 * 8 + j) * D + n] + red[(2 * 8 + j) * D + n] +
+                red[(3 * 8 + j) * D + n];
+      vec_partial[((int64_t)blockIdx.x * 8 + j) * D + n] = s;
+    }
+  }
+}
+
 static size_t gru_smem_bytes(int D) { return (size_t)(3 * D * D + 3 * D * RB) * sizeof(float); }
 int gru_num_blocks(int B) { return cdiv(B, RB); }
 
@@ -600,7 +809,13 @@ int gru_forward(int D, const float* X, const float* GX, const float* timelast, c
 }
 int gru_backward(int D, const float* X, const float* timelast, const int32_t* seq_len, const float* Wgru,
                  const float* vecs, const float* Hs, const float* RUCT, const float* dq0, const float* dOut, int B, int L, float* dGX,
-                 float* dX, float* vec_partial, cudaStream_t st) {
+                 float* dX, float* vec_partial, cudaStream_t st, int tensor_cores) {
+  if (tensor_cores && (D == 64 || D == 32)) {
+    if (D == 64) gru_bwd_mma_kernel<64><<<gru_num_blocks(B), 256, 0, st>>>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, dOut, B, L, dGX, dX, vec_partial);
+    else gru_bwd_mma_kernel<32><<<gru_num_blocks(B), 128, 0, st>>>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, dOut, B, L, dGX, dX, vec_partial);
+    MTAM_LAUNCH_CHECK();
+    return 0;
+  }
   switch (D) {
     case 32: return gru_bwd_launch<32>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, dOut, B, L, dGX, dX, vec_partial, st);
     case 64: return gru_bwd_launch<64>(X, timelast, seq_len, Wgru, vecs, Hs, RUCT, dq0, dOut, B, L, dGX, dX, vec_partial, st);

@@ -588,7 +588,7 @@ static int mtam_bwd(mtam_model* h, const mtam_batch* bt, int global_batch, float
   phase(h, MTAM_PH_GRU_BWD, st);
   MTAM_CUDA_CHECK(cudaMemsetAsync(w.dGX, 0, (size_t)T * 3 * D * sizeof(float), st));
   MTAM_TRY(gru_backward(D, w.X, bt->timelast_list, bt->seq_length, P + l.Wgru, P + l.gruvec, w.Hs, w.RUCT, dq0,
-                        via ? dMem : nullptr, B, L, w.dGX, w.dX, w.vec_partial, st));
+                        via ? dMem : nullptr, B, L, w.dGX, w.dX, w.vec_partial, st, gemm_mode_is_tc(c.gemm_mode) ? 1 : 0));
   phase(h, MTAM_PH_GRU_PARAM_GRADS, st);
   MTAM_TRY(pg_after_main(1));
   MTAM_TRY(colsum2(h, w.vec_partial, 8 * D, nullptr, 0, gru_num_blocks(B), 8 * D, G + l.gruvec, pg));

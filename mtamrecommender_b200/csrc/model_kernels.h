@@ -27,7 +27,7 @@ int gru_forward(int D, const float* X, const float* GX, const float* timelast, c
                 cudaStream_t st, int plain = 0, int tensor_cores = 0);
 int gru_backward(int D, const float* X, const float* timelast, const int32_t* seq_len, const float* Wgru,
                  const float* vecs, const float* Hs, const float* RUCT, const float* dq0, const float* dOut, int B, int L,
-                 float* dGX, float* dX, float* vec_partial, cudaStream_t st);
+                 float* dGX, float* dX, float* vec_partial, cudaStream_t st, int tensor_cores = 0);
 
 // ---- hops.cu --------------------------------------------------------------------------------
 struct HopArgs {
