@@ -204,3 +204,43 @@ def test_tensor_core_mode_parity(case):
     for k, v in tr.params.items():
         ok, r, tol = grad_close(_test_name(), k, newp[k], v, tr32.params[k])
         assert ok, (k, r, tol)
+
+
+@pytest.mark.parametrize("gemm_mode", [0, 1])
+def test_train_steps_are_bit_reproducible_and_the_split_adam_matches_the_whole(gemm_mode):
+    """(1) Two engines from the same weights give the same bits after three train steps -- eager and from the captured
+    graph -- in both arithmetic modes (the tensor-core mode runs the mma.sync T-GRU kernels, whose warp pairs meet in
+    shared memory, and the user table's Adam in two parts on two streams: a race would show here).  (2) The two-part
+    Adam of mtam_train_step (rows without a gradient early, the batch's rows late) against the one-kernel update of
+    forward_backward + finish_grads + apply: the same bits in every arena."""
+    import torch
+    from mtamrecommender_b200 import _lib, engine as E
+    import ctypes as C
+    case = dict(D=64, L=12, N=2, H=1, B=37, items=500, users=300, cats=11)
+    cfg, P, feed, e1 = make(**case, gemm_mode=gemm_mode)
+    _, _, _, e2 = make(**case, gemm_mode=gemm_mode)
+    _, _, _, e3 = make(**case, gemm_mode=gemm_mode)
+    _, _, _, e4 = make(**case, gemm_mode=gemm_mode)
+    feed2 = O.synth_batch(cfg, 37, 99)
+    for f, lr in ((feed, 1e-3), (feed2, 2e-3), (feed, 5e-4)):
+        l1, l2 = e1.train_step(f, lr), e2.train_step(f, lr)
+        assert l1 == l2
+    for a in ("params", "adam_m", "adam_v"):
+        assert bool((getattr(e1, a) == getattr(e2, a)).all()), a
+    e3.capture_train_graph(37)
+    for f, lr in ((feed, 1e-3), (feed2, 2e-3), (feed, 5e-4)):
+        e3.train_step(f, lr)
+    assert bool((e1.params == e3.params).all()) and bool((e1.adam_v == e3.adam_v).all())
+    # the one-kernel update, driven through the split C entry points (what the data-parallel driver calls)
+    lib = e4.lib
+    nsq = torch.zeros(1, device="cuda")
+    for f, lr in ((feed, 1e-3), (feed2, 2e-3), (feed, 5e-4)):
+        b = e4.upload(f)
+        nsq.zero_()
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.mtam_forward_backward(e4.h, C.byref(b.c), b.B, e4.scalars.data_ptr(), nsq.data_ptr(), st), "fb")
+        _lib.check(lib.mtam_finish_grads(e4.h, nsq.data_ptr(), 1, st), "finish")
+        _lib.check(lib.mtam_apply(e4.h, float(lr), nsq.data_ptr(), e4.scalars.data_ptr(), st), "apply")
+    torch.cuda.synchronize()
+    for a in ("params", "adam_m", "adam_v"):
+        assert bool((getattr(e1, a) == getattr(e4, a)).all()), a
