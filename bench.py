@@ -402,7 +402,12 @@ def _run_cuda(args, w):
             return {"kernel": name, "bound": kind, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                     "traffic": traffic.get(name), "traffic_source": "profiles/traffic_r02.json (ncu --set full capture of this step)",
                     "peak_source": pk["src"] + (" bf16 sustained" if kind == "tensor" else " copy"),
-                    "ms": ms, "share_of_step": ms / tot}
+                    "ms": ms, "share_of_step": ms / tot,
+                    **({"note": "the whole Adam update as ONE adam_kernel launch, as the profiling step (and the data-"
+                                "parallel driver) runs it; in the timed, graphed step of the MTAM kinds the same update "
+                                "is three launches: adam_rows_nograd_kernel (user rows the batch does not name, started "
+                                "at the top of the step on a side stream), adam_rows_listed_kernel, adam_kernel (the rest)"}
+                       if name == "adam" else {})}
         roof, roofs = None, []
         if phases:
             ranked = sorted((k for k in phases if k in work), key=lambda k: -phases[k])

@@ -12,8 +12,8 @@ python bench.py --impl reference > $out/bench_ref_$tag.json 2> $out/bench_ref_$t
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/launches_$tag.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-graph --no-cfg4 > $out/ncu_list_$tag.log 2>&1
 # (the .ncu-rep files stay on the box: gpurun_out/ may carry 64 MiB back, so only the raw-page CSV exports travel)
-ncu --set full --clock-control none -k regex:"adam_kernel|ce_tc_kernel|gru_|hop_|tc_gemm_ws|embed_gather" \
-    -s 60 -c 36 -o /tmp/step_$tag -f python bench.py --steps 2 --warmup 3 --no-cpu --no-graph --no-cfg4 > $out/ncu_full_$tag.log 2>&1
+ncu --set full --clock-control none -k regex:"adam_|ce_tc_kernel|gru_|hop_|tc_gemm_ws|embed_gather" \
+    -s 60 -c 40 -o /tmp/step_$tag -f python bench.py --steps 2 --warmup 3 --no-cpu --no-graph --no-cfg4 > $out/ncu_full_$tag.log 2>&1
 ncu -i /tmp/step_$tag.ncu-rep --page raw --csv > $out/step_${tag}_ncu_full_raw.csv 2>/dev/null
 ncu --set full --clock-control none -k regex:"gather_rows|os_hist|os_pass|seg_reduce" -c 8 \
     -o /tmp/bw_$tag -f python tools/prof_scatter.py > $out/ncu_bw_$tag.log 2>&1
