@@ -49,6 +49,7 @@ struct Workspace {
   unsigned* user_marks;   // one bit per user row: named by the current batch (zero between steps)
   size_t user_marks_words;
   void *ce_ws, *gemm_ws, *colsum_ws, *gemm_ws2, *colsum_ws2, *scatter_ws, *sa_ws, *topk_ws, *sort_ws[4], *seg_ws;
+  void* seg_ws_side[3];   // the category / position / user reductions run beside the item table's, each with its own scratch
   size_t ce_ws_bytes, gemm_ws_bytes, colsum_ws_bytes, scatter_ws_bytes, sa_ws_bytes, topk_ws_bytes, sort_ws_bytes[4],
       seg_ws_bytes;
   size_t total_bytes;
@@ -79,6 +80,7 @@ struct mtam_model {
   cudaEvent_t ev_pg[3] = {}, ev_join3 = nullptr;   // backward chain reads them, so they run beside it
   cudaStream_t side4 = nullptr;      // the user table's gradient-free Adam rows, from the start of the step (optim.cu)
   cudaEvent_t ev_fork4 = nullptr, ev_join4 = nullptr;
+  cudaEvent_t ev_sc_fork = nullptr, ev_sc[3] = {};   // the four segmented reductions of a step, side by side
   cudaEvent_t ev_ce_done = nullptr;  // caller-owned: recorded once the dense item-table gradient is complete
   const float* item_rows_ext = nullptr;   // row-sharded item table: the batch's item rows, fetched by the caller
   bool rows_mode = false;                 // ... and the softmax is the caller's too (mtam_forward_rows / mtam_backward_rows)
@@ -301,6 +303,7 @@ static int plan_workspace(const mtam_config& c, void* base, size_t cap, Workspac
     }
     w.seg_ws_bytes = seg_reduce_workspace_bytes(T, (int)D);
     w.seg_ws = b.take<char>(w.seg_ws_bytes);
+    for (int k = 0; k < 3; ++k) w.seg_ws_side[k] = b.take<char>(w.seg_ws_bytes);
   }
   w.topk_ws_bytes = score_topk_workspace_bytes((int)B, c.item_rows, std::min(50, c.item_rows));
   w.topk_ws = b.take<char>(w.topk_ws_bytes);
@@ -832,7 +835,11 @@ int mtam_create(const mtam_config* cfg, float* params, float* grads, float* adam
       cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithPriority(&h->side4, cudaStreamNonBlocking, 0) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork4, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_sc_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_sc[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_sc[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_sc[2], cudaEventDisableTiming) != cudaSuccess) {
     int e = set_error(MTAM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     mtam_destroy(h);
     return e;
@@ -857,6 +864,9 @@ int mtam_destroy(mtam_handle h) {
     if (h->side4) cudaStreamDestroy(h->side4);
     if (h->ev_fork4) cudaEventDestroy(h->ev_fork4);
     if (h->ev_join4) cudaEventDestroy(h->ev_join4);
+    if (h->ev_sc_fork) cudaEventDestroy(h->ev_sc_fork);
+    for (int i = 0; i < 3; ++i)
+      if (h->ev_sc[i]) cudaEventDestroy(h->ev_sc[i]);
     for (int i = 0; i <= MTAM_PHASE_COUNT; ++i)
       if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   }
@@ -1100,11 +1110,32 @@ int mtam_finish_grads(mtam_handle h, float* norm_sq, int32_t scatter_local, void
   if (!scatter_local) return 0;
   if (c.kind == MTAM_KIND_BPRMF) return bpr_scatter(h, st);
   float* G = h->grads;
+  // Four independent reductions into four tables.  At a few ten thousand rows each is a single partial wave of CTAs (one per
+  // SM: 192 KB of shared memory), so they run side by side on the side streams -- all idle here: their work of this step
+  // was joined before the norm -- instead of one after the other.  (Not while profiling: the phase is timed on `st`.)
+  cudaStream_t s1 = st, s2 = st, s3 = st;
+  const bool aside = !h->prof;
+  if (aside) {
+    s1 = h->side; s2 = h->side2; s3 = h->side3;
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_sc_fork, st));
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(s1, h->ev_sc_fork, 0));
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(s2, h->ev_sc_fork, 0));
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(s3, h->ev_sc_fork, 0));
+  }
   MTAM_TRY(seg_reduce_sorted(h->sk[0], h->sp[0], w.dE2, 2 * D, T, D, G + l.item, D, w.seg_ws, w.seg_ws_bytes, st));
-  MTAM_TRY(seg_reduce_sorted(h->sk[1], h->sp[1], w.dE2 + D, 2 * D, T, D, G + l.cat, D, w.seg_ws, w.seg_ws_bytes, st));
-  MTAM_TRY(seg_reduce_sorted(h->sk[2], h->sp[2], w.dEp, D, T, D, G + l.pos, D, w.seg_ws, w.seg_ws_bytes, st));
+  MTAM_TRY(seg_reduce_sorted(h->sk[1], h->sp[1], w.dE2 + D, 2 * D, T, D, G + l.cat, D, aside ? w.seg_ws_side[0] : w.seg_ws,
+                             w.seg_ws_bytes, s1));
+  MTAM_TRY(seg_reduce_sorted(h->sk[2], h->sp[2], w.dEp, D, T, D, G + l.pos, D, aside ? w.seg_ws_side[1] : w.seg_ws,
+                             w.seg_ws_bytes, s2));
   if (c.kind != MTAM_KIND_PISTREC)
-    MTAM_TRY(seg_reduce_sorted(h->sk[3], h->sp[3], w.dEu, D, B, D, G + l.user, D, w.seg_ws, w.seg_ws_bytes, st));
+    MTAM_TRY(seg_reduce_sorted(h->sk[3], h->sp[3], w.dEu, D, B, D, G + l.user, D, aside ? w.seg_ws_side[2] : w.seg_ws,
+                               w.seg_ws_bytes, s3));
+  if (aside) {
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_sc[0], s1));
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_sc[1], s2));
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_sc[2], s3));
+    for (int i = 0; i < 3; ++i) MTAM_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_sc[i], 0));
+  }
   (void)bt;
   return 0;
 }
