@@ -1160,12 +1160,21 @@ int mtam_scatter_sparse_into(mtam_handle h, float* item_dst, float* category_dst
     MTAM_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join, 0));
     h->sort_pending = false;
   }
+  // side by side on the library's side streams (idle here: joined at the end of the backward pass), as in mtam_finish_grads
+  cudaStream_t ss[3] = {h->side, h->side2, h->side3};
+  MTAM_CUDA_CHECK(cudaEventRecord(h->ev_sc_fork, st));
+  for (int i = 0; i < 3; ++i) MTAM_CUDA_CHECK(cudaStreamWaitEvent(ss[i], h->ev_sc_fork, 0));
   if (item_dst) MTAM_TRY(seg_reduce_sorted(h->sk[0], h->sp[0], w.dE2, 2 * D, T, D, item_dst, D, w.seg_ws, w.seg_ws_bytes, st));
   if (category_dst)
-    MTAM_TRY(seg_reduce_sorted(h->sk[1], h->sp[1], w.dE2 + D, 2 * D, T, D, category_dst, D, w.seg_ws, w.seg_ws_bytes, st));
-  if (position_dst) MTAM_TRY(seg_reduce_sorted(h->sk[2], h->sp[2], w.dEp, D, T, D, position_dst, D, w.seg_ws, w.seg_ws_bytes, st));
+    MTAM_TRY(seg_reduce_sorted(h->sk[1], h->sp[1], w.dE2 + D, 2 * D, T, D, category_dst, D, w.seg_ws_side[0], w.seg_ws_bytes, ss[0]));
+  if (position_dst)
+    MTAM_TRY(seg_reduce_sorted(h->sk[2], h->sp[2], w.dEp, D, T, D, position_dst, D, w.seg_ws_side[1], w.seg_ws_bytes, ss[1]));
   if (user_dst && c.kind != MTAM_KIND_PISTREC)
-    MTAM_TRY(seg_reduce_sorted(h->sk[3], h->sp[3], w.dEu, D, B, D, user_dst, D, w.seg_ws, w.seg_ws_bytes, st));
+    MTAM_TRY(seg_reduce_sorted(h->sk[3], h->sp[3], w.dEu, D, B, D, user_dst, D, w.seg_ws_side[2], w.seg_ws_bytes, ss[2]));
+  for (int i = 0; i < 3; ++i) {
+    MTAM_CUDA_CHECK(cudaEventRecord(h->ev_sc[i], ss[i]));
+    MTAM_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_sc[i], 0));
+  }
   return 0;
 }
 
