@@ -244,3 +244,42 @@ def test_train_steps_are_bit_reproducible_and_the_split_adam_matches_the_whole(g
     torch.cuda.synchronize()
     for a in ("params", "adam_m", "adam_v"):
         assert bool((getattr(e1, a) == getattr(e4, a)).all()), a
+
+
+@pytest.mark.parametrize("gemm_mode", [0, 1])
+def test_cfg4_sequence_length_against_the_oracle(gemm_mode):
+    """BASELINE configs[3] / [4] run at L = 200 with 6 hops: the model at that sequence length (the hop kernels' shared-
+    memory layout at 200 keys, 199 recurrent steps, position table of 203 rows) against the oracle -- forward, every
+    gradient, two Adam steps -- in both arithmetic modes; full and minimal lengths included.  (The 10 M-row tables of
+    those configs are covered by the property tests of test_full_size_gpu.py.)"""
+    import torch
+    cfg, P, feed, eng = make(D=64, L=200, N=6, H=1, B=24, items=5000, users=100, cats=37, seed=11, gemm_mode=gemm_mode)
+    full = O.synth_batch(cfg, 1, 5, min_len=200)          # a full-length sequence and a minimal one
+    assert int(full["seq_length"][0]) == 200
+    for k in feed:
+        feed[k][0] = full[k][0]
+    feed["seq_length"][1] = 2
+    for k in ("item_list", "category_list", "position_list", "time_list", "timelast_list", "timenow_list"):
+        feed[k][1, 2:] = 0
+    feed["item_list"][1, 1] = cfg.item_count + 1
+    feed["category_list"][1, 1] = cfg.category_count + 1
+    feed["position_list"][1, 1] = 1
+    fwd, grads, pieces = O.loss_and_grads(cfg, P, feed)
+    _, g32, _ = O.loss_and_grads(cfg, P, feed, torch.float32)
+    out = eng.forward(feed)
+    lo = float(fwd["loss"].detach())
+    assert abs(out["loss"] - lo) <= 1e-5 * abs(lo)
+    assert rel(out["pred"], fwd["pred"].detach().numpy()) < 1e-5
+    g = eng.gradients(feed)
+    gn = O.global_norm(pieces)
+    assert abs(np.sqrt(g["__norm_sq__"]) - gn) <= 1e-5 * gn
+    for k, v in grads.items():
+        if v is None:
+            assert not np.any(g[k]), k
+        else:
+            ok, r, tol = grad_close(_test_name(), k, g[k], v, g32[k])
+            assert ok, (k, r, tol)
+    tr = O.OracleTrainer(cfg, P)
+    for s in range(2):
+        a, b = tr.train_step(feed, 1e-3), eng.train_step(feed, 1e-3)
+        assert abs(a - b) <= 2e-5 * abs(a), (s, a, b)
