@@ -131,6 +131,36 @@ int finalize_sum(const float* partial, int n, float scale, float* out, int accum
   return 0;
 }
 
+// The step's three loss scalars in one launch (they were four finalize_sum launches in a row on the step's critical
+// path): l2 = 0.5 * sum(l2_partial), origin = sum(ce_partial) / global batch, loss = reg * l2 + origin
+// (base_model.py:302-323).  Same summation order and the same roundings as the separate launches.
+__global__ void __launch_bounds__(64) loss_scalars_kernel(const float* __restrict__ l2_partial, int n_l2,
+                                                          const float* __restrict__ ce_partial, int n_ce, float inv_batch,
+                                                          float reg, float* __restrict__ l2_out, float* __restrict__ origin_out,
+                                                          float* __restrict__ loss_out) {
+  __shared__ float s_sum[2];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* p = w ? ce_partial : l2_partial;
+  const int n = w ? n_ce : n_l2;
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) s += p[i];
+  s = warp_sum(s);
+  if (lane == 0) s_sum[w] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float l2 = __fmul_rn(s_sum[0], 0.5f), origin = __fmul_rn(s_sum[1], inv_batch);
+    l2_out[0] = l2;
+    origin_out[0] = origin;
+    loss_out[0] = __fadd_rn(__fmul_rn(l2, reg), origin);
+  }
+}
+int loss_scalars_sum(const float* l2_partial, int n_l2, const float* ce_partial, int n_ce, float inv_batch, float reg,
+                     float* l2_out, float* origin_out, float* loss_out, cudaStream_t st) {
+  loss_scalars_kernel<<<1, 64, 0, st>>>(l2_partial, n_l2, ce_partial, n_ce, inv_batch, reg, l2_out, origin_out, loss_out);
+  MTAM_LAUNCH_CHECK();
+  return 0;
+}
+
 // X[t,:] = R[t,:] + Tp[pos[t],:]   (Behavior_...py:102)
 __global__ void __launch_bounds__(256) add_pos_kernel(const float4* __restrict__ R, const float4* __restrict__ Tp,
                                                       const int32_t* __restrict__ pos, int64_t total, int vpr,

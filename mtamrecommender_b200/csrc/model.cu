@@ -398,10 +398,8 @@ static int embed_forward(mtam_model* h, const mtam_batch* bt, int include_user, 
 static int loss_scalars(mtam_model* h, int n_l2, int n_ce, int global_batch, float* scalars_out, cudaStream_t st) {
   Workspace& w = h->ws;
   float* ds = w.dev_scalars;
-  MTAM_TRY(finalize_sum(w.l2_partial, n_l2, 0.5f, ds + MTAM_S_L2_NORM, 0, st));
-  MTAM_TRY(finalize_sum(w.ce_partial, n_ce, 1.0f / (float)global_batch, ds + MTAM_S_LOSS_ORIGIN, 0, st));
-  MTAM_TRY(finalize_sum(ds + MTAM_S_L2_NORM, 1, h->cfg.reg, ds + MTAM_S_LOSS, 0, st));
-  MTAM_TRY(finalize_sum(ds + MTAM_S_LOSS_ORIGIN, 1, 1.0f, ds + MTAM_S_LOSS, 1, st));
+  MTAM_TRY(loss_scalars_sum(w.l2_partial, n_l2, w.ce_partial, n_ce, 1.0f / (float)global_batch, h->cfg.reg,
+                            ds + MTAM_S_L2_NORM, ds + MTAM_S_LOSS_ORIGIN, ds + MTAM_S_LOSS, st));
   if (scalars_out)
     MTAM_CUDA_CHECK(cudaMemcpyAsync(scalars_out, ds, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;

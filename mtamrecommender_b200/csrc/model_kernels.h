@@ -16,6 +16,8 @@ int embed_bwd_tail(const float* E2, const float* dX, const float* Tp, const floa
                    const int32_t* user, int B, int L, int D, float reg, int include_user, float* dE2, float* dEp,
                    float* dEu, float* partial, int* n_partial, cudaStream_t st);
 int finalize_sum(const float* partial, int n, float scale, float* out, int accumulate, cudaStream_t st);
+int loss_scalars_sum(const float* l2_partial, int n_l2, const float* ce_partial, int n_ce, float inv_batch, float reg,
+                     float* l2_out, float* origin_out, float* loss_out, cudaStream_t st);
 int add_pos(const float* R, const float* Tp, const int32_t* pos, int64_t T, int D, float* X, cudaStream_t st);
 int relu_mask(const float* x, const float* mask, int64_t n, float* out, cudaStream_t st);
 int zero_rows(float* dst, const int32_t* idx, int64_t n, int D, cudaStream_t st);
